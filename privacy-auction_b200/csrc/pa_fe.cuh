@@ -1,0 +1,337 @@
+// secp256k1 base-field arithmetic: p = 2^256 - 2^32 - 977  (OpenSSL NID 714,
+// reference SEAL/params.h:4).  One field element per thread, 8 x 32-bit limbs in
+// registers, little-endian limb order.
+//
+// This replaces what libcrypto's BN_mod_mul_montgomery / ec_GFp_mont_field_mul
+// do underneath every EC_POINT_* call of the reference.
+// Instead of Montgomery form the special shape of p is used:
+// 2^256 = C (mod p), C = 2^32 + 977, so a 512-bit product folds to 256 bits
+// with 8 extra multiply-accumulates (vs 72 for a CIOS Montgomery reduction).
+//
+// Values are kept WEAKLY reduced: any representative in [0, 2^256).  fe_canon /
+// fe_is_zero / fe_eq give canonical answers.
+#pragma once
+#include "pa_ptx.cuh"
+
+struct fe {
+  u32 v[8];
+};
+
+#define PA_P0 0xFFFFFC2Fu
+#define PA_P1 0xFFFFFFFEu
+#define PA_C0 977u  // C = 2^32 + 977
+
+PA_HD void fe_set_zero(fe &r) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = 0;
+}
+PA_HD void fe_set_one(fe &r) {
+  fe_set_zero(r);
+  r.v[0] = 1;
+}
+
+// r = a + b  (weak)
+PA_HD void fe_add(fe &r, const fe &a, const fe &b) {
+  u32 t[8];
+  t[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t[i] = addc_cc(a.v[i], b.v[i]);
+  u32 m = 0u - addc(0, 0);  // all-ones if the sum passed 2^256: fold 2^256 -> C
+  t[0] = add_cc(t[0], PA_C0 & m);
+  t[1] = addc_cc(t[1], 1u & m);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) t[i] = addc_cc(t[i], 0);
+  m = 0u - addc(0, 0);  // only when both inputs were >= p; remainder < C then
+  t[0] = add_cc(t[0], PA_C0 & m);
+  t[1] = addc(t[1], 1u & m);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = t[i];
+}
+
+// r = a - b  (weak)
+PA_HD void fe_sub(fe &r, const fe &a, const fe &b) {
+  u32 t[8];
+  t[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t[i] = subc_cc(a.v[i], b.v[i]);
+  u32 m = 0u - subc(0, 0) /* subc(0,0) = 0 - borrow */;
+  m = 0u - (m & 1u);  // all-ones if it borrowed: wrapped by 2^256 -> subtract C
+  t[0] = sub_cc(t[0], PA_C0 & m);
+  t[1] = subc_cc(t[1], 1u & m);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) t[i] = subc_cc(t[i], 0);
+  m = 0u - subc(0, 0);
+  m = 0u - (m & 1u);  // only when b was > p + a
+  t[0] = sub_cc(t[0], PA_C0 & m);
+  t[1] = subc_cc(t[1], 1u & m);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) t[i] = subc_cc(t[i], 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = t[i];
+}
+
+PA_HD void fe_neg(fe &r, const fe &a) {
+  fe z;
+  fe_set_zero(z);
+  fe_sub(r, z, a);
+}
+PA_HD void fe_dbl(fe &r, const fe &a) { fe_add(r, a, a); }
+
+// canonical representative in [0, p)
+PA_HD void fe_canon(fe &r, const fe &a) {
+  u32 t[8];
+  t[0] = add_cc(a.v[0], PA_C0);
+  t[1] = addc_cc(a.v[1], 1u);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) t[i] = addc_cc(a.v[i], 0);
+  u32 ge = addc(0, 0);  // a + C >= 2^256  <=>  a >= p
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = ge ? t[i] : a.v[i];
+}
+
+PA_HD bool fe_is_zero(const fe &a) {
+  u32 z = a.v[0] | a.v[1], q = (a.v[0] ^ PA_P0) | (a.v[1] ^ PA_P1);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) {
+    z |= a.v[i];
+    q |= ~a.v[i];
+  }
+  return z == 0 || q == 0;
+}
+
+PA_HD bool fe_eq(const fe &a, const fe &b) {
+  fe d;
+  fe_sub(d, a, b);
+  return fe_is_zero(d);
+}
+
+// 16-limb product by two interleaved carry chains: `ev` collects the 64-bit
+// partial products that start on an even limb, `od` the ones that start on an
+// odd limb (stored shifted down by one limb), so inside a chain the products
+// never overlap and every step is one 32x32+64 -> 64 multiply-accumulate with
+// carry-in/out (IMAD.WIDE.U32.X).  64 such MACs in total.
+PA_HD void mp_mul8(u32 t[16], const u32 a[8], const u32 b[8]) {
+  u32 ev[16], od[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ev[i] = od[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if ((i & 1) == 0) {
+      // a[even] * b[i] -> ev[i+j .. i+j+1]
+      ev[i + 0] = mad_lo_cc(a[0], b[i], ev[i + 0]);
+      ev[i + 1] = madc_hi_cc(a[0], b[i], ev[i + 1]);
+#pragma unroll
+      for (int j = 2; j < 8; j += 2) {
+        ev[i + j] = madc_lo_cc(a[j], b[i], ev[i + j]);
+        ev[i + j + 1] = madc_hi_cc(a[j], b[i], ev[i + j + 1]);
+      }
+      ev[i + 8] = addc(ev[i + 8], 0);
+      // a[odd] * b[i] -> limb i+j (odd) = od[i+j-1 .. i+j]
+      od[i + 0] = mad_lo_cc(a[1], b[i], od[i + 0]);
+      od[i + 1] = madc_hi_cc(a[1], b[i], od[i + 1]);
+#pragma unroll
+      for (int j = 3; j < 8; j += 2) {
+        od[i + j - 1] = madc_lo_cc(a[j], b[i], od[i + j - 1]);
+        od[i + j] = madc_hi_cc(a[j], b[i], od[i + j]);
+      }
+      // partial sums so far fit below limb i+9, so no carry leaves od[i+7]
+    } else {
+      // a[even] * b[i] -> limb i+j (odd) = od[i+j-1 .. i+j]
+      od[i - 1] = mad_lo_cc(a[0], b[i], od[i - 1]);
+      od[i + 0] = madc_hi_cc(a[0], b[i], od[i + 0]);
+#pragma unroll
+      for (int j = 2; j < 8; j += 2) {
+        od[i + j - 1] = madc_lo_cc(a[j], b[i], od[i + j - 1]);
+        od[i + j] = madc_hi_cc(a[j], b[i], od[i + j]);
+      }
+      od[i + 7] = addc(od[i + 7], 0);
+      // a[odd] * b[i] -> ev[i+j .. i+j+1]
+      ev[i + 1] = mad_lo_cc(a[1], b[i], ev[i + 1]);
+      ev[i + 2] = madc_hi_cc(a[1], b[i], ev[i + 2]);
+#pragma unroll
+      for (int j = 3; j < 8; j += 2) {
+        ev[i + j] = madc_lo_cc(a[j], b[i], ev[i + j]);
+        ev[i + j + 1] = madc_hi_cc(a[j], b[i], ev[i + j + 1]);
+      }
+    }
+  }
+  t[0] = ev[0];
+  t[1] = add_cc(ev[1], od[0]);
+#pragma unroll
+  for (int k = 2; k < 16; ++k) t[k] = addc_cc(ev[k], od[k - 1]);
+}
+
+// fold a 512-bit value to a weak 256-bit representative: 2^256 = 2^32 + 977 (mod p)
+PA_HD void fe_reduce512(fe &r, const u32 t[16]) {
+  const u32 *hi = t + 8;
+  u32 s[10];
+  // s = lo + 977 * hi   (even products then odd products, as in mp_mul8)
+  s[0] = mad_lo_cc(hi[0], PA_C0, t[0]);
+  s[1] = madc_hi_cc(hi[0], PA_C0, t[1]);
+#pragma unroll
+  for (int j = 2; j < 8; j += 2) {
+    s[j] = madc_lo_cc(hi[j], PA_C0, t[j]);
+    s[j + 1] = madc_hi_cc(hi[j], PA_C0, t[j + 1]);
+  }
+  s[8] = addc(0, 0);
+  s[1] = mad_lo_cc(hi[1], PA_C0, s[1]);
+  s[2] = madc_hi_cc(hi[1], PA_C0, s[2]);
+#pragma unroll
+  for (int j = 3; j < 8; j += 2) {
+    s[j] = madc_lo_cc(hi[j], PA_C0, s[j]);
+    s[j + 1] = madc_hi_cc(hi[j], PA_C0, s[j + 1]);
+  }
+  s[9] = addc(0, 0);
+  // s += hi << 32
+  s[1] = add_cc(s[1], hi[0]);
+#pragma unroll
+  for (int j = 2; j < 9; ++j) s[j] = addc_cc(s[j], hi[j - 1]);
+  s[9] = addc(s[9], 0);
+  // second fold: q = s[9]:s[8] (< 2^34);  s[0..7] += q * (2^32 + 977)
+  u32 m0 = mul_lo(s[8], PA_C0);
+  u32 m1 = mul_hi(s[8], PA_C0) + s[9] * PA_C0;  // < 2^11
+  s[0] = add_cc(s[0], m0);
+  s[1] = addc_cc(s[1], m1);
+#pragma unroll
+  for (int j = 2; j < 8; ++j) s[j] = addc_cc(s[j], 0);
+  u32 c1 = addc(0, 0);
+  s[1] = add_cc(s[1], s[8]);
+  s[2] = addc_cc(s[2], s[9]);
+#pragma unroll
+  for (int j = 3; j < 8; ++j) s[j] = addc_cc(s[j], 0);
+  u32 c2 = addc(0, 0);
+  // at most one of c1, c2 is set and then the remainder is < 2^68
+  u32 m = 0u - (c1 | c2);
+  s[0] = add_cc(s[0], PA_C0 & m);
+  s[1] = addc_cc(s[1], 1u & m);
+  s[2] = addc_cc(s[2], 0);
+  s[3] = addc(s[3], 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = s[i];
+}
+
+PA_HD void fe_mul(fe &r, const fe &a, const fe &b) {
+  u32 t[16];
+  mp_mul8(t, a.v, b.v);
+  fe_reduce512(r, t);
+}
+
+// 16-limb square: the 28 cross products once, doubled, plus the 8 diagonal
+// squares (36 MACs instead of 64).
+PA_HD void mp_sqr8(u32 t[16], const u32 a[8]) {
+  // cross products a[i]*a[j], i<j, accumulated with the same even/odd split
+  u32 ev[16], od[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ev[i] = od[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    // row i: products a[j]*a[i] for j > i, landing on limb i+j
+    // first the j with (i+j) even, then the j with (i+j) odd
+    bool first = true;
+#pragma unroll
+    for (int j = i + 1; j < 8; ++j) {
+      if (((i + j) & 1) == 0) {
+        if (first) {
+          ev[i + j] = mad_lo_cc(a[j], a[i], ev[i + j]);
+          first = false;
+        } else {
+          ev[i + j] = madc_lo_cc(a[j], a[i], ev[i + j]);
+        }
+        ev[i + j + 1] = madc_hi_cc(a[j], a[i], ev[i + j + 1]);
+      }
+    }
+    if (!first) {
+      // highest even landing limb of this row is h = i + jmax; carry into h+2
+      int jmax = ((i + 7) & 1) == 0 ? 7 : 6;
+      if (i + jmax + 2 < 16) ev[i + jmax + 2] = addc(ev[i + jmax + 2], 0);
+    }
+    first = true;
+#pragma unroll
+    for (int j = i + 1; j < 8; ++j) {
+      if (((i + j) & 1) == 1) {
+        if (first) {
+          od[i + j - 1] = mad_lo_cc(a[j], a[i], od[i + j - 1]);
+          first = false;
+        } else {
+          od[i + j - 1] = madc_lo_cc(a[j], a[i], od[i + j - 1]);
+        }
+        od[i + j] = madc_hi_cc(a[j], a[i], od[i + j]);
+      }
+    }
+    if (!first) {
+      int jmax = ((i + 7) & 1) == 1 ? 7 : 6;
+      if (i + jmax + 1 < 16) od[i + jmax + 1] = addc(od[i + jmax + 1], 0);
+    }
+  }
+  // cross = ev + (od << 32)
+  u32 x[16];
+  x[0] = ev[0];
+  x[1] = add_cc(ev[1], od[0]);
+#pragma unroll
+  for (int k = 2; k < 16; ++k) x[k] = addc_cc(ev[k], od[k - 1]);
+  // t = 2*cross + sum a[i]^2 << 64i
+  u32 top = 0;
+#pragma unroll
+  for (int k = 15; k > 0; --k) x[k] = (x[k] << 1) | (x[k - 1] >> 31);
+  x[0] <<= 1;
+  (void)top;
+  t[0] = mad_lo_cc(a[0], a[0], x[0]);
+  t[1] = madc_hi_cc(a[0], a[0], x[1]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    t[2 * i] = madc_lo_cc(a[i], a[i], x[2 * i]);
+    t[2 * i + 1] = madc_hi_cc(a[i], a[i], x[2 * i + 1]);
+  }
+}
+
+PA_HD void fe_sqr(fe &r, const fe &a) {
+  u32 t[16];
+  mp_sqr8(t, a.v);
+  fe_reduce512(r, t);
+}
+
+PA_HD void fe_sqr_n(fe &r, const fe &a, int n) {
+  fe t = a;
+  for (int i = 0; i < n; ++i) fe_sqr(t, t);
+  r = t;
+}
+
+// r = a^(p-2): 255 squarings + 15 multiplications.  p - 2 in binary is
+// 223 ones, 0, 22 ones, 0000, 1, 0, 11, 0, 1.
+PA_HD void fe_inv(fe &r, const fe &a) {
+  fe x2, x3, x6, x9, x11, x22, x44, x88, x176, x220, x223, t;
+  fe_sqr(t, a);        fe_mul(x2, t, a);
+  fe_sqr(t, x2);       fe_mul(x3, t, a);
+  fe_sqr_n(t, x3, 3);  fe_mul(x6, t, x3);
+  fe_sqr_n(t, x6, 3);  fe_mul(x9, t, x3);
+  fe_sqr_n(t, x9, 2);  fe_mul(x11, t, x2);
+  fe_sqr_n(t, x11, 11); fe_mul(x22, t, x11);
+  fe_sqr_n(t, x22, 22); fe_mul(x44, t, x22);
+  fe_sqr_n(t, x44, 44); fe_mul(x88, t, x44);
+  fe_sqr_n(t, x88, 88); fe_mul(x176, t, x88);
+  fe_sqr_n(t, x176, 44); fe_mul(x220, t, x44);
+  fe_sqr_n(t, x220, 3); fe_mul(x223, t, x3);
+  fe_sqr_n(t, x223, 23); fe_mul(t, t, x22);
+  fe_sqr_n(t, t, 5);   fe_mul(t, t, a);
+  fe_sqr_n(t, t, 3);   fe_mul(t, t, x2);
+  fe_sqr_n(t, t, 2);   fe_mul(r, t, a);
+}
+
+// 32-byte big-endian <-> limbs
+PA_HD void fe_from_be(fe &r, const unsigned char *b) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const unsigned char *q = b + 4 * (7 - i);
+    r.v[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+  }
+}
+PA_HD void fe_to_be(unsigned char *b, const fe &a) {  // a must be canonical
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    unsigned char *q = b + 4 * (7 - i);
+    q[0] = (unsigned char)(a.v[i] >> 24);
+    q[1] = (unsigned char)(a.v[i] >> 16);
+    q[2] = (unsigned char)(a.v[i] >> 8);
+    q[3] = (unsigned char)(a.v[i]);
+  }
+}

@@ -1,0 +1,119 @@
+// TEST-ONLY host build of the device arithmetic headers (privacy-auction_b200/csrc/*.cuh).
+// The headers emulate the PTX carry flag when compiled by g++ (pa_ptx.cuh), so
+// the limb algorithms can be checked against Python integers / the oracle on a
+// machine without a GPU.  This file is never linked into libpa_engine.so and
+// the product has no CPU path.
+#include "pa_fe.cuh"
+#include <string.h>
+
+extern "C" {
+void hc_fe_op(int op, const unsigned char *a, const unsigned char *b, unsigned char *out) {
+  fe x, y, r;
+  fe_from_be(x, a);
+  fe_from_be(y, b);
+  switch (op) {
+  case 0: fe_mul(r, x, y); break;
+  case 1: fe_sqr(r, x); break;
+  case 2: fe_add(r, x, y); break;
+  case 3: fe_sub(r, x, y); break;
+  case 4: fe_inv(r, x); break;
+  case 5: fe_neg(r, x); break;
+  case 6: r = x; break;
+  case 7: { fe_set_zero(r); r.v[0] = fe_is_zero(x); fe_to_be(out, r); return; }
+  case 8: { fe_set_zero(r); r.v[0] = fe_eq(x, y); fe_to_be(out, r); return; }
+  default: fe_set_zero(r);
+  }
+  fe_canon(r, r);
+  fe_to_be(out, r);
+}
+void hc_mp_mul8(const unsigned char *a, const unsigned char *b, unsigned char *out64, int sqr) {
+  fe x, y;
+  fe_from_be(x, a);
+  fe_from_be(y, b);
+  u32 t[16];
+  if (sqr) mp_sqr8(t, x.v); else mp_mul8(t, x.v, y.v);
+  for (int i = 0; i < 16; ++i) {
+    unsigned char *q = out64 + 4 * (15 - i);
+    q[0] = t[i] >> 24; q[1] = t[i] >> 16; q[2] = t[i] >> 8; q[3] = t[i];
+  }
+}
+}
+
+#include "pa_smul.cuh"
+#include <vector>
+
+static std::vector<u32> g_tab;
+static void ensure_tab() {
+  if (!g_tab.empty()) return;
+  g_tab.assign(PA_COMB_WORDS, 0);
+  aff G;
+  aff_set_generator(G);
+  for (int w = 0; w < PA_COMB_WINDOWS; ++w) {
+    aff Bw;
+    comb_base(Bw, w, G);
+    for (u32 d = 1; d < PA_COMB_ENTRIES; ++d) {
+      aff e;
+      comb_entry(e, d, Bw);
+      u32 *o = g_tab.data() + ((size_t)w * PA_COMB_ENTRIES + d) * 16;
+      for (int i = 0; i < 8; ++i) { o[i] = e.x.v[i]; o[8 + i] = e.y.v[i]; }
+    }
+  }
+}
+static void out_jac(unsigned char *out, const jac &r) {
+  aff a;
+  jac_to_aff(a, r);
+  aff_to_be64(out, a);
+}
+extern "C" {
+void hc_sc_op(int op, const unsigned char *a, const unsigned char *b, unsigned char *out) {
+  sc x, y, r;
+  sc_from_be(x, a);
+  sc_from_be(y, b);
+  switch (op) {
+  case 0: sc_mul(r, x, y); break;
+  case 1: sc_add(r, x, y); break;
+  case 2: sc_sub(r, x, y); break;
+  case 3: sc_neg(r, x); break;
+  default: r = x;
+  }
+  sc_to_be(out, r);
+}
+void hc_fixed_base(const unsigned char *k, unsigned char *out) {
+  ensure_tab();
+  sc s; sc_from_be(s, k);
+  jac r; fixed_base_mul(r, s, g_tab.data());
+  out_jac(out, r);
+}
+void hc_var_base(const unsigned char *p, const unsigned char *k, unsigned char *out) {
+  aff a; aff_from_be64(a, p);
+  jac P; jac_from_aff(P, a);
+  sc s; sc_from_be(s, k);
+  jac r; var_base_mul(r, P, s);
+  out_jac(out, r);
+}
+void hc_lincomb2(const unsigned char *p, const unsigned char *ka, const unsigned char *q, const unsigned char *kb, unsigned char *out) {
+  aff a, b; aff_from_be64(a, p); aff_from_be64(b, q);
+  jac P, Q; jac_from_aff(P, a); jac_from_aff(Q, b);
+  sc s, t; sc_from_be(s, ka); sc_from_be(t, kb);
+  jac r; strauss<2>(r, P, s, Q, t);
+  out_jac(out, r);
+}
+void hc_point_add(const unsigned char *p, const unsigned char *q, unsigned char *out, int mixed) {
+  aff a, b; aff_from_be64(a, p); aff_from_be64(b, q);
+  jac P, Q, r; jac_from_aff(P, a); jac_from_aff(Q, b);
+  // give P a non-trivial Z so the Jacobian paths are exercised: (X*4, Y*8, 2)
+  if (!jac_is_inf(P)) { fe two; fe_set_zero(two); two.v[0] = 2; fe t; fe_add(t, P.X, P.X); fe_add(P.X, t, t); fe_add(t, P.Y, P.Y); fe_add(t, t, t); fe_add(P.Y, t, t); P.Z = two; }
+  if (mixed) jac_madd(r, P, b); else {
+    if (!jac_is_inf(Q)) { fe three; fe_set_zero(three); three.v[0] = 3; fe z2, z3; fe_sqr(z2, three); fe_mul(z3, z2, three); fe_mul(Q.X, Q.X, z2); fe_mul(Q.Y, Q.Y, z3); Q.Z = three; }
+    jac_add(r, P, Q);
+  }
+  out_jac(out, r);
+}
+int hc_jac_eq_aff(const unsigned char *p, const unsigned char *q) {
+  aff a, b; aff_from_be64(a, p); aff_from_be64(b, q);
+  jac P; jac_from_aff(P, a);
+  if (!jac_is_inf(P)) { fe z; fe_set_zero(z); z.v[0] = 5; fe z2, z3; fe_sqr(z2, z); fe_mul(z3, z2, z); fe_mul(P.X, P.X, z2); fe_mul(P.Y, P.Y, z3); P.Z = z; }
+  return jac_eq_aff(P, b) ? 1 : 0;
+}
+const unsigned int *hc_comb_table() { ensure_tab(); return g_tab.data(); }
+}
