@@ -59,8 +59,16 @@ PA_HD void jac_neg(jac &r, const jac &p) {
   r.Z = p.Z;
 }
 
+#if defined(__CUDA_ARCH__) && !defined(PA_EC_INLINE)
+static __device__ __noinline__ jac jac_dbl_call(jac p);
+PA_D void jac_dbl(jac &r, const jac &p) { r = jac_dbl_call(p); }
+#else
+PA_HD void jac_dbl_inl(jac &r, const jac &p);
+PA_HD void jac_dbl(jac &r, const jac &p) { jac_dbl_inl(r, p); }
+#endif
+
 // r = 2p   (dbl-2009-l, 2M + 5S).  No point of order 2 exists (prime order).
-PA_HD void jac_dbl(jac &r, const jac &p) {
+PA_HD void jac_dbl_inl(jac &r, const jac &p) {
   if (jac_is_inf(p)) {
     jac_set_inf(r);
     return;
@@ -90,7 +98,7 @@ PA_HD void jac_dbl(jac &r, const jac &p) {
 }
 
 // r = p + q, q affine   (8M + 3S)
-PA_HD void jac_madd(jac &r, const jac &p, const aff &q) {
+PA_HD void jac_madd_inl(jac &r, const jac &p, const aff &q) {
   if (aff_is_inf(q)) {
     r = p;
     return;
@@ -132,7 +140,7 @@ PA_HD void jac_madd(jac &r, const jac &p, const aff &q) {
 }
 
 // r = p + q   (12M + 4S)
-PA_HD void jac_add(jac &r, const jac &p, const jac &q) {
+PA_HD void jac_add_inl(jac &r, const jac &p, const jac &q) {
   if (jac_is_inf(q)) {
     r = p;
     return;
@@ -175,6 +183,31 @@ PA_HD void jac_add(jac &r, const jac &p, const jac &q) {
   fe_mul(v, rr, v);
   fe_sub(r.Y, v, hhh);
 }
+
+// On the device the three group operations are real functions (arguments and
+// result in registers) so that a scalar multiplication is a few KB of code.
+#if defined(__CUDA_ARCH__) && !defined(PA_EC_INLINE)
+static __device__ __noinline__ jac jac_dbl_call(jac p) {
+  jac r;
+  jac_dbl_inl(r, p);
+  return r;
+}
+static __device__ __noinline__ jac jac_madd_call(jac p, aff q) {
+  jac r;
+  jac_madd_inl(r, p, q);
+  return r;
+}
+static __device__ __noinline__ jac jac_add_call(jac p, jac q) {
+  jac r;
+  jac_add_inl(r, p, q);
+  return r;
+}
+PA_D void jac_madd(jac &r, const jac &p, const aff &q) { r = jac_madd_call(p, q); }
+PA_D void jac_add(jac &r, const jac &p, const jac &q) { r = jac_add_call(p, q); }
+#else
+PA_HD void jac_madd(jac &r, const jac &p, const aff &q) { jac_madd_inl(r, p, q); }
+PA_HD void jac_add(jac &r, const jac &p, const jac &q) { jac_add_inl(r, p, q); }
+#endif
 
 // Jacobian == affine without an inversion (EC_POINT_cmp, SEAL/bidder.cpp:131)
 PA_HD bool jac_eq_aff(const jac &p, const aff &q) {

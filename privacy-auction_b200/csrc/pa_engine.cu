@@ -1,0 +1,454 @@
+// Host side of the C ABI declared in include/pa_engine.h.  Nothing in this file
+// computes on the CPU: every entry point stages buffers and launches the
+// kernels of pa_kernels.cuh on the context's stream.
+#include "../../include/pa_engine.h"
+#include "pa_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+struct pa_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  u32 *d_comb = nullptr;  // PA_COMB_WORDS
+  // grow-only device arenas
+  unsigned char *d_work = nullptr;  // Jacobian scratch + prefix products
+  size_t work_bytes = 0;
+  unsigned char *d_stage = nullptr;  // staging for the host-buffer entry points
+  size_t stage_bytes = 0;
+  uint64_t launches = 0;
+  std::string err;
+  // optional per-kernel CUDA-event timing (pa_profile_begin / pa_profile_end)
+  bool profiling = false;
+  struct Span { int kid; cudaEvent_t e0, e1; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_pool;
+};
+
+enum {
+  PA_K_COMB = 0, PA_K_FIXED, PA_K_VAR, PA_K_DOUBLE, PA_K_LINCOMB2, PA_K_POINT_ADD, PA_K_NORMALIZE, PA_K_ENCODE,
+  PA_K_PEAK, PA_K_COUNT
+};
+static const char *const PA_K_NAMES[PA_K_COUNT] = {"k_comb", "k_fixed_base", "k_var_base", "k_double_mul", "k_lincomb2",
+                                                   "k_point_add", "k_normalize", "k_encode", "k_peak"};
+
+static cudaEvent_t ev_get(pa_ctx *ctx) {
+  if (!ctx->ev_pool.empty()) {
+    cudaEvent_t e = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// launch a kernel on the context's stream; when profiling, bracket it with events
+#define PA_LAUNCH(ctx, kid, ...)                                   \
+  do {                                                             \
+    pa_ctx::Span sp_{kid, nullptr, nullptr};                       \
+    if ((ctx)->profiling) {                                        \
+      sp_.e0 = ev_get(ctx);                                        \
+      sp_.e1 = ev_get(ctx);                                        \
+      cudaEventRecord(sp_.e0, (ctx)->stream);                      \
+    }                                                              \
+    __VA_ARGS__;                                                   \
+    if ((ctx)->profiling) {                                        \
+      cudaEventRecord(sp_.e1, (ctx)->stream);                      \
+      (ctx)->spans.push_back(sp_);                                 \
+    }                                                              \
+    (ctx)->launches++;                                             \
+    PA_CUDA(ctx, cudaGetLastError());                              \
+  } while (0)
+
+static std::string g_create_err;
+
+#define PA_CUDA(ctx, call)                                                                      \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      char buf_[512];                                                                           \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      (ctx)->err = buf_;                                                                        \
+      return PA_ECUDA;                                                                          \
+    }                                                                                           \
+  } while (0)
+
+#define PA_LAUNCH_CHECK(ctx)       \
+  do {                             \
+    (ctx)->launches++;             \
+    PA_CUDA(ctx, cudaGetLastError()); \
+  } while (0)
+
+static int pa_fail(pa_ctx *ctx, int code, const char *msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + PA_BLOCK - 1) / PA_BLOCK); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int ensure(pa_ctx *ctx, unsigned char **buf, size_t *cap, size_t need) {
+  if (need <= *cap) return PA_OK;
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*buf) PA_CUDA(ctx, cudaFree(*buf));
+  *buf = nullptr;
+  *cap = 0;
+  size_t want = align_up(need + need / 4, 1 << 20);
+  PA_CUDA(ctx, cudaMalloc((void **)buf, want));
+  *cap = want;
+  return PA_OK;
+}
+
+extern "C" {
+
+int pa_abi_version(void) { return 1; }
+
+const char *pa_last_error(pa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int pa_ctx_create(pa_ctx **out, int device) {
+  if (!out) return PA_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                   " (this engine has no CPU path)";
+    return PA_ENODEV;
+  }
+  if (device < 0 || device >= count) {
+    g_create_err = "device ordinal out of range";
+    return PA_EINVAL;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    g_create_err = "device is not compute capability 10.x (the engine ships sm_100a code only)";
+    return PA_ENODEV;
+  }
+  pa_ctx *ctx = new pa_ctx();
+  ctx->device = device;
+  auto fail = [&](const char *what, cudaError_t ce) {
+    g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
+    delete ctx;
+    return PA_ECUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaMalloc((void **)&ctx->d_comb, PA_COMB_WORDS * sizeof(u32))) != cudaSuccess) return fail("cudaMalloc(comb)", e);
+  u32 *d_bases = nullptr;
+  if ((e = cudaMalloc((void **)&d_bases, PA_COMB_WINDOWS * 16 * sizeof(u32))) != cudaSuccess) return fail("cudaMalloc(bases)", e);
+  k_comb_base<<<1, PA_COMB_WINDOWS, 0, ctx->stream>>>(d_bases);
+  k_comb_entries<<<PA_COMB_WINDOWS * PA_COMB_ENTRIES / PA_BLOCK, PA_BLOCK, 0, ctx->stream>>>(d_bases, ctx->d_comb);
+  ctx->launches += 2;
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("comb table build", e);
+  cudaFree(d_bases);
+  *out = ctx;
+  return PA_OK;
+}
+
+int pa_ctx_destroy(pa_ctx *ctx) {
+  if (!ctx) return PA_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_comb);
+  cudaFree(ctx->d_work);
+  cudaFree(ctx->d_stage);
+  for (auto &sp : ctx->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return PA_OK;
+}
+
+int pa_sync(pa_ctx *ctx) {
+  if (!ctx) return PA_EINVAL;
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+void *pa_ctx_stream(pa_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t pa_ctx_launches(pa_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pa_dev_alloc(pa_ctx *ctx, void **dptr, size_t bytes) {
+  if (!ctx || !dptr) return PA_EINVAL;
+  PA_CUDA(ctx, cudaSetDevice(ctx->device));
+  PA_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+  return PA_OK;
+}
+int pa_dev_free(pa_ctx *ctx, void *dptr) {
+  if (!ctx) return PA_EINVAL;
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PA_CUDA(ctx, cudaFree(dptr));
+  return PA_OK;
+}
+int pa_dev_upload(pa_ctx *ctx, void *dptr, const void *host, size_t bytes) {
+  if (!ctx) return PA_EINVAL;
+  PA_CUDA(ctx, cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return PA_OK;
+}
+int pa_dev_download(pa_ctx *ctx, void *host, const void *dptr, size_t bytes) {
+  if (!ctx) return PA_EINVAL;
+  PA_CUDA(ctx, cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+}  // extern "C"
+
+// ---- internal: Jacobian scratch -> affine output ------------------------------------
+// work arena layout: [ n * 96 B Jacobian | n * 32 B prefix products ]
+static int work_reserve(pa_ctx *ctx, size_t n) { return ensure(ctx, &ctx->d_work, &ctx->work_bytes, n * 128 + 256); }
+static u32 *work_jac(pa_ctx *ctx) { return (u32 *)ctx->d_work; }
+static u32 *work_prefix(pa_ctx *ctx, size_t n) { return (u32 *)(ctx->d_work + n * 96); }
+
+static int normalize_to(pa_ctx *ctx, unsigned char *d_out, size_t n) {
+  // points per thread: amortise the ~270-multiplication inversion once the
+  // batch is large enough to keep every SM busy anyway
+  size_t per = n / (148 * 1024);
+  if (per < 1) per = 1;
+  if (per > 16) per = 16;
+  size_t T = (n + per - 1) / per;
+  PA_LAUNCH(ctx, PA_K_NORMALIZE, k_normalize<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(work_jac(ctx), work_prefix(ctx, n), d_out, (int)n, (int)T));
+  return PA_OK;
+}
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+#define PA_ARGCHECK(ctx, cond) \
+  if (!(cond)) return pa_fail(ctx, PA_EINVAL, "invalid argument: " #cond)
+
+extern "C" {
+
+int pa_fixed_base_mul_dev(pa_ctx *ctx, const uint8_t *d_scalars, uint8_t *d_out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (d_scalars && d_out)) && n < (1u << 30));
+  PA_ARGCHECK(ctx, aligned16(d_scalars) && aligned16(d_out));
+  if (n == 0) return PA_OK;
+  int rc = work_reserve(ctx, n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_FIXED, k_fixed_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_scalars, ctx->d_comb, work_jac(ctx), (int)n));
+  return normalize_to(ctx, d_out, n);
+}
+
+int pa_var_base_mul_dev(pa_ctx *ctx, const uint8_t *d_points, const uint8_t *d_scalars, uint8_t *d_out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (d_points && d_scalars && d_out)) && n < (1u << 30));
+  PA_ARGCHECK(ctx, aligned16(d_points) && aligned16(d_scalars) && aligned16(d_out));
+  if (n == 0) return PA_OK;
+  int rc = work_reserve(ctx, n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_VAR, k_var_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_points, d_scalars, work_jac(ctx), (int)n));
+  return normalize_to(ctx, d_out, n);
+}
+
+int pa_double_mul_dev(pa_ctx *ctx, const uint8_t *d_a, const uint8_t *d_points, const uint8_t *d_b, uint8_t *d_out,
+                      size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (d_a && d_points && d_b && d_out)) && n < (1u << 30));
+  PA_ARGCHECK(ctx, aligned16(d_a) && aligned16(d_points) && aligned16(d_b) && aligned16(d_out));
+  if (n == 0) return PA_OK;
+  int rc = work_reserve(ctx, n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_DOUBLE, k_double_mul<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_a, d_points, d_b, ctx->d_comb, work_jac(ctx), (int)n));
+  return normalize_to(ctx, d_out, n);
+}
+
+int pa_lincomb2_dev(pa_ctx *ctx, const uint8_t *d_p, const uint8_t *d_a, const uint8_t *d_q, const uint8_t *d_b,
+                    uint8_t *d_out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (d_p && d_a && d_q && d_b && d_out)) && n < (1u << 30));
+  PA_ARGCHECK(ctx, aligned16(d_p) && aligned16(d_a) && aligned16(d_q) && aligned16(d_b) && aligned16(d_out));
+  if (n == 0) return PA_OK;
+  int rc = work_reserve(ctx, n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_LINCOMB2, k_lincomb2<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_p, d_a, d_q, d_b, work_jac(ctx), (int)n));
+  return normalize_to(ctx, d_out, n);
+}
+
+}  // extern "C"
+
+// ---- host-buffer wrappers: stage in, run, stage out ---------------------------------
+namespace {
+struct Stage {
+  pa_ctx *ctx;
+  size_t off = 0;
+  explicit Stage(pa_ctx *c) : ctx(c) {}
+  unsigned char *take(size_t bytes) {
+    unsigned char *p = ctx->d_stage + off;
+    off += align_up(bytes, 256);
+    return p;
+  }
+};
+int stage_reserve(pa_ctx *ctx, size_t bytes) { return ensure(ctx, &ctx->d_stage, &ctx->stage_bytes, bytes); }
+}  // namespace
+
+extern "C" {
+
+int pa_fixed_base_mul(pa_ctx *ctx, const uint8_t *scalars, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (scalars && out)));
+  if (n == 0) return PA_OK;
+  int rc = stage_reserve(ctx, n * 96 + 1024);
+  if (rc) return rc;
+  Stage s(ctx);
+  unsigned char *d_k = s.take(n * 32), *d_o = s.take(n * 64);
+  PA_CUDA(ctx, cudaMemcpyAsync(d_k, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = pa_fixed_base_mul_dev(ctx, d_k, d_o, n))) return rc;
+  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+int pa_var_base_mul(pa_ctx *ctx, const uint8_t *points, const uint8_t *scalars, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (points && scalars && out)));
+  if (n == 0) return PA_OK;
+  int rc = stage_reserve(ctx, n * 160 + 1024);
+  if (rc) return rc;
+  Stage s(ctx);
+  unsigned char *d_p = s.take(n * 64), *d_k = s.take(n * 32), *d_o = s.take(n * 64);
+  PA_CUDA(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(d_k, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = pa_var_base_mul_dev(ctx, d_p, d_k, d_o, n))) return rc;
+  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+int pa_double_mul(pa_ctx *ctx, const uint8_t *a, const uint8_t *points, const uint8_t *b, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (a && points && b && out)));
+  if (n == 0) return PA_OK;
+  int rc = stage_reserve(ctx, n * 192 + 1024);
+  if (rc) return rc;
+  Stage s(ctx);
+  unsigned char *d_a = s.take(n * 32), *d_p = s.take(n * 64), *d_b = s.take(n * 32), *d_o = s.take(n * 64);
+  PA_CUDA(ctx, cudaMemcpyAsync(d_a, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(d_b, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = pa_double_mul_dev(ctx, d_a, d_p, d_b, d_o, n))) return rc;
+  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+int pa_lincomb2(pa_ctx *ctx, const uint8_t *p, const uint8_t *a, const uint8_t *q, const uint8_t *b, uint8_t *out,
+                size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (p && a && q && b && out)));
+  if (n == 0) return PA_OK;
+  int rc = stage_reserve(ctx, n * 256 + 2048);
+  if (rc) return rc;
+  Stage s(ctx);
+  unsigned char *d_p = s.take(n * 64), *d_a = s.take(n * 32), *d_q = s.take(n * 64), *d_b = s.take(n * 32),
+                *d_o = s.take(n * 64);
+  PA_CUDA(ctx, cudaMemcpyAsync(d_p, p, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(d_a, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(d_q, q, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(d_b, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = pa_lincomb2_dev(ctx, d_p, d_a, d_q, d_b, d_o, n))) return rc;
+  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, int sub) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (p && q && out)) && n < (1u << 30));
+  if (n == 0) return PA_OK;
+  int rc = stage_reserve(ctx, n * 192 + 1024);
+  if (rc) return rc;
+  if ((rc = work_reserve(ctx, n))) return rc;
+  Stage s(ctx);
+  unsigned char *d_p = s.take(n * 64), *d_q = s.take(n * 64), *d_o = s.take(n * 64);
+  PA_CUDA(ctx, cudaMemcpyAsync(d_p, p, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(d_q, q, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  PA_LAUNCH(ctx, PA_K_POINT_ADD, k_point_add<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_p, d_q, work_jac(ctx), (int)n, sub));
+  if ((rc = normalize_to(ctx, d_o, n))) return rc;
+  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+int pa_point_encode(pa_ctx *ctx, const uint8_t *points, size_t n, int compressed, uint8_t *out, size_t stride,
+                    uint32_t *lens) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (points && out && lens)) && n < (1u << 30));
+  PA_ARGCHECK(ctx, stride >= (compressed ? 33u : 65u));
+  if (n == 0) return PA_OK;
+  int rc = stage_reserve(ctx, n * (64 + stride + 4) + 1024);
+  if (rc) return rc;
+  Stage s(ctx);
+  unsigned char *d_p = s.take(n * 64), *d_o = s.take(n * stride), *d_l = s.take(n * 4);
+  PA_CUDA(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  PA_LAUNCH(ctx, PA_K_ENCODE, k_encode<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_p, (int)n, compressed, d_o, stride, (u32 *)d_l));
+  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * stride, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(lens, d_l, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+int pa_profile_begin(pa_ctx *ctx) {
+  PA_ARGCHECK(ctx, ctx);
+  ctx->profiling = true;
+  return PA_OK;
+}
+
+int pa_profile_end(pa_ctx *ctx, pa_kernel_stat *out, size_t cap, size_t *count) {
+  PA_ARGCHECK(ctx, ctx && count && (out || cap == 0));
+  ctx->profiling = false;
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double total[PA_K_COUNT] = {0};
+  uint64_t cnt[PA_K_COUNT] = {0};
+  for (auto &sp : ctx->spans) {
+    float ms = 0;
+    PA_CUDA(ctx, cudaEventElapsedTime(&ms, sp.e0, sp.e1));
+    total[sp.kid] += ms;
+    cnt[sp.kid]++;
+    ctx->ev_pool.push_back(sp.e0);
+    ctx->ev_pool.push_back(sp.e1);
+  }
+  ctx->spans.clear();
+  size_t k = 0;
+  for (int i = 0; i < PA_K_COUNT; ++i) {
+    if (!cnt[i]) continue;
+    if (k < cap) {
+      memset(&out[k], 0, sizeof out[k]);
+      strncpy(out[k].name, PA_K_NAMES[i], sizeof out[k].name - 1);
+      out[k].launches = cnt[i];
+      out[k].total_ms = total[i];
+    }
+    ++k;
+  }
+  *count = k;
+  return PA_OK;
+}
+
+int pa_measure_int_peak(pa_ctx *ctx, double out[4]) {
+  PA_ARGCHECK(ctx, ctx && out);
+  int rc = stage_reserve(ctx, 4096);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  PA_CUDA(ctx, cudaEventCreate(&e0));
+  PA_CUDA(ctx, cudaEventCreate(&e1));
+  const int blocks = 148 * 8, threads = 256;
+  for (int which = 0; which < 4; ++which) {
+    int iters = which < 2 ? 4096 : 2048;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      PA_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+      if (which == 0) k_peak_imad<<<blocks, threads, 0, ctx->stream>>>((u32 *)ctx->d_stage, iters, 3u + rep, 7u);
+      if (which == 1) k_peak_imad_wide<<<blocks, threads, 0, ctx->stream>>>((u64 *)ctx->d_stage, iters, 3u + rep);
+      if (which == 2) k_peak_fe<<<blocks, threads, 0, ctx->stream>>>((u32 *)ctx->d_stage, iters, 0);
+      if (which == 3) k_peak_fe<<<blocks, threads, 0, ctx->stream>>>((u32 *)ctx->d_stage, iters, 1);
+      ctx->launches++;
+      PA_CUDA(ctx, cudaGetLastError());
+      PA_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+      PA_CUDA(ctx, cudaEventSynchronize(e1));
+      float ms = 0;
+      PA_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+      double ops = (double)blocks * threads * iters * (which < 2 ? 64.0 : 2.0);
+      double rate = ops / (ms * 1e-3);
+      if (rep > 0 && rate > best) best = rate;  // first repetition is warm-up
+    }
+    out[which] = best;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return PA_OK;
+}
+
+}  // extern "C"

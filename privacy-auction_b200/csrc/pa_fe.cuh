@@ -210,7 +210,7 @@ PA_HD void fe_reduce512(fe &r, const u32 t[16]) {
   for (int i = 0; i < 8; ++i) r.v[i] = s[i];
 }
 
-PA_HD void fe_mul(fe &r, const fe &a, const fe &b) {
+PA_HD void fe_mul_inl(fe &r, const fe &a, const fe &b) {
   u32 t[16];
   mp_mul8(t, a.v, b.v);
   fe_reduce512(r, t);
@@ -284,11 +284,34 @@ PA_HD void mp_sqr8(u32 t[16], const u32 a[8]) {
   }
 }
 
-PA_HD void fe_sqr(fe &r, const fe &a) {
+PA_HD void fe_sqr_inl(fe &r, const fe &a) {
   u32 t[16];
   mp_sqr8(t, a.v);
   fe_reduce512(r, t);
 }
+
+// On the device the multiplier and the squarer are real (non-inlined)
+// functions taking and returning the 8 limbs in registers: a scalar
+// multiplication contains ~3000 of them, and inlining each (~150 SASS
+// instructions) produces hundreds of KB of code that thrashes the 32 KB
+// instruction cache.  Define PA_FE_INLINE to inline them instead.
+#if defined(__CUDA_ARCH__) && !defined(PA_FE_INLINE)
+static __device__ __noinline__ fe fe_mul_call(fe a, fe b) {
+  fe r;
+  fe_mul_inl(r, a, b);
+  return r;
+}
+static __device__ __noinline__ fe fe_sqr_call(fe a) {
+  fe r;
+  fe_sqr_inl(r, a);
+  return r;
+}
+PA_D void fe_mul(fe &r, const fe &a, const fe &b) { r = fe_mul_call(a, b); }
+PA_D void fe_sqr(fe &r, const fe &a) { r = fe_sqr_call(a); }
+#else
+PA_HD void fe_mul(fe &r, const fe &a, const fe &b) { fe_mul_inl(r, a, b); }
+PA_HD void fe_sqr(fe &r, const fe &a) { fe_sqr_inl(r, a); }
+#endif
 
 PA_HD void fe_sqr_n(fe &r, const fe &a, int n) {
   fe t = a;

@@ -1,0 +1,221 @@
+"""ctypes binding of the engine's C ABI (include/pa_engine.h).
+
+This is plumbing for the tests and bench.py: every method forwards to the
+symbol of the same name in libpa_engine.so.  There is no Python or CPU
+implementation behind it — if the library or a B200 is missing, construction
+fails loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpa_engine.so")
+
+PA_OK, PA_EINVAL, PA_ENODEV, PA_ECUDA, PA_ENOMEM = 0, -1, -2, -3, -4
+POINT_BYTES, SCALAR_BYTES = 64, 32
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_sz = ctypes.c_size_t
+_ctx = ctypes.c_void_p
+
+# symbol -> (restype, argtypes); kept in step with include/pa_engine.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "pa_ctx_create": (ctypes.c_int, [ctypes.POINTER(_ctx), ctypes.c_int]),
+    "pa_ctx_destroy": (ctypes.c_int, [_ctx]),
+    "pa_sync": (ctypes.c_int, [_ctx]),
+    "pa_last_error": (ctypes.c_char_p, [_ctx]),
+    "pa_abi_version": (ctypes.c_int, []),
+    "pa_ctx_stream": (ctypes.c_void_p, [_ctx]),
+    "pa_ctx_launches": (ctypes.c_uint64, [_ctx]),
+    "pa_dev_alloc": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_void_p), _sz]),
+    "pa_dev_free": (ctypes.c_int, [_ctx, ctypes.c_void_p]),
+    "pa_dev_upload": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, _sz]),
+    "pa_dev_download": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, _sz]),
+    "pa_fixed_base_mul": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, _sz]),
+    "pa_fixed_base_mul_dev": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, _sz]),
+    "pa_var_base_mul": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _sz]),
+    "pa_var_base_mul_dev": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _sz]),
+    "pa_double_mul": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _sz]),
+    "pa_double_mul_dev": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _sz]),
+    "pa_lincomb2": (ctypes.c_int, [_ctx] + [ctypes.c_void_p] * 5 + [_sz]),
+    "pa_lincomb2_dev": (ctypes.c_int, [_ctx] + [ctypes.c_void_p] * 5 + [_sz]),
+    "pa_point_add": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _sz, ctypes.c_int]),
+    "pa_point_encode": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.c_int, ctypes.c_void_p, _sz, ctypes.c_void_p]),
+    "pa_measure_int_peak": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_double)]),
+    "pa_profile_begin": (ctypes.c_int, [_ctx]),
+    "pa_profile_end": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.POINTER(_sz)]),
+}
+
+
+class KernelStat(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 32), ("launches", ctypes.c_uint64), ("total_ms", ctypes.c_double)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    """dlopen libpa_engine.so and attach the prototypes.  Works without a GPU
+    (the CUDA runtime is only touched by pa_ctx_create)."""
+    if not os.path.exists(path):
+        raise EngineError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a); there is no fallback implementation"
+        )
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def _buf(b):
+    """bytes-like -> (ctypes pointer, keepalive)"""
+    if isinstance(b, (bytes, bytearray, memoryview)):
+        arr = (ctypes.c_uint8 * len(b)).from_buffer_copy(bytes(b)) if not isinstance(b, bytearray) else (ctypes.c_uint8 * len(b)).from_buffer(b)
+        return ctypes.cast(arr, ctypes.c_void_p), arr
+    if hasattr(b, "ctypes"):  # numpy array
+        return ctypes.c_void_p(b.ctypes.data), b
+    raise TypeError(type(b))
+
+
+class Engine:
+    """One engine context on one GPU (pa_ctx)."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib or load_library()
+        self.ctx = _ctx()
+        rc = self.lib.pa_ctx_create(ctypes.byref(self.ctx), device)
+        if rc != PA_OK:
+            msg = self.lib.pa_last_error(None)
+            self.ctx = None
+            raise EngineError(f"pa_ctx_create failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self.ctx:
+            self.lib.pa_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != PA_OK:
+            msg = self.lib.pa_last_error(self.ctx)
+            raise EngineError(f"engine call failed ({rc}): {msg.decode() if msg else ''}")
+
+    # -- raw helpers -------------------------------------------------------------
+    @property
+    def stream(self):
+        return self.lib.pa_ctx_stream(self.ctx)
+
+    @property
+    def launches(self):
+        return self.lib.pa_ctx_launches(self.ctx)
+
+    def sync(self):
+        self._check(self.lib.pa_sync(self.ctx))
+
+    def dev_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(self.lib.pa_dev_alloc(self.ctx, ctypes.byref(p), nbytes))
+        return p.value
+
+    def dev_free(self, dptr):
+        self._check(self.lib.pa_dev_free(self.ctx, dptr))
+
+    def upload(self, dptr, data):
+        p, keep = _buf(data)
+        self._check(self.lib.pa_dev_upload(self.ctx, dptr, p, len(data) if not hasattr(data, "nbytes") else data.nbytes))
+        self.sync()
+        return keep
+
+    def download(self, dptr, nbytes):
+        out = bytearray(nbytes)
+        p, keep = _buf(out)
+        self._check(self.lib.pa_dev_download(self.ctx, p, dptr, nbytes))
+        return bytes(out)
+
+    # -- host-buffer entry points -----------------------------------------------------
+    def fixed_base_mul(self, scalars):
+        n = len(scalars) // 32
+        out = bytearray(64 * n)
+        ps, k1 = _buf(scalars)
+        po, k2 = _buf(out)
+        self._check(self.lib.pa_fixed_base_mul(self.ctx, ps, po, n))
+        return bytes(out)
+
+    def var_base_mul(self, points, scalars):
+        n = len(scalars) // 32
+        out = bytearray(64 * n)
+        pp, k0 = _buf(points)
+        ps, k1 = _buf(scalars)
+        po, k2 = _buf(out)
+        self._check(self.lib.pa_var_base_mul(self.ctx, pp, ps, po, n))
+        return bytes(out)
+
+    def double_mul(self, a, points, b):
+        n = len(a) // 32
+        out = bytearray(64 * n)
+        pa_, k0 = _buf(a)
+        pp, k1 = _buf(points)
+        pb, k2 = _buf(b)
+        po, k3 = _buf(out)
+        self._check(self.lib.pa_double_mul(self.ctx, pa_, pp, pb, po, n))
+        return bytes(out)
+
+    def lincomb2(self, p, a, q, b):
+        n = len(a) // 32
+        out = bytearray(64 * n)
+        bufs = [_buf(x) for x in (p, a, q, b, out)]
+        self._check(self.lib.pa_lincomb2(self.ctx, *[x[0] for x in bufs], n))
+        return bytes(out)
+
+    def point_add(self, p, q, sub=False):
+        n = len(p) // 64
+        out = bytearray(64 * n)
+        bufs = [_buf(x) for x in (p, q, out)]
+        self._check(self.lib.pa_point_add(self.ctx, *[x[0] for x in bufs], n, 1 if sub else 0))
+        return bytes(out)
+
+    def point_encode(self, points, compressed=False, stride=None):
+        n = len(points) // 64
+        stride = stride or (33 if compressed else 65)
+        out = bytearray(stride * n)
+        lens = (ctypes.c_uint32 * max(n, 1))()
+        pp, k0 = _buf(points)
+        po, k1 = _buf(out)
+        self._check(self.lib.pa_point_encode(self.ctx, pp, n, 1 if compressed else 0, po, stride, ctypes.cast(lens, ctypes.c_void_p)))
+        return [bytes(out[i * stride:i * stride + lens[i]]) for i in range(n)]
+
+    def profile_begin(self):
+        self._check(self.lib.pa_profile_begin(self.ctx))
+
+    def profile_end(self):
+        arr = (KernelStat * 64)()
+        cnt = _sz(0)
+        self._check(self.lib.pa_profile_end(self.ctx, ctypes.cast(arr, ctypes.c_void_p), 64, ctypes.byref(cnt)))
+        return {arr[i].name.decode(): {"launches": int(arr[i].launches), "total_ms": float(arr[i].total_ms)}
+                for i in range(min(cnt.value, 64))}
+
+    # device-pointer entry points (asynchronous on the context's stream)
+    def fixed_base_mul_dev(self, d_scalars, d_out, n):
+        self._check(self.lib.pa_fixed_base_mul_dev(self.ctx, d_scalars, d_out, n))
+
+    def var_base_mul_dev(self, d_points, d_scalars, d_out, n):
+        self._check(self.lib.pa_var_base_mul_dev(self.ctx, d_points, d_scalars, d_out, n))
+
+    def double_mul_dev(self, d_a, d_points, d_b, d_out, n):
+        self._check(self.lib.pa_double_mul_dev(self.ctx, d_a, d_points, d_b, d_out, n))
+
+    def lincomb2_dev(self, d_p, d_a, d_q, d_b, d_out, n):
+        self._check(self.lib.pa_lincomb2_dev(self.ctx, d_p, d_a, d_q, d_b, d_out, n))
+
+    def measure_int_peak(self):
+        out = (ctypes.c_double * 4)()
+        self._check(self.lib.pa_measure_int_peak(self.ctx, out))
+        return {"imad_per_s": out[0], "imad_wide_per_s": out[1], "fe_mul_per_s": out[2], "fe_sqr_per_s": out[3]}

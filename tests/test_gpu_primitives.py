@@ -1,0 +1,115 @@
+"""Parity of the CUDA scalar-multiplication path against the oracle, through the
+C ABI, on seeded inputs — bit-exact (integer work)."""
+import random
+
+import pytest
+
+import secp256k1_py as E
+
+pytestmark = pytest.mark.gpu
+N, M = E.N, 2**256
+
+
+def _b(ks):
+    return b"".join(k.to_bytes(32, "big") for k in ks)
+
+
+EDGE_K = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 255, 256, N - 1, N - 2, N, N + 5, M - 1, (N - 1) // 2,
+          int("8" * 64, 16) % N, int("7" * 64, 16), 2**255, 2**128, 1 << 8, 1 << 248, 0xFF << 248]
+
+
+def _scalars(seed, n):
+    rnd = random.Random(seed)
+    return EDGE_K + [rnd.getrandbits(256) for _ in range(n - len(EDGE_K))]
+
+
+def test_fixed_base_parity(engine, oracle):
+    ks = _scalars(21, 4096)
+    got = engine.fixed_base_mul(_b(ks))
+    assert got == oracle.fixed_base_mul(_b(ks))
+    # independent restatement on a few
+    for i in list(range(len(EDGE_K))) + [100, 4095]:
+        assert E.dec64(got[64 * i:64 * i + 64]) == E.mul(ks[i], E.G)
+
+
+def test_var_base_parity(engine, oracle):
+    ks = _scalars(22, 2048)
+    base_k = _scalars(23, 2048)[::-1]          # includes 0 (infinity base) and n (infinity)
+    pts = oracle.fixed_base_mul(_b(base_k))
+    assert engine.var_base_mul(pts, _b(ks)) == oracle.var_base_mul(pts, _b(ks))
+
+
+def test_var_base_edge_scalars_on_one_point(engine, oracle):
+    p = oracle.fixed_base_mul(_b([0xC0FFEE]))
+    ks = EDGE_K
+    pts = p * len(ks)
+    assert engine.var_base_mul(pts, _b(ks)) == oracle.var_base_mul(pts, _b(ks))
+
+
+def test_double_mul_parity(engine, oracle):
+    a, b = _scalars(24, 2048), _scalars(25, 2048)[::-1]
+    pts = oracle.fixed_base_mul(_b(_scalars(26, 2048)))
+    assert engine.double_mul(_b(a), pts, _b(b)) == oracle.double_mul(_b(a), pts, _b(b))
+
+
+def test_double_mul_cancellation(engine, oracle):
+    """a*G + b*(k*G) hitting infinity and the doubling case inside the final add."""
+    k = 0xABCDEF
+    kinv = pow(k, -1, N)
+    p = oracle.fixed_base_mul(_b([k]))
+    a = [5, N - 5, 7, 0, 9]
+    b = [(N - 5) * kinv % N, 5 * kinv % N, 7 * kinv % N, 0, 0]
+    pts = p * len(a)
+    got = engine.double_mul(_b(a), pts, _b(b))
+    assert got == oracle.double_mul(_b(a), pts, _b(b))
+    assert got[:128] == bytes(128)  # the first two cancel to infinity
+
+
+def test_lincomb2_parity(engine, oracle):
+    a, b = _scalars(27, 1024), _scalars(28, 1024)[::-1]
+    p = oracle.fixed_base_mul(_b(_scalars(29, 1024)))
+    q = oracle.fixed_base_mul(_b(_scalars(30, 1024)[::-1]))
+    assert engine.lincomb2(p, _b(a), q, _b(b)) == oracle.lincomb2(p, _b(a), q, _b(b))
+    # same base twice, and base + its negative
+    assert engine.lincomb2(p, _b(a), p, _b(b)) == oracle.lincomb2(p, _b(a), p, _b(b))
+    negp = oracle.point_add(bytes(len(p)), p, sub=True)
+    assert engine.lincomb2(p, _b(a), negp, _b(a)) == bytes(len(p))
+
+
+def test_point_add_sub_encode(engine, oracle):
+    p = oracle.fixed_base_mul(_b(_scalars(31, 512)))
+    q = oracle.fixed_base_mul(_b(_scalars(32, 512)[::-1]))
+    assert engine.point_add(p, q) == oracle.point_add(p, q)
+    assert engine.point_add(p, q, sub=True) == oracle.point_add(p, q, sub=True)
+    assert engine.point_add(p, p) == oracle.point_add(p, p)
+    assert engine.point_add(p, p, sub=True) == bytes(len(p))
+    assert engine.point_encode(p) == oracle.point_encode(p)
+    assert engine.point_encode(p, compressed=True) == oracle.point_encode(p, compressed=True)
+
+
+def test_empty_and_ragged_batches(engine, oracle):
+    assert engine.fixed_base_mul(b"") == b""
+    for n in (1, 31, 33, 127, 129, 1000):
+        ks = _scalars(40 + n, max(n, len(EDGE_K)))[:n]
+        assert engine.fixed_base_mul(_b(ks)) == oracle.fixed_base_mul(_b(ks))
+
+
+def test_full_size_properties(engine, oracle):
+    """2^20 scalars (BASELINE config 3): linearity k*G + k'*G == (k+k')*G through
+    three different code paths, plus a seeded sample against libcrypto."""
+    n = 1 << 20
+    rnd = random.Random(99)
+    k1 = [rnd.getrandbits(256) for _ in range(n)]
+    k2 = [rnd.getrandbits(256) for _ in range(n)]
+    g1 = engine.fixed_base_mul(_b(k1))
+    g2 = engine.fixed_base_mul(_b(k2))
+    gs = engine.fixed_base_mul(_b([(a + b) % N for a, b in zip(k1, k2)]))
+    assert engine.point_add(g1, g2) == gs
+    # variable base: k2 * (k1 * G) == (k1 * k2) * G
+    v = engine.var_base_mul(g1, _b(k2))
+    assert v == engine.fixed_base_mul(_b([(a % N) * (b % N) % N for a, b in zip(k1, k2)]))
+    idx = rnd.sample(range(n), 512)
+    sub_k = _b([k1[i] for i in idx])
+    assert b"".join(g1[64 * i:64 * i + 64] for i in idx) == oracle.fixed_base_mul(sub_k)
+    sub_p = b"".join(g1[64 * i:64 * i + 64] for i in idx)
+    assert b"".join(v[64 * i:64 * i + 64] for i in idx) == oracle.var_base_mul(sub_p, _b([k2[i] for i in idx]))

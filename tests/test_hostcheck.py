@@ -1,0 +1,129 @@
+"""Limb-level check of the device arithmetic headers (pa_fe.cuh, pa_sc.cuh,
+pa_ec.cuh, pa_smul.cuh) compiled by g++ with the PTX carry flag emulated
+(tests/hostcheck/hostcheck.cpp) against Python integers.  This is a unit test of
+the algorithms; the product library contains device code only."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+import secp256k1_py as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HC = os.path.join(ROOT, "tests", "hostcheck")
+P, N, M = E.P, E.N, 2**256
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(HC, "libhostcheck.so")
+    subprocess.run(["g++", "-O2", "-x", "c++", "-std=c++17", "-fPIC", "-shared",
+                    "-I" + os.path.join(ROOT, "privacy-auction_b200", "csrc"), "-o", so,
+                    os.path.join(HC, "hostcheck.cpp")], check=True)
+    return ctypes.CDLL(so)
+
+
+def b32(x):
+    return x.to_bytes(32, "big")
+
+
+EDGE = [0, 1, 2, P - 1, P, P + 1, M - 1, M - 2, P - 2, 977, 2**32, 2**32 + 977, M - 2**32, 2**255, 2**128 - 1,
+        M - 2**224] + [(M - 1) & ~((1 << (32 * i + 32)) - (1 << (32 * i))) for i in range(8)] + \
+       [((1 << (32 * i + 32)) - (1 << (32 * i))) for i in range(8)]
+
+
+def test_field_ops(hc):
+    rnd = random.Random(1)
+    vals = EDGE + [rnd.getrandbits(256) for _ in range(120)]
+
+    def op(o, a, b=0):
+        out = ctypes.create_string_buffer(32)
+        hc.hc_fe_op(o, b32(a), b32(b), out)
+        return int.from_bytes(out.raw, "big")
+
+    def mp(a, b, sqr=0):
+        out = ctypes.create_string_buffer(64)
+        hc.hc_mp_mul8(b32(a), b32(b), out, sqr)
+        return int.from_bytes(out.raw, "big")
+
+    for a in vals:
+        for b in rnd.sample(vals, 12) + EDGE[:16]:
+            assert mp(a, b) == a * b
+            assert op(0, a, b) == a * b % P
+            assert op(2, a, b) == (a + b) % P
+            assert op(3, a, b) == (a - b) % P
+            assert op(8, a, b) == int((a - b) % P == 0)
+        assert mp(a, a, 1) == a * a
+        assert op(1, a) == a * a % P
+        assert op(5, a) == (-a) % P
+        assert op(6, a) == a % P
+        assert op(7, a) == int(a % P == 0)
+    for a in vals[:40]:
+        if a % P:
+            assert op(4, a) == pow(a, P - 2, P)
+
+
+def test_scalar_ops(hc):
+    rnd = random.Random(2)
+    vals = [0, 1, 2, N - 1, N - 2, N, N + 1, M - 1, 2**255, 2**128, N // 2] + [rnd.getrandbits(256) for _ in range(100)]
+
+    def op(o, a, b=0):
+        out = ctypes.create_string_buffer(32)
+        hc.hc_sc_op(o, b32(a), b32(b), out)
+        return int.from_bytes(out.raw, "big")
+
+    for a in vals:
+        for b in rnd.sample(vals, 10):
+            ar, br = a % N, b % N
+            assert op(0, a, b) == ar * br % N
+            assert op(1, a, b) == (ar + br) % N
+            assert op(2, a, b) == (ar - br) % N
+        assert op(3, a) == (-a) % N
+
+
+def test_group_and_scalar_mult(hc):
+    rnd = random.Random(3)
+
+    def fixed(k):
+        out = ctypes.create_string_buffer(64)
+        hc.hc_fixed_base(b32(k), out)
+        return E.dec64(out.raw)
+
+    def var(p, k):
+        out = ctypes.create_string_buffer(64)
+        hc.hc_var_base(E.enc64(p), b32(k), out)
+        return E.dec64(out.raw)
+
+    def lin(p, a, q, b):
+        out = ctypes.create_string_buffer(64)
+        hc.hc_lincomb2(E.enc64(p), b32(a), E.enc64(q), b32(b), out)
+        return E.dec64(out.raw)
+
+    def padd(p, q, m):
+        out = ctypes.create_string_buffer(64)
+        hc.hc_point_add(E.enc64(p), E.enc64(q), out, m)
+        return E.dec64(out.raw)
+
+    ks = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 255, 256, N - 1, N - 2, N, N + 5, M - 1, (N - 1) // 2,
+          int("8" * 64, 16) % N, int("7" * 64, 16)] + [rnd.getrandbits(256) for _ in range(12)]
+    for k in ks:
+        assert fixed(k) == E.mul(k, E.G)
+    pts = [E.G, E.mul(2, E.G), E.mul(12345, E.G), E.neg(E.G), E.INF, E.mul(N - 1, E.G)] + \
+          [E.mul(rnd.getrandbits(256), E.G) for _ in range(3)]
+    for p in pts:
+        for q in pts:
+            for m in (0, 1):
+                assert padd(p, q, m) == E.add(p, q)
+            assert hc.hc_jac_eq_aff(E.enc64(p), E.enc64(q)) == int(p == q)
+    for p in pts[:6]:
+        for k in ks[:20] + ks[-3:]:
+            assert var(p, k) == E.mul(k, p)
+    for _ in range(12):
+        p, q, a, b = rnd.choice(pts), rnd.choice(pts), rnd.choice(ks), rnd.choice(ks)
+        assert lin(p, a, q, b) == E.lincomb(a, p, b, q)
+    p = pts[2]
+    for a, b in [(5, N - 5), (1, 1), (0, 0), (7, 0), (0, 9), (N - 1, 1), (8, 8)]:
+        assert lin(p, a, p, b) == E.mul(a + b, p)
+        assert lin(p, a, E.neg(p), b) == E.mul(a - b, p)
