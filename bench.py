@@ -68,37 +68,70 @@ def run_ecmul_ref(threads, pairs, seed=1):
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock, power and throttle reasons of one GPU DURING the timed
+    region (NVML every 20 ms; nvidia-smi every 200 ms if NVML is unavailable)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+        self.gpu, self.stop_flag = gpu_index, threading.Event()
+        self.sm, self.mx, self.power, self.reasons, self.how = [], [], [], set(), "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # torch honours CUDA_VISIBLE_DEVICES; NVML does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nv, self.how = None, "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [c.strip() for c in out.split(",")]
+        self.sm.append(float(r[1]))
+        self.mx.append(float(r[2]))
+        for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+            if val.lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self._sample_nvml() if self.nv else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nv else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "how": self.how}
 
 
 def reference_arm(args, rank, world):
@@ -133,7 +166,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_KIND, help="scalar mults per kind per GPU per step (default 2^20)")
