@@ -106,6 +106,94 @@ int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, 
  * zero padded; lens[i] receives the encoded length. */
 int pa_point_encode(pa_ctx *ctx, const uint8_t *points, size_t n, int compressed, uint8_t *out, size_t stride, uint32_t *lens);
 
+/* ---- Fiat-Shamir challenge ---------------------------------------------------
+ * out[i] = SHA-256( enc(g) || enc(points[i][0]) .. enc(points[i][k-1]) || LE64(ids[i]) )
+ * read big-endian, mod the group order; enc = 04||X||Y, or the single byte 00
+ * for infinity.  The generator is prepended by the engine, as the reference's
+ * points[] arrays do.  k <= 32.   SHA256inNIZKPoKDLog / PoWFCom / PoWFStage1 /
+ * PoWFStage2, SEAL/hash.cpp:8-53, 55-104, 106-162, 164-228 */
+int pa_challenge(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_t *ids, uint8_t *out, size_t n);
+int pa_challenge_dev(pa_ctx *ctx, const uint8_t *d_points, size_t k, const uint64_t *d_ids, uint8_t *d_out, size_t n);
+
+/* ---- the four NIZK proofs, batched ----------------------------------------------
+ * Record layouts (points 64 B, scalars 32 B, field order of SEAL/types.h:13-93):
+ *   PoKDLog   eps | rho                                               96 B
+ *   PoWFCom   eps11 eps12 eps21 eps22 | rho1 rho2 ch2                352 B
+ *   Stage1    eps11..eps14 eps21..eps24 | rho11 rho12 rho21 rho22 ch2   672 B
+ *   Stage2    eps11 eps12 eps13 eps11' eps12' eps13' eps21 eps22 eps23 eps21' eps22'
+ *             eps23' eps31 eps32 eps31' eps32' | rho11 rho12 rho13 rho21 rho22 rho23
+ *             rho31 rho32 ch2 ch3                                   1344 B
+ * Statement points are n x k contiguous points in the order of the reference's
+ * parameter lists.  A prover takes the values the reference would draw with
+ * BN_rand_range as an explicit array `rnd` (n x draws x 32 B, in the reference's
+ * draw order), which makes it a pure function of its
+ * inputs; pa_rng_fill produces such arrays from a seed.  A verifier writes one
+ * byte per proof (1 = every check holds); like the reference it evaluates all
+ * checks, no early exit (SEAL/bidder.cpp:244-298). */
+
+/* genNIZKPoKDLog SEAL/bidder.cpp:90-107; X = g^x; rnd: v */
+int pa_pokdlog_prove(pa_ctx *ctx, const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+int pa_pokdlog_prove_dev(pa_ctx *ctx, const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+/* verNIZKPoKDLog SEAL/bidder.cpp:119-136 */
+int pa_pokdlog_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *X, const uint64_t *ids, uint8_t *verdict, size_t n);
+int pa_pokdlog_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *X, const uint64_t *ids, uint8_t *verdict, size_t n);
+
+/* genNIZKPoWFCom SEAL/bidder.cpp:149-226; stmt = (phi, A, B); rnd: r1, then
+ * bit 0: ch2, rho2 / bit 1: ch1, rho1 */
+int pa_powfcom_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *alpha, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+int pa_powfcom_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *alpha, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+/* verNIZKPoWFCom SEAL/bidder.cpp:241-299 */
+int pa_powfcom_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+int pa_powfcom_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+
+/* genNIZKPoWFStage1 SEAL/bidder.cpp:318-451; stmt = (b, X, Y, R, c, A, B);
+ * secrets = (x, alpha); rnd: r11, r12, then bit 0: rho21, rho22, ch2 / bit 1: rho11, rho12, ch1 */
+int pa_stage1_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+int pa_stage1_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+/* verNIZKPoWFStage1 SEAL/bidder.cpp:470-571 */
+int pa_stage1_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+int pa_stage1_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+
+/* genNIZKPoWFStage2 SEAL/bidder.cpp:598-890; stmt = (Bi, Xi, Ri, Bj, Xj, Rj, Ci, A, B, Yi, Yj);
+ * secrets = (xi, xj, alpha); bi/bj as the reference's int arguments (bi == 1 requires
+ * bj == 1, the assert at :604); rnd: the 11 draws of :643-655 / :692-699 / :749-756,
+ * including the ones the reference discards */
+int pa_stage2_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+int pa_stage2_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+/* verNIZKPoWFStage2 SEAL/bidder.cpp:913-1101 */
+int pa_stage2_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+int pa_stage2_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+
+/* ---- round logic -----------------------------------------------------------------------
+ * out[i] = (phi, A, B) = (g^(alpha*beta) * g^bit, g^alpha, g^beta).  Bidder::commitBid,
+ * SEAL/bidder.cpp:1131-1138 */
+int pa_commit_points(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n);
+int pa_commit_points_dev(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n);
+
+/* Y[id] = sum_{i<id} X[i] - sum_{i>id} X[i] for every id of one auction, in one
+ * prefix/suffix scan.  Bidder::roundTwo, SEAL/bidder.cpp:1286-1299 (there: O(n^2)
+ * additions, repeated by every bidder).  _batch / _dev: many auctions at once,
+ * auction s owns points offsets[s] .. offsets[s+1] (offsets == NULL: one auction). */
+int pa_y_scan(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, size_t n);
+int pa_y_scan_batch(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, const uint32_t *offsets, size_t nseg);
+int pa_y_scan_dev(pa_ctx *ctx, const uint8_t *d_X, uint8_t *d_Y, const uint32_t *d_offsets, size_t nseg, size_t npoints);
+
+/* *is_inf = (sum_i B[i] is the point at infinity).  Bidder::roundThree,
+ * SEAL/bidder.cpp:1393-1397 */
+int pa_point_sum_is_inf(pa_ctx *ctx, const uint8_t *B, size_t n, int *is_inf);
+int pa_point_sum_is_inf_batch(pa_ctx *ctx, const uint8_t *B, const uint32_t *offsets, size_t nseg, int32_t *flags);
+int pa_point_sum_is_inf_dev(pa_ctx *ctx, const uint8_t *d_B, const uint32_t *d_offsets, size_t nseg, size_t npoints, int32_t *d_flags);
+
+/* ---- seeded randomness ------------------------------------------------------------------
+ * The reference draws from OpenSSL's DRBG and is not reproducible.
+ * The PA stream replaces BN_rand_range(., order) (SEAL/bidder.cpp:97 and 44 more sites):
+ *   draw(seed, stream, ctr) = SHA-256("PAv1" || LE64 seed || LE64 stream || LE64 ctr)
+ * as a big-endian integer, redrawn with ctr+1 while >= order.  Item i receives
+ * per_item consecutive draws of stream streams[i] starting at counters[i];
+ * counters[i] is advanced. */
+int pa_rng_fill(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n);
+int pa_rng_fill_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *d_streams, uint64_t *d_counters, size_t per_item, uint8_t *d_out, size_t n);
+
 /* ---- measurement ----------------------------------------------------------
  * Per-kernel device timing: between pa_profile_begin and pa_profile_end every
  * kernel the context launches is bracketed by CUDA events on the context's

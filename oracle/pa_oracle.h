@@ -42,6 +42,34 @@ int po_point_add(const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, int
 /* EC_POINT_point2oct, SEAL/hash.cpp:27-29 */
 int po_point_encode(const uint8_t *points, size_t n, int compressed, uint8_t *out, size_t stride, uint32_t *lens);
 
+
+/* ---- Fiat-Shamir challenge, SEAL/hash.cpp:8-228: points WITHOUT the generator
+ * (it is prepended, as the reference's points[] arrays do); k points per item */
+int po_challenge(const uint8_t *points, size_t k, const uint64_t *ids, uint8_t *out, size_t n);
+
+/* ---- the four NIZK proofs.  Layouts and argument order as in include/pa_engine.h.
+ * rnd holds the values the reference would draw with BN_rand_range, in draw
+ * order, so a prover is a pure function. */
+int po_pokdlog_prove(const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+int po_pokdlog_verify(const uint8_t *proofs, const uint8_t *X, const uint64_t *ids, uint8_t *verdict, size_t n);
+int po_powfcom_prove(const uint8_t *stmt, const uint8_t *alpha, const uint8_t *bits, const uint64_t *ids,
+                     const uint8_t *rnd, uint8_t *proofs, size_t n);
+int po_powfcom_verify(const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+int po_stage1_prove(const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids,
+                    const uint8_t *rnd, uint8_t *proofs, size_t n);
+int po_stage1_verify(const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+int po_stage2_prove(const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj,
+                    const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
+int po_stage2_verify(const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n);
+
+/* ---- round logic */
+/* phi = g^(alpha*beta) * g^bit, A = g^alpha, B = g^beta; out = n x (phi, A, B).  SEAL/bidder.cpp:1131-1138 */
+int po_commit_points(const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n);
+/* Y_id = sum_{i<id} X_i - sum_{i>id} X_i for every id, the reference's O(n^2) loops.  SEAL/bidder.cpp:1286-1299 */
+int po_y_scan(const uint8_t *X, uint8_t *Y, size_t n);
+/* *is_inf = (sum_i b_i == infinity).  SEAL/bidder.cpp:1393-1397 */
+int po_point_sum_is_inf(const uint8_t *b, size_t n, int *is_inf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,10 +30,14 @@ struct pa_ctx {
 
 enum {
   PA_K_COMB = 0, PA_K_FIXED, PA_K_VAR, PA_K_DOUBLE, PA_K_LINCOMB2, PA_K_POINT_ADD, PA_K_NORMALIZE, PA_K_ENCODE,
-  PA_K_PEAK, PA_K_COUNT
+  PA_K_PEAK, PA_K_VDERIVE, PA_K_VCHECKS, PA_K_VERDICT, PA_K_POPS, PA_K_PRESPOND, PA_K_CHALLENGE, PA_K_RNG,
+  PA_K_COMMIT, PA_K_YSCAN, PA_K_SUMINF, PA_K_COUNT
 };
 static const char *const PA_K_NAMES[PA_K_COUNT] = {"k_comb", "k_fixed_base", "k_var_base", "k_double_mul", "k_lincomb2",
-                                                   "k_point_add", "k_normalize", "k_encode", "k_peak"};
+                                                   "k_point_add", "k_normalize", "k_encode", "k_peak", "k_verify_derive",
+                                                   "k_verify_checks", "k_verdict", "k_prove_ops", "k_prove_respond",
+                                                   "k_challenge", "k_rng_fill", "k_commit_points", "k_y_scan",
+                                                   "k_point_sum_is_inf"};
 
 static cudaEvent_t ev_get(pa_ctx *ctx) {
   if (!ctx->ev_pool.empty()) {
@@ -204,14 +208,14 @@ static int work_reserve(pa_ctx *ctx, size_t n) { return ensure(ctx, &ctx->d_work
 static u32 *work_jac(pa_ctx *ctx) { return (u32 *)ctx->d_work; }
 static u32 *work_prefix(pa_ctx *ctx, size_t n) { return (u32 *)(ctx->d_work + n * 96); }
 
-static int normalize_to(pa_ctx *ctx, unsigned char *d_out, size_t n) {
+static int normalize_to(pa_ctx *ctx, unsigned char *d_out, size_t n, int nper = 1, size_t stride = 64) {
   // points per thread: amortise the ~270-multiplication inversion once the
   // batch is large enough to keep every SM busy anyway
   size_t per = n / (148 * 1024);
   if (per < 1) per = 1;
   if (per > 16) per = 16;
   size_t T = (n + per - 1) / per;
-  PA_LAUNCH(ctx, PA_K_NORMALIZE, k_normalize<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(work_jac(ctx), work_prefix(ctx, n), d_out, (int)n, (int)T));
+  PA_LAUNCH(ctx, PA_K_NORMALIZE, k_normalize<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(work_jac(ctx), work_prefix(ctx, n), d_out, (int)n, (int)T, nper, stride));
   return PA_OK;
 }
 
@@ -449,6 +453,237 @@ int pa_measure_int_peak(pa_ctx *ctx, double out[4]) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return PA_OK;
+}
+
+}  // extern "C"
+
+
+// =====================================================================================
+// Proofs, challenges, round logic
+// =====================================================================================
+namespace {
+
+// Staging for the host-buffer entry points: every argument gets a 256-byte aligned
+// slot in the stage arena; inputs are uploaded before and outputs downloaded after
+// the device-pointer implementation runs.
+struct HArg {
+  const void *in;
+  void *out;
+  size_t bytes;
+};
+template <typename F>
+int staged(pa_ctx *ctx, const HArg *args, int nargs, F run) {
+  size_t total = 1024;
+  for (int i = 0; i < nargs; ++i) total += align_up(args[i].bytes, 256) + 256;
+  int rc = stage_reserve(ctx, total);
+  if (rc) return rc;
+  Stage s(ctx);
+  unsigned char *d[16];
+  for (int i = 0; i < nargs; ++i) {
+    d[i] = s.take(args[i].bytes ? args[i].bytes : 1);
+    if (args[i].in && args[i].bytes)
+      PA_CUDA(ctx, cudaMemcpyAsync(d[i], args[i].in, args[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if ((rc = run(d))) return rc;
+  for (int i = 0; i < nargs; ++i)
+    if (args[i].out && args[i].bytes)
+      PA_CUDA(ctx, cudaMemcpyAsync(args[i].out, d[i], args[i].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+// work arena for proofs: [ Jacobian scratch | prefix | derived scalars | check bytes ]
+template <int KIND, int NCHK>
+int verify_dev(pa_ctx *ctx, const unsigned char *proofs, size_t pstride, const unsigned char *stmts, const u64 *ids,
+               unsigned char *verdict, size_t n) {
+  if (n == 0) return PA_OK;
+  size_t need = n * 32 + n * NCHK + 512;
+  int rc = ensure(ctx, &ctx->d_work, &ctx->work_bytes, need);
+  if (rc) return rc;
+  u32 *derived = (u32 *)ctx->d_work;
+  unsigned char *chk = ctx->d_work + align_up(n * 32, 256);
+  PA_LAUNCH(ctx, PA_K_VDERIVE, (k_verify_derive<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, pstride, stmts, ids, derived, (int)n)));
+  PA_LAUNCH(ctx, PA_K_VCHECKS, (k_verify_checks<KIND, NCHK><<<grid_for(n * NCHK), PA_BLOCK, 0, ctx->stream>>>(proofs, pstride, stmts, derived, ctx->d_comb, chk, (int)n)));
+  PA_LAUNCH(ctx, PA_K_VERDICT, (k_verdict<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(chk, NCHK, (int)n, verdict)));
+  return PA_OK;
+}
+
+template <int KIND>
+int prove_dev(pa_ctx *ctx, const unsigned char *stmts, const unsigned char *secrets, const unsigned char *b0,
+              const unsigned char *b1, const u64 *ids, const unsigned char *rnd, unsigned char *proofs, size_t pstride,
+              size_t n) {
+  typedef proof_kind<KIND> K;
+  if (n == 0) return PA_OK;
+  size_t m = n * K::NEPS;
+  int rc = work_reserve(ctx, m);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_POPS, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n)));
+  if ((rc = normalize_to(ctx, proofs, m, K::NEPS, pstride))) return rc;
+  PA_LAUNCH(ctx, PA_K_PRESPOND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, pstride, stmts, ids, secrets, rnd, b0, b1, (int)n)));
+  return PA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- device-pointer entry points -------------------------------------------------------
+int pa_pokdlog_prove_dev(pa_ctx *ctx, const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (X && x && ids && rnd && proofs)) && n < (1u << 26));
+  return prove_dev<PA_POK>(ctx, X, x, nullptr, nullptr, (const u64 *)ids, rnd, proofs, 96, n);
+}
+int pa_pokdlog_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *X, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && X && ids && verdict)) && n < (1u << 26));
+  return verify_dev<PA_POK, 1>(ctx, proofs, 96, X, (const u64 *)ids, verdict, n);
+}
+int pa_powfcom_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *alpha, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && alpha && bits && ids && rnd && proofs)) && n < (1u << 26));
+  return prove_dev<PA_COM>(ctx, stmt, alpha, bits, nullptr, (const u64 *)ids, rnd, proofs, 352, n);
+}
+int pa_powfcom_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
+  return verify_dev<PA_COM, 4>(ctx, proofs, 352, stmt, (const u64 *)ids, verdict, n);
+}
+int pa_stage1_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)) && n < (1u << 26));
+  return prove_dev<PA_S1>(ctx, stmt, secrets, bits, nullptr, (const u64 *)ids, rnd, proofs, 672, n);
+}
+int pa_stage1_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
+  return verify_dev<PA_S1, 8>(ctx, proofs, 672, stmt, (const u64 *)ids, verdict, n);
+}
+int pa_stage2_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bi && bj && ids && rnd && proofs)) && n < (1u << 26));
+  return prove_dev<PA_S2>(ctx, stmt, secrets, bi, bj, (const u64 *)ids, rnd, proofs, 1344, n);
+}
+int pa_stage2_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
+  return verify_dev<PA_S2, 16>(ctx, proofs, 1344, stmt, (const u64 *)ids, verdict, n);
+}
+
+int pa_commit_points_dev(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (alpha && beta && bits && out)) && n < (1u << 26));
+  if (n == 0) return PA_OK;
+  int rc = work_reserve(ctx, 3 * n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_COMMIT, (k_commit_points<<<grid_for(3 * n), PA_BLOCK, 0, ctx->stream>>>(alpha, beta, bits, ctx->d_comb, work_jac(ctx), (int)n)));
+  return normalize_to(ctx, out, 3 * n);
+}
+
+int pa_y_scan_dev(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, const uint32_t *offsets, size_t nseg, size_t npoints) {
+  PA_ARGCHECK(ctx, ctx && (npoints == 0 || (X && Y)) && npoints < (1u << 28) && nseg >= 1);
+  if (npoints == 0) return PA_OK;
+  int rc = work_reserve(ctx, npoints);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)nseg, PA_SCAN_T, 0, ctx->stream>>>(X, offsets, (int)npoints, work_jac(ctx))));
+  return normalize_to(ctx, Y, npoints);
+}
+
+int pa_point_sum_is_inf_dev(pa_ctx *ctx, const uint8_t *B, const uint32_t *offsets, size_t nseg, size_t npoints, int32_t *flags) {
+  PA_ARGCHECK(ctx, ctx && flags && (npoints == 0 || B) && nseg >= 1);
+  PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<(unsigned)nseg, PA_SCAN_T, 0, ctx->stream>>>(B, offsets, (int)npoints, flags)));
+  return PA_OK;
+}
+
+int pa_challenge_dev(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_t *ids, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && k <= 32 && (n == 0 || (ids && out && (points || k == 0))));
+  if (n == 0) return PA_OK;
+  PA_LAUNCH(ctx, PA_K_CHALLENGE, (k_challenge<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(points, (int)k, (const u64 *)ids, out, (int)n)));
+  return PA_OK;
+}
+
+int pa_rng_fill_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
+  if (n == 0 || per_item == 0) return PA_OK;
+  PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(seed, (const u64 *)streams, (u64 *)counters, (int)per_item, out, (int)n)));
+  return PA_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------
+int pa_pokdlog_prove(pa_ctx *ctx, const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (X && x && ids && rnd && proofs)));
+  HArg a[] = {{X, 0, n * 64}, {x, 0, n * 32}, {ids, 0, n * 8}, {rnd, 0, n * 32}, {0, proofs, n * 96}};
+  return staged(ctx, a, 5, [&](unsigned char **d) { return pa_pokdlog_prove_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], d[4], n); });
+}
+int pa_pokdlog_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *X, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && X && ids && verdict)));
+  HArg a[] = {{proofs, 0, n * 96}, {X, 0, n * 64}, {ids, 0, n * 8}, {0, verdict, n}};
+  return staged(ctx, a, 4, [&](unsigned char **d) { return pa_pokdlog_verify_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], n); });
+}
+int pa_powfcom_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *alpha, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && alpha && bits && ids && rnd && proofs)));
+  HArg a[] = {{stmt, 0, n * 192}, {alpha, 0, n * 32}, {bits, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 96}, {0, proofs, n * 352}};
+  return staged(ctx, a, 6, [&](unsigned char **d) { return pa_powfcom_prove_dev(ctx, d[0], d[1], d[2], (const uint64_t *)d[3], d[4], d[5], n); });
+}
+int pa_powfcom_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)));
+  HArg a[] = {{proofs, 0, n * 352}, {stmt, 0, n * 192}, {ids, 0, n * 8}, {0, verdict, n}};
+  return staged(ctx, a, 4, [&](unsigned char **d) { return pa_powfcom_verify_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], n); });
+}
+int pa_stage1_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)));
+  HArg a[] = {{stmt, 0, n * 448}, {secrets, 0, n * 64}, {bits, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 160}, {0, proofs, n * 672}};
+  return staged(ctx, a, 6, [&](unsigned char **d) { return pa_stage1_prove_dev(ctx, d[0], d[1], d[2], (const uint64_t *)d[3], d[4], d[5], n); });
+}
+int pa_stage1_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)));
+  HArg a[] = {{proofs, 0, n * 672}, {stmt, 0, n * 448}, {ids, 0, n * 8}, {0, verdict, n}};
+  return staged(ctx, a, 4, [&](unsigned char **d) { return pa_stage1_verify_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], n); });
+}
+int pa_stage2_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bi && bj && ids && rnd && proofs)));
+  for (size_t i = 0; i < n; ++i)
+    if (bi[i] && !bj[i]) return pa_fail(ctx, PA_EINVAL, "stage 2: bi == 1 requires bj == 1 (assert at SEAL/bidder.cpp:604)");
+  HArg a[] = {{stmt, 0, n * 704}, {secrets, 0, n * 96}, {bi, 0, n}, {bj, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 352}, {0, proofs, n * 1344}};
+  return staged(ctx, a, 7, [&](unsigned char **d) { return pa_stage2_prove_dev(ctx, d[0], d[1], d[2], d[3], (const uint64_t *)d[4], d[5], d[6], n); });
+}
+int pa_stage2_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)));
+  HArg a[] = {{proofs, 0, n * 1344}, {stmt, 0, n * 704}, {ids, 0, n * 8}, {0, verdict, n}};
+  return staged(ctx, a, 4, [&](unsigned char **d) { return pa_stage2_verify_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], n); });
+}
+int pa_commit_points(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (alpha && beta && bits && out)));
+  HArg a[] = {{alpha, 0, n * 32}, {beta, 0, n * 32}, {bits, 0, n}, {0, out, n * 192}};
+  return staged(ctx, a, 4, [&](unsigned char **d) { return pa_commit_points_dev(ctx, d[0], d[1], d[2], d[3], n); });
+}
+int pa_y_scan(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (X && Y)));
+  if (n == 0) return PA_OK;
+  HArg a[] = {{X, 0, n * 64}, {0, Y, n * 64}};
+  return staged(ctx, a, 2, [&](unsigned char **d) { return pa_y_scan_dev(ctx, d[0], d[1], nullptr, 1, n); });
+}
+int pa_y_scan_batch(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, const uint32_t *offsets, size_t nseg) {
+  PA_ARGCHECK(ctx, ctx && offsets && nseg >= 1);
+  size_t n = offsets[nseg];
+  PA_ARGCHECK(ctx, n == 0 || (X && Y));
+  if (n == 0) return PA_OK;
+  HArg a[] = {{X, 0, n * 64}, {0, Y, n * 64}, {offsets, 0, (nseg + 1) * 4}};
+  return staged(ctx, a, 3, [&](unsigned char **d) { return pa_y_scan_dev(ctx, d[0], d[1], (const uint32_t *)d[2], nseg, n); });
+}
+int pa_point_sum_is_inf(pa_ctx *ctx, const uint8_t *B, size_t n, int *is_inf) {
+  PA_ARGCHECK(ctx, ctx && is_inf && (n == 0 || B));
+  int32_t flag = 0;
+  HArg a[] = {{B, 0, n * 64}, {0, &flag, 4}};
+  int rc = staged(ctx, a, 2, [&](unsigned char **d) { return pa_point_sum_is_inf_dev(ctx, d[0], nullptr, 1, n, (int32_t *)d[1]); });
+  *is_inf = flag;
+  return rc;
+}
+int pa_point_sum_is_inf_batch(pa_ctx *ctx, const uint8_t *B, const uint32_t *offsets, size_t nseg, int32_t *flags) {
+  PA_ARGCHECK(ctx, ctx && offsets && flags && nseg >= 1);
+  size_t n = offsets[nseg];
+  HArg a[] = {{B, 0, n * 64}, {offsets, 0, (nseg + 1) * 4}, {0, flags, nseg * 4}};
+  return staged(ctx, a, 3, [&](unsigned char **d) { return pa_point_sum_is_inf_dev(ctx, d[0], (const uint32_t *)d[1], nseg, n, (int32_t *)d[2]); });
+}
+int pa_challenge(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_t *ids, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && k <= 32 && (n == 0 || (ids && out)));
+  HArg a[] = {{points, 0, n * k * 64}, {ids, 0, n * 8}, {0, out, n * 32}};
+  return staged(ctx, a, 3, [&](unsigned char **d) { return pa_challenge_dev(ctx, d[0], k, (const uint64_t *)d[1], d[2], n); });
+}
+int pa_rng_fill(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
+  HArg a[] = {{streams, 0, n * 8}, {counters, counters, n * 8}, {0, out, n * per_item * 32}};
+  return staged(ctx, a, 3, [&](unsigned char **d) { return pa_rng_fill_dev(ctx, seed, (const uint64_t *)d[0], (uint64_t *)d[1], per_item, d[2], n); });
 }
 
 }  // extern "C"

@@ -9,7 +9,7 @@
 // among the points of a thread (Montgomery's trick) — the reference pays one
 // inversion per point inside EC_POINT_point2oct (25 us each).
 #pragma once
-#include "pa_smul.cuh"
+#include "pa_proof.cuh"
 
 #define PA_BLOCK 128
 
@@ -169,8 +169,11 @@ k_point_add(const unsigned char *p, const unsigned char *q, u32 *jout, int n, in
 
 // ---- Jacobian -> 64-byte affine, one inversion per thread ------------------------
 // Thread t owns points t, t + T, t + 2T, ... (coalesced across the warp).
+// Output slot of point idx: out + (idx / nper) * stride + (idx % nper) * 64, so the
+// same kernel writes plain arrays (nper = 1, stride = 64) and the eps fields of
+// proof records (nper = eps per proof, stride = record size).
 __global__ void __launch_bounds__(PA_BLOCK)
-k_normalize(const u32 *jin, u32 *prefix, unsigned char *out, int n, int T) {
+k_normalize(const u32 *jin, u32 *prefix, unsigned char *out, int n, int T, int nper, size_t stride) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   fe acc, z;
@@ -203,7 +206,7 @@ k_normalize(const u32 *jin, u32 *prefix, unsigned char *out, int n, int T) {
       fe_mul(inv, inv, p.Z);
       jac_to_aff_with_zinv(a, p, zi);
     }
-    st_aff(out + 64 * (size_t)idx, a);
+    st_aff(out + (size_t)(idx / nper) * stride + (size_t)(idx % nper) * 64, a);
   }
 }
 
@@ -278,4 +281,207 @@ __global__ void k_peak_fe(u32 *sink, int iters, int sqr) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) s ^= x.v[i] ^ y.v[i];
   if (s == 0x12345u) sink[0] = s;
+}
+
+
+// ---- proofs: one thread per operation -----------------------------------------------
+// verifier step 1: challenge + unpublished challenge share, one thread per proof
+template <int KIND>
+__global__ void __launch_bounds__(PA_BLOCK)
+k_verify_derive(const unsigned char *proofs, size_t pstride, const unsigned char *stmts, const u64 *ids, u32 *derived, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sc ch1;
+  verify_derive<KIND>(ch1, proofs + pstride * i, stmts + (size_t)proof_kind<KIND>::NSTMT * 64 * i, ids[i]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) derived[8 * (size_t)i + k] = ch1.v[k];
+}
+// verifier step 2: thread t owns check j = t / n of proof i = t % n (check-major: a warp
+// runs the same check, hence the same shape, for 32 proofs)
+template <int KIND, int NCHK>
+__global__ void __launch_bounds__(PA_BLOCK)
+k_verify_checks(const unsigned char *proofs, size_t pstride, const unsigned char *stmts, const u32 *derived,
+                const u32 *__restrict__ comb, unsigned char *chk, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * NCHK) return;
+  int j = t / n, i = t % n;
+  sc ch1;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ch1.v[k] = derived[8 * (size_t)i + k];
+  bool ok = verify_check_one<KIND>(j, proofs + pstride * i, stmts + (size_t)proof_kind<KIND>::NSTMT * 64 * i, ch1, comb);
+  chk[t] = ok ? 1 : 0;
+}
+// verifier step 3: verdict = AND of all checks (no early exit, as SEAL/bidder.cpp:244-298)
+__global__ void k_verdict(const unsigned char *chk, int nchk, int n, unsigned char *verdict) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned v = 1;
+  for (int j = 0; j < nchk; ++j) v &= chk[(size_t)j * n + i];
+  verdict[i] = (unsigned char)v;
+}
+
+PA_D int proof_branch(int kind, const unsigned char *b0, const unsigned char *b1, int i) {
+  if (kind == PA_POK) return 0;
+  if (kind == PA_S2) return b0[i] ? 0 : (b1[i] ? 1 : 2);
+  return b0[i] ? 1 : 0;
+}
+// prover step 1: thread t owns operation j = t / n of proof i = t % n
+template <int KIND>
+__global__ void __launch_bounds__(PA_BLOCK)
+k_prove_ops(const unsigned char *stmts, const unsigned char *rnd, const unsigned char *b0, const unsigned char *b1,
+            const u32 *__restrict__ comb, u32 *jout, int n) {
+  typedef proof_kind<KIND> K;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * K::NEPS) return;
+  int j = t / n, i = t % n;
+  jac r;
+  int e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + (size_t)K::NSTMT * 64 * i,
+                             rnd + (size_t)K::NRND * 32 * i, comb);
+  st_jac(jout + 24 * ((size_t)i * K::NEPS + e), r);
+}
+// prover step 3 (after k_normalize wrote the eps points): challenge and responses
+template <int KIND>
+__global__ void __launch_bounds__(PA_BLOCK)
+k_prove_respond(unsigned char *proofs, size_t pstride, const unsigned char *stmts, const u64 *ids,
+                const unsigned char *secrets, const unsigned char *rnd, const unsigned char *b0,
+                const unsigned char *b1, int n) {
+  typedef proof_kind<KIND> K;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  prove_respond<KIND>(proofs + pstride * i, stmts + (size_t)K::NSTMT * 64 * i, ids[i],
+                      secrets + (size_t)K::NSECRET * 32 * i, rnd + (size_t)K::NRND * 32 * i, proof_branch(KIND, b0, b1, i));
+}
+
+// ---- generic Fiat-Shamir challenge over k wire points per item ---------------------------
+__global__ void k_challenge(const unsigned char *points, int k, const u64 *ids, unsigned char *out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char *pts[32];
+  for (int j = 0; j < k; ++j) pts[j] = points + 64 * ((size_t)i * k + j);
+  sc h;
+  challenge_hash(h, pts, k, ids[i]);
+  st_sc(out + 32 * (size_t)i, h);
+}
+
+// ---- PA stream: cnt consecutive BN_rand_range draws per item --------------------------------
+__global__ void k_rng_fill(u64 seed, const u64 *streams, u64 *ctrs, int cnt, unsigned char *out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 ctr = ctrs[i];
+  for (int k = 0; k < cnt; ++k) {
+    sc r;
+    pa_stream_rand_range(r, seed, streams[i], ctr);
+    st_sc(out + 32 * ((size_t)i * cnt + k), r);
+  }
+  ctrs[i] = ctr;
+}
+
+// ---- commitment points: phi = g^(alpha beta + bit), A = g^alpha, B = g^beta -------------------
+// SEAL/bidder.cpp:1131-1138 (the reference multiplies alpha*beta unreduced; the result is the same)
+__global__ void __launch_bounds__(PA_BLOCK)
+k_commit_points(const unsigned char *alpha, const unsigned char *beta, const unsigned char *bits,
+                const u32 *__restrict__ comb, u32 *jout, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n) return;
+  int which = t / n, i = t % n;
+  sc a, b, k;
+  ld_sc(a, alpha + 32 * (size_t)i);
+  ld_sc(b, beta + 32 * (size_t)i);
+  if (which == 0) {
+    sc bit;
+    sc_set_zero(bit);
+    bit.v[0] = bits[i] ? 1u : 0u;
+    sc_mul(k, a, b);
+    sc_add(k, k, bit);
+  } else {
+    k = which == 1 ? a : b;
+  }
+  jac r;
+  fixed_base_mul(r, k, comb);
+  st_jac(jout + 24 * ((size_t)i * 3 + which), r);
+}
+
+// ---- Y reconstruction: Y_id = sum_{i<id} X_i - sum_{i>id} X_i  (SEAL/bidder.cpp:1286-1299) --------
+// The reference recomputes both sums for every id (O(n^2) additions per bidder).
+// Here one block scans one auction: Y_id = E_id + P_id - T with E / P the
+// exclusive / inclusive prefix sums and T the total; the affine result is the same
+// whatever the association order.  offs[s] .. offs[s+1] delimit auction s.
+#define PA_SCAN_T 128
+__global__ void __launch_bounds__(PA_SCAN_T)
+k_y_scan(const unsigned char *X, const u32 *offs, int nseg_single, u32 *jout) {
+  __shared__ __align__(16) u32 part[2][PA_SCAN_T][24];
+  int seg = blockIdx.x;
+  int lo = offs ? (int)offs[seg] : 0, hi = offs ? (int)offs[seg + 1] : nseg_single;
+  int m = hi - lo, t = threadIdx.x;
+  int chunk = (m + PA_SCAN_T - 1) / PA_SCAN_T;
+  int c0 = min(m, t * chunk), c1 = min(m, c0 + chunk);
+  jac s;
+  jac_set_inf(s);
+  for (int id = c0; id < c1; ++id) {
+    aff x;
+    ld_aff(x, X + 64 * (size_t)(lo + id));
+    jac_madd(s, s, x);
+  }
+  st_jac(part[0][t], s);
+  __syncthreads();
+  int cur = 0;
+  for (int d = 1; d < PA_SCAN_T; d <<= 1) {  // Hillis-Steele inclusive scan of the chunk sums
+    jac a;
+    ld_jac(a, part[cur][t]);
+    if (t >= d) {
+      jac b;
+      ld_jac(b, part[cur][t - d]);
+      jac_add(a, a, b);
+    }
+    st_jac(part[cur ^ 1][t], a);
+    __syncthreads();
+    cur ^= 1;
+  }
+  jac total, e;
+  ld_jac(total, part[cur][PA_SCAN_T - 1]);
+  jac_neg(total, total);
+  if (t == 0) jac_set_inf(e); else ld_jac(e, part[cur][t - 1]);
+  for (int id = c0; id < c1; ++id) {
+    aff x;
+    ld_aff(x, X + 64 * (size_t)(lo + id));
+    jac p, y;
+    jac_madd(p, e, x);     // inclusive prefix
+    jac_add(y, e, p);      // E + P
+    jac_add(y, y, total);  // - T
+    st_jac(jout + 24 * (size_t)(lo + id), y);
+    e = p;
+  }
+}
+
+// ---- round three: is sum_i b_i the point at infinity?  (SEAL/bidder.cpp:1393-1397) ----------------
+__global__ void __launch_bounds__(PA_SCAN_T)
+k_point_sum_is_inf(const unsigned char *B, const u32 *offs, int nseg_single, int *flags) {
+  __shared__ __align__(16) u32 part[PA_SCAN_T][24];
+  int seg = blockIdx.x;
+  int lo = offs ? (int)offs[seg] : 0, hi = offs ? (int)offs[seg + 1] : nseg_single;
+  int m = hi - lo, t = threadIdx.x;
+  jac s;
+  jac_set_inf(s);
+  for (int id = t; id < m; id += PA_SCAN_T) {
+    aff x;
+    ld_aff(x, B + 64 * (size_t)(lo + id));
+    jac_madd(s, s, x);
+  }
+  st_jac(part[t], s);
+  __syncthreads();
+  for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
+    if (t < d) {
+      jac a, b;
+      ld_jac(a, part[t]);
+      ld_jac(b, part[t + d]);
+      jac_add(a, a, b);
+      st_jac(part[t], a);
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    jac a;
+    ld_jac(a, part[0]);
+    flags[seg] = jac_is_inf(a) ? 1 : 0;
+  }
 }

@@ -1,0 +1,165 @@
+// SHA-256 (FIPS 180-4) and the Fiat-Shamir challenge of the reference:
+//   h = SHA-256( enc(p_0) || ... || enc(p_k) || LE64(id) )  as a big-endian
+//   integer, reduced modulo the group order       (SEAL/hash.cpp:8-53 etc.)
+// where enc() is EC_POINT_point2oct(..., POINT_CONVERSION_UNCOMPRESSED):
+// 04 || X || Y, or the single byte 00 for the point at infinity,
+// and p_0 is always the generator.  The engine's 64-byte wire form of a point
+// is exactly the X || Y part, so hashing needs no field arithmetic at all (the
+// reference pays a field inversion per hashed point inside point2oct).
+//
+// One thread hashes one message; the message is streamed byte-wise into the
+// 16-word block buffer because the 65-byte encodings are not word aligned.
+// A challenge is 4..29 blocks next to ~10^6 multiply-adds of curve work.
+#pragma once
+#include "pa_sc.cuh"
+
+struct sha256_state {
+  u32 h[8];
+  u32 w[16];
+  u32 fill;  // bytes in w
+  u32 blocks;
+};
+
+PA_HD u32 sha_rotr(u32 x, int n) { return (x >> n) | (x << (32 - n)); }
+
+PA_HD void sha256_compress(u32 h[8], const u32 blk[16]) {
+  const u32 K[64] = {
+      0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+      0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+      0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+      0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+      0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+      0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+      0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+      0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+  u32 w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = blk[i];
+  u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    u32 wi;
+    if (i < 16) {
+      wi = w[i];
+    } else {
+      u32 w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+      u32 s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+      u32 s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+      wi = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+      w[i & 15] = wi;
+    }
+    u32 S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+    u32 ch = (e & f) ^ (~e & g);
+    u32 t1 = hh + S1 + ch + K[i] + wi;
+    u32 S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+    u32 mj = (a & b) ^ (a & c) ^ (b & c);
+    u32 t2 = S0 + mj;
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+PA_HD void sha256_init(sha256_state &s) {
+  const u32 iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s.h[i] = iv[i];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s.w[i] = 0;
+  s.fill = 0;
+  s.blocks = 0;
+}
+
+PA_HD void sha256_put(sha256_state &s, u32 byte) {
+  u32 wi = s.fill >> 2, sh = 24 - 8 * (s.fill & 3);
+  // dynamic word index: keep it a loop the compiler can turn into selects
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if ((u32)i == wi) s.w[i] |= (byte & 0xFFu) << sh;
+  if (++s.fill == 64) {
+    sha256_compress(s.h, s.w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s.w[i] = 0;
+    s.fill = 0;
+    s.blocks++;
+  }
+}
+
+PA_HD void sha256_put_bytes(sha256_state &s, const unsigned char *p, int n) {
+  for (int i = 0; i < n; ++i) sha256_put(s, p[i]);
+}
+
+// one curve point in wire form (64 bytes X||Y, zeros = infinity)
+PA_HD void sha256_put_point(sha256_state &s, const unsigned char *p) {
+  u32 nz = 0;
+  for (int i = 0; i < 64; ++i) nz |= p[i];
+  if (!nz) {
+    sha256_put(s, 0);  // EC_POINT_point2oct of infinity is the single byte 00
+    return;
+  }
+  sha256_put(s, 4);
+  sha256_put_bytes(s, p, 64);
+}
+
+PA_HD void sha256_final(sha256_state &s, u32 digest[8]) {
+  u64 bits = ((u64)s.blocks * 64 + s.fill) * 8;
+  sha256_put(s, 0x80);
+  while (s.fill != 56) sha256_put(s, 0);
+  s.w[14] = (u32)(bits >> 32);
+  s.w[15] = (u32)bits;
+  sha256_compress(s.h, s.w);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) digest[i] = s.h[i];
+}
+
+// digest (big-endian words) -> scalar mod n   (BN_bin2bn + BN_mod, SEAL/hash.cpp:50-51)
+PA_HD void sc_from_digest(sc &r, const u32 digest[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = digest[7 - i];
+  sc_reduce(r);
+}
+
+// generator in wire form
+PA_HD void wire_generator(unsigned char g[64]) {
+  const unsigned char G[64] = {
+      0x79, 0xBE, 0x66, 0x7E, 0xF9, 0xDC, 0xBB, 0xAC, 0x55, 0xA0, 0x62, 0x95, 0xCE, 0x87, 0x0B, 0x07,
+      0x02, 0x9B, 0xFC, 0xDB, 0x2D, 0xCE, 0x28, 0xD9, 0x59, 0xF2, 0x81, 0x5B, 0x16, 0xF8, 0x17, 0x98,
+      0x48, 0x3A, 0xDA, 0x77, 0x26, 0xA3, 0xC4, 0x65, 0x5D, 0xA4, 0xFB, 0xFC, 0x0E, 0x11, 0x08, 0xA8,
+      0xFD, 0x17, 0xB4, 0x48, 0xA6, 0x85, 0x54, 0x19, 0x9C, 0x47, 0xD0, 0x8F, 0xFB, 0x10, 0xD4, 0xB8};
+  for (int i = 0; i < 64; ++i) g[i] = G[i];
+}
+
+// h = H(g, pts[0], ..., pts[k-1], id): pts are pointers to 64-byte wire points
+PA_HD void challenge_hash(sc &h, const unsigned char *const *pts, int k, u64 id) {
+  sha256_state s;
+  sha256_init(s);
+  unsigned char g[64];
+  wire_generator(g);
+  sha256_put_point(s, g);
+  for (int i = 0; i < k; ++i) sha256_put_point(s, pts[i]);
+  for (int i = 0; i < 8; ++i) sha256_put(s, (u32)(id >> (8 * i)) & 0xFFu);  // raw little-endian size_t
+  u32 d[8];
+  sha256_final(s, d);
+  sc_from_digest(h, d);
+}
+
+// PA deterministic draw stream (include/pa_engine.h, "seeded randomness"):
+//   draw(seed, stream, ctr) = SHA-256("PAv1" || LE64 seed || LE64 stream || LE64 ctr)
+PA_HD void pa_stream_draw(u32 digest[8], u64 seed, u64 stream, u64 ctr) {
+  sha256_state s;
+  sha256_init(s);
+  sha256_put(s, 'P'); sha256_put(s, 'A'); sha256_put(s, 'v'); sha256_put(s, '1');
+  for (int i = 0; i < 8; ++i) sha256_put(s, (u32)(seed >> (8 * i)) & 0xFFu);
+  for (int i = 0; i < 8; ++i) sha256_put(s, (u32)(stream >> (8 * i)) & 0xFFu);
+  for (int i = 0; i < 8; ++i) sha256_put(s, (u32)(ctr >> (8 * i)) & 0xFFu);
+  sha256_final(s, digest);
+}
+// BN_rand_range(., order) on the PA stream: redraw while the value is >= n
+PA_HD void pa_stream_rand_range(sc &r, u64 seed, u64 stream, u64 &ctr) {
+  for (;;) {
+    u32 d[8];
+    pa_stream_draw(d, seed, stream, ctr++);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = d[7 - i];
+    if (!sc_ge_n(r.v)) return;
+  }
+}

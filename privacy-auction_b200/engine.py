@@ -17,6 +17,7 @@ POINT_BYTES, SCALAR_BYTES = 64, 32
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _sz = ctypes.c_size_t
 _ctx = ctypes.c_void_p
+_vp = ctypes.c_void_p
 
 # symbol -> (restype, argtypes); kept in step with include/pa_engine.h (tests/test_abi.py checks)
 SIGNATURES = {
@@ -42,6 +43,34 @@ SIGNATURES = {
     "pa_point_add": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _sz, ctypes.c_int]),
     "pa_point_encode": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.c_int, ctypes.c_void_p, _sz, ctypes.c_void_p]),
     "pa_measure_int_peak": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_double)]),
+    "pa_challenge": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _vp, _sz]),
+    "pa_challenge_dev": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _vp, _sz]),
+    "pa_pokdlog_prove": (ctypes.c_int, [_ctx] + [_vp] * 5 + [_sz]),
+    "pa_pokdlog_prove_dev": (ctypes.c_int, [_ctx] + [_vp] * 5 + [_sz]),
+    "pa_pokdlog_verify": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_pokdlog_verify_dev": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_powfcom_prove": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_powfcom_prove_dev": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_powfcom_verify": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_powfcom_verify_dev": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_stage1_prove": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_stage1_prove_dev": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_stage1_verify": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_stage1_verify_dev": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_stage2_prove": (ctypes.c_int, [_ctx] + [_vp] * 7 + [_sz]),
+    "pa_stage2_prove_dev": (ctypes.c_int, [_ctx] + [_vp] * 7 + [_sz]),
+    "pa_stage2_verify": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_stage2_verify_dev": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_commit_points": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_commit_points_dev": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_y_scan": (ctypes.c_int, [_ctx, _vp, _vp, _sz]),
+    "pa_y_scan_batch": (ctypes.c_int, [_ctx, _vp, _vp, _vp, _sz]),
+    "pa_y_scan_dev": (ctypes.c_int, [_ctx, _vp, _vp, _vp, _sz, _sz]),
+    "pa_point_sum_is_inf": (ctypes.c_int, [_ctx, _vp, _sz, ctypes.POINTER(ctypes.c_int)]),
+    "pa_point_sum_is_inf_batch": (ctypes.c_int, [_ctx, _vp, _vp, _sz, _vp]),
+    "pa_point_sum_is_inf_dev": (ctypes.c_int, [_ctx, _vp, _vp, _sz, _sz, _vp]),
+    "pa_rng_fill": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
+    "pa_rng_fill_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_profile_begin": (ctypes.c_int, [_ctx]),
     "pa_profile_end": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.POINTER(_sz)]),
 }
@@ -214,6 +243,89 @@ class Engine:
 
     def lincomb2_dev(self, d_p, d_a, d_q, d_b, d_out, n):
         self._check(self.lib.pa_lincomb2_dev(self.ctx, d_p, d_a, d_q, d_b, d_out, n))
+
+    # -- proofs and round logic (host buffers) -----------------------------------------------
+    def _run(self, fn, ins, out_bytes, n, extra=()):
+        out = bytearray(out_bytes)
+        bufs = [_buf(x) for x in ins] + [_buf(out)]
+        self._check(getattr(self.lib, fn)(self.ctx, *[b[0] for b in bufs], *extra, n))
+        return bytes(out)
+
+    @staticmethod
+    def _ids(ids):
+        return bytes((ctypes.c_uint64 * max(len(ids), 1))(*ids))[:8 * len(ids)]
+
+    def challenge(self, points, k, ids):
+        n = len(ids)
+        out = bytearray(32 * n)
+        b = [_buf(points), _buf(self._ids(ids)), _buf(out)]
+        self._check(self.lib.pa_challenge(self.ctx, b[0][0], k, b[1][0], b[2][0], n))
+        return bytes(out)
+
+    def pokdlog_prove(self, X, x, ids, rnd):
+        return self._run("pa_pokdlog_prove", (X, x, self._ids(ids), rnd), 96 * len(ids), len(ids))
+
+    def pokdlog_verify(self, proofs, X, ids):
+        return self._run("pa_pokdlog_verify", (proofs, X, self._ids(ids)), len(ids), len(ids))
+
+    def powfcom_prove(self, stmt, alpha, bits, ids, rnd):
+        return self._run("pa_powfcom_prove", (stmt, alpha, bytes(bits), self._ids(ids), rnd), 352 * len(ids), len(ids))
+
+    def powfcom_verify(self, proofs, stmt, ids):
+        return self._run("pa_powfcom_verify", (proofs, stmt, self._ids(ids)), len(ids), len(ids))
+
+    def stage1_prove(self, stmt, secrets, bits, ids, rnd):
+        return self._run("pa_stage1_prove", (stmt, secrets, bytes(bits), self._ids(ids), rnd), 672 * len(ids), len(ids))
+
+    def stage1_verify(self, proofs, stmt, ids):
+        return self._run("pa_stage1_verify", (proofs, stmt, self._ids(ids)), len(ids), len(ids))
+
+    def stage2_prove(self, stmt, secrets, bi, bj, ids, rnd):
+        return self._run("pa_stage2_prove", (stmt, secrets, bytes(bi), bytes(bj), self._ids(ids), rnd), 1344 * len(ids), len(ids))
+
+    def stage2_verify(self, proofs, stmt, ids):
+        return self._run("pa_stage2_verify", (proofs, stmt, self._ids(ids)), len(ids), len(ids))
+
+    def commit_points(self, alpha, beta, bits):
+        return self._run("pa_commit_points", (alpha, beta, bytes(bits)), 192 * len(bits), len(bits))
+
+    def y_scan(self, X):
+        n = len(X) // 64
+        if n == 0:
+            return b""
+        return self._run("pa_y_scan", (X,), 64 * n, n)
+
+    def y_scan_batch(self, X, offsets):
+        import struct
+        nseg = len(offsets) - 1
+        out = bytearray(len(X))
+        b = [_buf(X), _buf(out), _buf(struct.pack(f"<{len(offsets)}I", *offsets))]
+        self._check(self.lib.pa_y_scan_batch(self.ctx, b[0][0], b[1][0], b[2][0], nseg))
+        return bytes(out)
+
+    def point_sum_is_inf(self, B):
+        flag = ctypes.c_int(0)
+        p, keep = _buf(B) if len(B) else (None, None)
+        self._check(self.lib.pa_point_sum_is_inf(self.ctx, p, len(B) // 64, ctypes.byref(flag)))
+        return bool(flag.value)
+
+    def point_sum_is_inf_batch(self, B, offsets):
+        import struct
+        nseg = len(offsets) - 1
+        flags = bytearray(4 * nseg)
+        b = [_buf(B), _buf(struct.pack(f"<{len(offsets)}I", *offsets)), _buf(flags)]
+        self._check(self.lib.pa_point_sum_is_inf_batch(self.ctx, b[0][0], b[1][0], nseg, b[2][0]))
+        return [bool(v) for v in struct.unpack(f"<{nseg}i", bytes(flags))]
+
+    def rng_fill(self, seed, streams, counters, per_item):
+        """returns (draws bytes, advanced counters list)"""
+        import struct
+        n = len(streams)
+        out = bytearray(32 * per_item * n)
+        ctr = bytearray(struct.pack(f"<{n}Q", *counters))
+        b = [_buf(struct.pack(f"<{n}Q", *streams)), _buf(ctr), _buf(out)]
+        self._check(self.lib.pa_rng_fill(self.ctx, seed, b[0][0], b[1][0], per_item, b[2][0], n))
+        return bytes(out), list(struct.unpack(f"<{n}Q", bytes(ctr)))
 
     def measure_int_peak(self):
         out = (ctypes.c_double * 4)()

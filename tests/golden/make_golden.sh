@@ -1,0 +1,12 @@
+#!/bin/sh
+# Regenerates tests/golden/seal_*.bin by running the UNMODIFIED reference SEAL
+# classes (oracle/_ref/seal_ref, built by `make -C oracle ref` from
+# /root/reference with the seeded RNG shim force-included).  Build container only.
+# args of seal_ref: <n> <c> <seed> <bids|-> <out>
+set -e
+cd "$(dirname "$0")/../.."
+make -s -C oracle ref
+for cfg in "3 4 42 -" "1 3 1 5" "2 3 1 -" "4 6 7 -" "5 5 11 0,0,0,0,0" "3 8 5 255,255,3" "6 4 99 -"; do
+  set -- $cfg
+  ./oracle/_ref/seal_ref "$1" "$2" "$3" "$4" "tests/golden/seal_n$1_c$2_s$3.bin"
+done

@@ -117,3 +117,57 @@ int hc_jac_eq_aff(const unsigned char *p, const unsigned char *q) {
 }
 const unsigned int *hc_comb_table() { ensure_tab(); return g_tab.data(); }
 }
+
+#include "pa_proof.cuh"
+
+template <int KIND> static unsigned verify_all(const unsigned char *proof, const unsigned char *stmt, u64 id, int nchk) {
+  ensure_tab();
+  sc ch1;
+  verify_derive<KIND>(ch1, proof, stmt, id);
+  unsigned mask = 0;
+  for (int j = 0; j < nchk; ++j)
+    if (verify_check_one<KIND>(j, proof, stmt, ch1, g_tab.data())) mask |= 1u << j;
+  return mask;
+}
+template <int KIND> static void prove_all(unsigned char *proof, const unsigned char *stmt, u64 id, const unsigned char *secrets,
+                                          const unsigned char *rnd, int branch) {
+  typedef proof_kind<KIND> K;
+  ensure_tab();
+  for (int j = 0; j < K::NEPS; ++j) {
+    jac r;
+    int e = prove_op_one<KIND>(r, branch, j, stmt, rnd, g_tab.data());
+    out_jac(proof + 64 * e, r);
+  }
+  prove_respond<KIND>(proof, stmt, id, secrets, rnd, branch);
+}
+extern "C" {
+unsigned hc_proof_verify(int kind, const unsigned char *proof, const unsigned char *stmt, unsigned long long id) {
+  switch (kind) {
+  case PA_POK: return verify_all<PA_POK>(proof, stmt, id, 1);
+  case PA_COM: return verify_all<PA_COM>(proof, stmt, id, 4);
+  case PA_S1: return verify_all<PA_S1>(proof, stmt, id, 8);
+  default: return verify_all<PA_S2>(proof, stmt, id, 16);
+  }
+}
+void hc_proof_prove(int kind, unsigned char *proof, const unsigned char *stmt, unsigned long long id,
+                    const unsigned char *secrets, const unsigned char *rnd, int branch) {
+  switch (kind) {
+  case PA_POK: prove_all<PA_POK>(proof, stmt, id, secrets, rnd, branch); break;
+  case PA_COM: prove_all<PA_COM>(proof, stmt, id, secrets, rnd, branch); break;
+  case PA_S1: prove_all<PA_S1>(proof, stmt, id, secrets, rnd, branch); break;
+  default: prove_all<PA_S2>(proof, stmt, id, secrets, rnd, branch);
+  }
+}
+void hc_stream_draw(unsigned long long seed, unsigned long long stream, unsigned long long ctr, unsigned char *out) {
+  u32 d[8];
+  pa_stream_draw(d, seed, stream, ctr);
+  for (int i = 0; i < 8; ++i) { out[4*i] = d[i] >> 24; out[4*i+1] = d[i] >> 16; out[4*i+2] = d[i] >> 8; out[4*i+3] = d[i]; }
+}
+void hc_challenge(const unsigned char *pts, int k, unsigned long long id, unsigned char *out) {
+  const unsigned char *p[32];
+  for (int i = 0; i < k; ++i) p[i] = pts + 64 * i;
+  sc h;
+  challenge_hash(h, p, k, id);
+  sc_to_be(out, h);
+}
+}

@@ -77,3 +77,91 @@ class Oracle:
         self._call("po_point_encode", _p(points), ctypes.c_size_t(n), ctypes.c_int(1 if compressed else 0), _p(out),
                    ctypes.c_size_t(stride), ctypes.cast(lens, ctypes.c_void_p))
         return [bytes(out[i * stride:i * stride + lens[i]]) for i in range(n)]
+
+
+def _ids(ids):
+    return (ctypes.c_uint64 * max(len(ids), 1))(*ids)
+
+
+def _add_protocol_methods(cls):
+    """Protocol-level restatement functions (oracle/pa_oracle.c) — same argument
+    order and layouts as the engine's ABI."""
+
+    def challenge(self, points, k, ids):
+        n = len(ids)
+        out = bytearray(32 * n)
+        self._call("po_challenge", _p(points), ctypes.c_size_t(k), _ids(ids), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def commit_points(self, alpha, beta, bits):
+        n = len(bits)
+        out = bytearray(192 * n)
+        self._call("po_commit_points", _p(alpha), _p(beta), _p(bits), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def pokdlog_prove(self, X, x, ids, rnd):
+        n = len(ids)
+        out = bytearray(96 * n)
+        self._call("po_pokdlog_prove", _p(X), _p(x), _ids(ids), _p(rnd), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def pokdlog_verify(self, proofs, X, ids):
+        n = len(ids)
+        out = bytearray(n)
+        self._call("po_pokdlog_verify", _p(proofs), _p(X), _ids(ids), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def powfcom_prove(self, stmt, alpha, bits, ids, rnd):
+        n = len(ids)
+        out = bytearray(352 * n)
+        self._call("po_powfcom_prove", _p(stmt), _p(alpha), _p(bits), _ids(ids), _p(rnd), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def powfcom_verify(self, proofs, stmt, ids):
+        n = len(ids)
+        out = bytearray(n)
+        self._call("po_powfcom_verify", _p(proofs), _p(stmt), _ids(ids), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def stage1_prove(self, stmt, secrets, bits, ids, rnd):
+        n = len(ids)
+        out = bytearray(672 * n)
+        self._call("po_stage1_prove", _p(stmt), _p(secrets), _p(bits), _ids(ids), _p(rnd), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def stage1_verify(self, proofs, stmt, ids):
+        n = len(ids)
+        out = bytearray(n)
+        self._call("po_stage1_verify", _p(proofs), _p(stmt), _ids(ids), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def stage2_prove(self, stmt, secrets, bi, bj, ids, rnd):
+        n = len(ids)
+        out = bytearray(1344 * n)
+        self._call("po_stage2_prove", _p(stmt), _p(secrets), _p(bi), _p(bj), _ids(ids), _p(rnd), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def stage2_verify(self, proofs, stmt, ids):
+        n = len(ids)
+        out = bytearray(n)
+        self._call("po_stage2_verify", _p(proofs), _p(stmt), _ids(ids), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def y_scan(self, X):
+        n = len(X) // 64
+        out = bytearray(64 * n)
+        self._call("po_y_scan", _p(X), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
+    def point_sum_is_inf(self, b):
+        flag = ctypes.c_int(0)
+        self._call("po_point_sum_is_inf", _p(b), ctypes.c_size_t(len(b) // 64), ctypes.byref(flag))
+        return bool(flag.value)
+
+    for name, fn in list(locals().items()):
+        if callable(fn) and name != "cls":
+            setattr(cls, name, fn)
+    return cls
+
+
+_add_protocol_methods(Oracle)

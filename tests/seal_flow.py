@@ -1,0 +1,215 @@
+"""Host-side orchestration of one SEAL auction over a batched backend, written to
+read like the reference's own main (SEAL/main.cpp:32-120) and Bidder round logic
+(SEAL/bidder.cpp:1109-1421).  The backend is anything exposing the engine's
+batched operator interface (include/pa_engine.h): the CUDA engine, the libcrypto
+oracle port, or the host-compiled device headers.  Output is the PASEALT1
+transcript the Tier-A driver (oracle/ref_seal_driver.cpp) writes for the
+unmodified reference, so parity is a byte comparison.
+
+Randomness: bidder j draws from PA stream (seed, j) in the reference's draw
+order.
+"""
+import struct
+
+import secp256k1_py as E
+
+N_ORD = E.N
+
+
+def b32(x):
+    return int(x).to_bytes(32, "big")
+
+
+class SealFlow:
+    def __init__(self, backend, n, c, seed, bids, verify=True, auction=0):
+        assert len(bids) == n
+        self.be, self.n, self.c, self.seed, self.bids, self.verify = backend, n, c, seed, list(bids), verify
+        self.streams = [E.PaStream(seed, (auction << 32) | j) for j in range(n)]
+        # binaryBidStr: MSB first (SEAL/bidder.cpp:31, 1128)
+        self.bits = [[(bid >> (c - 1 - i)) & 1 for i in range(c)] for bid in bids]
+        self.ids = list(range(n))
+        self.junction = False            # junctionFlag, identical for all bidders
+        self.prev_step = None            # prevDecidingStep
+        self.prev_bit = [1] * n          # prevDecidingBit (private, initialised to 1, SEAL/bidder.cpp:23)
+        self.max_bid = [0] * n
+        self.out = bytearray()
+        self.ok = True
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _draw(self, j, k):
+        return [self.streams[j].rand_range() for _ in range(k)]
+
+    @staticmethod
+    def _cat(items):
+        return b"".join(items)
+
+    def _ids(self, js):
+        return list(js)
+
+    def _per_verifier(self, verdict_by_prover):
+        """Reference: verifier j checks every i != j (SEAL/bidder.cpp:1178-1190).  Every
+        proof is verified once here; verifier j's answer is the AND over i != j."""
+        n = self.n
+        res = []
+        for j in range(n):
+            v = all(verdict_by_prover[i] for i in range(n) if i != j)
+            res.append(1 if v else 0)
+            self.ok &= bool(v)
+        return bytes(res)
+
+    # -- phases ------------------------------------------------------------------------------
+    def commit(self):
+        """Bidder::commitBid for every bidder and bit (SEAL/bidder.cpp:1109-1162)."""
+        n, c, be = self.n, self.c, self.be
+        al, bt, vA, vB, rc, bits, ids = [], [], [], [], [], [], []
+        for j in range(n):
+            for i in range(c):
+                a, b, va, vb, r1, d1, d2 = self._draw(j, 7)
+                al.append(b32(a)); bt.append(b32(b)); vA.append(b32(va)); vB.append(b32(vb))
+                rc.append(b32(r1) + b32(d1) + b32(d2))
+                bits.append(self.bits[j][i]); ids.append(j)
+        alpha, beta = self._cat(al), self._cat(bt)
+        pts = be.commit_points(alpha, beta, bytes(bits))                      # phi, A, B
+        A = self._cat(pts[192 * k + 64:192 * k + 128] for k in range(n * c))
+        B = self._cat(pts[192 * k + 128:192 * k + 192] for k in range(n * c))
+        pokA = be.pokdlog_prove(A, alpha, ids, self._cat(vA))
+        pokB = be.pokdlog_prove(B, beta, ids, self._cat(vB))
+        com = be.powfcom_prove(pts, alpha, bytes(bits), ids, self._cat(rc))
+        self.alpha = [[al[j * c + i] for i in range(c)] for j in range(n)]
+        self.cpts = [[pts[192 * (j * c + i):192 * (j * c + i + 1)] for i in range(c)] for j in range(n)]
+        for k in range(n * c):
+            self.out += pts[192 * k:192 * k + 192] + pokA[96 * k:96 * k + 96] + pokB[96 * k:96 * k + 96] + com[352 * k:352 * k + 352]
+        # Bidder::verifyCommitment (SEAL/bidder.cpp:1171-1195)
+        if self.verify and n > 1:
+            vA_ = be.pokdlog_verify(pokA, A, ids)
+            vB_ = be.pokdlog_verify(pokB, B, ids)
+            vC_ = be.powfcom_verify(com, pts, ids)
+            per_prover = [all(vA_[j * c + i] and vB_[j * c + i] and vC_[j * c + i] for i in range(c)) for j in range(n)]
+        else:
+            per_prover = [True] * n
+        self.out += self._per_verifier(per_prover)
+
+    def round_one(self, step):
+        """Bidder::roundOne (SEAL/bidder.cpp:1203-1236) + verifyRoundOne (:1245-1262)."""
+        n, be = self.n, self.be
+        xs, rs, vx, vr = [], [], [], []
+        for j in range(n):
+            x, r, a, b = self._draw(j, 4)
+            xs.append(b32(x)); rs.append(b32(r)); vx.append(b32(a)); vr.append(b32(b))
+        x_b, r_b = self._cat(xs), self._cat(rs)
+        X = be.fixed_base_mul(x_b)
+        R = be.fixed_base_mul(r_b)
+        pokX = be.pokdlog_prove(X, x_b, self.ids, self._cat(vx))
+        pokR = be.pokdlog_prove(R, r_b, self.ids, self._cat(vr))
+        self.x, self.X, self.R = xs, X, R
+        for j in range(n):
+            self.out += X[64 * j:64 * j + 64] + R[64 * j:64 * j + 64] + pokX[96 * j:96 * j + 96] + pokR[96 * j:96 * j + 96]
+        if self.verify and n > 1:
+            v1 = be.pokdlog_verify(pokX, X, self.ids)
+            v2 = be.pokdlog_verify(pokR, R, self.ids)
+            per_prover = [bool(v1[j] and v2[j]) for j in range(n)]
+        else:
+            per_prover = [True] * n
+        self.out += self._per_verifier(per_prover)
+
+    def round_two(self, step):
+        """Bidder::roundTwo (SEAL/bidder.cpp:1271-1336) + verifyRoundTwo (:1346-1377)."""
+        n, be = self.n, self.be
+        Y = be.y_scan(self.X)                                             # :1286-1299
+        base, ebit = [], []
+        for j in range(n):
+            bit = self.bits[j][step]
+            if (not self.junction and bit == 0) or (self.junction and (bit == 0 or self.prev_bit[j] == 0)):
+                base.append(Y[64 * j:64 * j + 64]); ebit.append(0)        # b = Y^x   :1303
+            else:
+                base.append(self.R[64 * j:64 * j + 64]); ebit.append(1)   # b = R^x   :1307
+        b = be.var_base_mul(self._cat(base), self._cat(self.x))
+        pt = lambda buf, j: buf[64 * j:64 * j + 64]
+        if not self.junction:
+            stmt, sec, rnd = [], [], []
+            for j in range(n):
+                stmt.append(pt(b, j) + pt(self.X, j) + pt(Y, j) + pt(self.R, j) + self.cpts[j][step])
+                sec.append(self.x[j] + self.alpha[j][step])
+                rnd.append(self._cat(b32(v) for v in self._draw(j, 5)))
+            stmt_b = self._cat(stmt)
+            proofs = be.stage1_prove(stmt_b, self._cat(sec), bytes(ebit), self.ids, self._cat(rnd))
+            rec = 672
+            tag = 1
+        else:
+            stmt, sec, rnd = [], [], []
+            P = self.prev
+            for j in range(n):
+                stmt.append(pt(b, j) + pt(self.X, j) + pt(self.R, j) + pt(P["b"], j) + pt(P["X"], j) + pt(P["R"], j) +
+                            self.cpts[j][step] + pt(Y, j) + pt(P["Y"], j))
+                sec.append(self.x[j] + P["x"][j] + self.alpha[j][step])
+                rnd.append(self._cat(b32(v) for v in self._draw(j, 11)))
+            stmt_b = self._cat(stmt)
+            proofs = be.stage2_prove(stmt_b, self._cat(sec), bytes(ebit), bytes(self.prev_bit), self.ids, self._cat(rnd))
+            rec = 1344
+            tag = 2
+        for j in range(n):
+            self.out += struct.pack("<I", tag) + pt(b, j) + proofs[rec * j:rec * (j + 1)]
+        if self.verify and n > 1:
+            v = be.stage1_verify(proofs, stmt_b, self.ids) if tag == 1 else be.stage2_verify(proofs, stmt_b, self.ids)
+            per_prover = [bool(v[j]) for j in range(n)]
+        else:
+            per_prover = [True] * n
+        self.out += self._per_verifier(per_prover)
+        self.Y, self.b = Y, b
+
+    def round_three(self, step):
+        """Bidder::roundThree (SEAL/bidder.cpp:1386-1421)."""
+        deciding = not self.be.point_sum_is_inf(self.b)                  # :1393-1397
+        if deciding:
+            self.junction = True
+            self.prev_step = step
+            for j in range(self.n):
+                self.prev_bit[j] &= self.bits[j][step]                    # :1402 (true bit)
+                self.max_bid[j] |= 1 << (self.c - step - 1)               # :1403 (64-bit shift here)
+            self.prev = {"X": self.X, "R": self.R, "Y": self.Y, "b": self.b, "x": list(self.x)}   # :1406-1411
+        self.out += bytes([1 if deciding else 0] * self.n)
+
+    def run(self):
+        self.out += b"PASEALT1" + struct.pack("<QQQ", self.n, self.c, self.seed)
+        for bid in self.bids:
+            self.out += struct.pack("<Q", bid)
+        self.commit()
+        for step in range(self.c):
+            self.round_one(step)
+            self.round_two(step)
+            self.round_three(step)
+        for j in range(self.n):
+            self.out += struct.pack("<Q", self.max_bid[j])
+        self.ok &= all(m == max(self.bids) for m in self.max_bid)
+        return bytes(self.out)
+
+
+def parse_transcript(buf):
+    """PASEALT1 -> dict of sections (used to feed single proofs to verifiers)."""
+    assert buf[:8] == b"PASEALT1"
+    n, c, seed = struct.unpack_from("<QQQ", buf, 8)
+    off = 32
+    bids = list(struct.unpack_from(f"<{n}Q", buf, off)); off += 8 * n
+    t = {"n": n, "c": c, "seed": seed, "bids": bids, "commit": [], "steps": []}
+    for j in range(n):
+        row = []
+        for i in range(c):
+            row.append(buf[off:off + 736]); off += 736
+        t["commit"].append(row)
+    t["commit_verdict"] = buf[off:off + n]; off += n
+    for step in range(c):
+        s = {"r1": [], "r2": []}
+        for j in range(n):
+            s["r1"].append(buf[off:off + 320]); off += 320
+        s["r1_verdict"] = buf[off:off + n]; off += n
+        for j in range(n):
+            tag = struct.unpack_from("<I", buf, off)[0]; off += 4
+            b = buf[off:off + 64]; off += 64
+            rec = 672 if tag == 1 else 1344
+            s["r2"].append((tag, b, buf[off:off + rec])); off += rec
+        s["r2_verdict"] = buf[off:off + n]; off += n
+        s["r3"] = buf[off:off + n]; off += n
+        t["steps"].append(s)
+    t["max_bid"] = list(struct.unpack_from(f"<{n}Q", buf, off)); off += 8 * n
+    assert off == len(buf), (off, len(buf))
+    return t

@@ -1,0 +1,208 @@
+"""Parity of the CUDA proof / round-logic path, through the C ABI, against (a) the
+transcripts of the unmodified reference (tests/golden) and (b) the libcrypto
+oracle on seeded random statements, including tampered proofs.  Bit-exact."""
+import glob
+import os
+import random
+
+import pytest
+
+import secp256k1_py as E
+import seal_flow
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "seal_*.bin")))
+N = E.N
+
+
+def b32(x):
+    return int(x).to_bytes(32, "big")
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_engine_reproduces_reference_transcript(engine, path):
+    gold = open(path, "rb").read()
+    t = seal_flow.parse_transcript(gold)
+    fl = seal_flow.SealFlow(engine, t["n"], t["c"], t["seed"], t["bids"])
+    out = fl.run()
+    assert out == gold
+    assert fl.ok and fl.max_bid == t["max_bid"]
+
+
+def test_engine_matches_oracle_on_a_larger_auction(engine, oracle):
+    """n = 12, c = 10 (too slow for the all-pairs reference, fine verify-once)"""
+    rnd = random.Random(5)
+    bids = [rnd.randrange(1 << 10) for _ in range(12)]
+    a = seal_flow.SealFlow(engine, 12, 10, 77, bids)
+    b = seal_flow.SealFlow(oracle, 12, 10, 77, bids)
+    assert a.run() == b.run() and a.ok and b.ok
+
+
+def _pts(oracle, rnd, k):
+    return oracle.fixed_base_mul(b"".join(b32(rnd.randrange(1, N)) for _ in range(k)))
+
+
+def test_challenge_parity(engine, oracle):
+    rnd = random.Random(31)
+    for k in (2, 7, 15, 27):
+        n = 64
+        pts = bytearray(_pts(oracle, rnd, n * k))
+        for i in rnd.sample(range(n * k), 10):   # infinity shortens the message
+            pts[64 * i:64 * i + 64] = bytes(64)
+        ids = [rnd.randrange(1 << 40) for _ in range(n)]
+        assert engine.challenge(bytes(pts), k, ids) == oracle.challenge(bytes(pts), k, ids)
+    # independent restatement
+    pts = _pts(oracle, rnd, 3)
+    h = engine.challenge(pts, 3, [9])
+    assert int.from_bytes(h, "big") == E.challenge([E.dec64(pts[64 * i:64 * i + 64]) for i in range(3)], 9)
+
+
+def test_rng_fill_matches_pa_stream(engine):
+    streams, ctrs = [0, 1, 5, (3 << 32) | 7], [0, 10, 0, 123456]
+    out, ctr2 = engine.rng_fill(42, streams, ctrs, 11)
+    for i, (s, c) in enumerate(zip(streams, ctrs)):
+        ps = E.PaStream(42, s, c)
+        for k in range(11):
+            assert out[32 * (11 * i + k):32 * (11 * i + k + 1)] == b32(ps.rand_range())
+        assert ctr2[i] == ps.ctr
+
+
+def test_commit_points_parity(engine, oracle):
+    rnd = random.Random(32)
+    n = 200
+    al = b"".join(b32(rnd.randrange(N)) for _ in range(n - 2)) + b32(0) + b32(N - 1)
+    be = b"".join(b32(rnd.randrange(N)) for _ in range(n - 2)) + b32(5) + b32(N - 1)
+    bits = bytes(rnd.randrange(2) for _ in range(n))
+    assert engine.commit_points(al, be, bits) == oracle.commit_points(al, be, bits)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 20, 127, 128, 129, 1000])
+def test_y_scan_and_sum(engine, oracle, n):
+    rnd = random.Random(100 + n)
+    X = bytearray(_pts(oracle, rnd, n))
+    if n >= 5:
+        X[64:128] = bytes(64)                      # an infinity among the keys
+        X[192:256] = X[128:192]                    # a repeated key (doubling inside the scan)
+    X = bytes(X)
+    Y = engine.y_scan(X)
+    if n <= 129:
+        assert Y == oracle.y_scan(X)               # the reference's O(n^2) loops
+    else:
+        pts = [E.dec64(X[64 * i:64 * i + 64]) for i in range(n)]
+        pre = [E.INF]
+        for p in pts:
+            pre.append(E.add(pre[-1], p))
+        tot = pre[-1]
+        for i in rnd.sample(range(n), 40) + [0, n - 1]:
+            want = E.add(pre[i], E.neg(E.add(tot, E.neg(pre[i + 1]))))
+            assert E.dec64(Y[64 * i:64 * i + 64]) == want
+    assert engine.point_sum_is_inf(X) == oracle.point_sum_is_inf(X)
+    # sum_i Y_i * x_i vanishes when nobody vetoes: use b_i = x_i * Y_i with X_i = x_i * G
+    if n <= 129:
+        xs = [rnd.randrange(1, N) for _ in range(n)]
+        Xs = oracle.fixed_base_mul(b"".join(b32(x) for x in xs))
+        Ys = engine.y_scan(Xs)
+        bs = engine.var_base_mul(Ys, b"".join(b32(x) for x in xs))
+        assert engine.point_sum_is_inf(bs) is True
+        assert oracle.point_sum_is_inf(bs) is True
+
+
+def test_y_scan_batch_matches_single(engine, oracle):
+    rnd = random.Random(55)
+    sizes = [1, 2, 20, 7, 1, 13, 128, 3]
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    X = _pts(oracle, rnd, offs[-1])
+    Y = engine.y_scan_batch(X, offs)
+    for a, b in zip(offs, offs[1:]):
+        assert Y[64 * a:64 * b] == oracle.y_scan(X[64 * a:64 * b])
+    flags = engine.point_sum_is_inf_batch(X, offs)
+    assert flags == [oracle.point_sum_is_inf(X[64 * a:64 * b]) for a, b in zip(offs, offs[1:])]
+
+
+def _random_proofs(oracle, rnd, kind, n):
+    """valid proofs of every branch, made by the oracle prover from random witnesses"""
+    ids = [rnd.randrange(1 << 20) for _ in range(n)]
+    sc = lambda: rnd.randrange(1, N)
+    G = E.G
+    if kind == "pokdlog":
+        x = [sc() for _ in range(n)]
+        X = oracle.fixed_base_mul(b"".join(map(b32, x)))
+        rndb = b"".join(b32(sc()) for _ in range(n))
+        return dict(stmt=X, secrets=b"".join(map(b32, x)), ids=ids, rnd=rndb, args=())
+    if kind == "powfcom":
+        al, be = [sc() for _ in range(n)], [sc() for _ in range(n)]
+        bits = bytes(rnd.randrange(2) for _ in range(n))
+        stmt = oracle.commit_points(b"".join(map(b32, al)), b"".join(map(b32, be)), bits)
+        return dict(stmt=stmt, secrets=b"".join(map(b32, al)), ids=ids, rnd=b"".join(b32(sc()) for _ in range(3 * n)), args=(bits,))
+    # stage 1 / stage 2 statements
+    x, r, al, be = ([sc() for _ in range(n)] for _ in range(4))
+    bits = [rnd.randrange(2) for _ in range(n)]
+    X = oracle.fixed_base_mul(b"".join(map(b32, x)))
+    R = oracle.fixed_base_mul(b"".join(map(b32, r)))
+    Y = oracle.fixed_base_mul(b"".join(b32(sc()) for _ in range(n)))
+    cpts = oracle.commit_points(b"".join(map(b32, al)), b"".join(map(b32, be)), bytes(bits))
+    base = b"".join((R if bits[i] else Y)[64 * i:64 * i + 64] for i in range(n))
+    b = oracle.var_base_mul(base, b"".join(map(b32, x)))
+    p = lambda buf, i: buf[64 * i:64 * i + 64]
+    if kind == "stage1":
+        stmt = b"".join(p(b, i) + p(X, i) + p(Y, i) + p(R, i) + cpts[192 * i:192 * i + 192] for i in range(n))
+        sec = b"".join(b32(x[i]) + b32(al[i]) for i in range(n))
+        return dict(stmt=stmt, secrets=sec, ids=ids, rnd=b"".join(b32(sc()) for _ in range(5 * n)), args=(bytes(bits),))
+    # stage 2: previous deciding step data; bj random, bi = bit & bj
+    xj, rj = [sc() for _ in range(n)], [sc() for _ in range(n)]
+    bj = [rnd.randrange(2) for _ in range(n)]
+    bi = [bits[i] & bj[i] for i in range(n)]
+    Xj = oracle.fixed_base_mul(b"".join(map(b32, xj)))
+    Rj = oracle.fixed_base_mul(b"".join(map(b32, rj)))
+    Yj = oracle.fixed_base_mul(b"".join(b32(sc()) for _ in range(n)))
+    basej = b"".join((Rj if bj[i] else Yj)[64 * i:64 * i + 64] for i in range(n))
+    Bj = oracle.var_base_mul(basej, b"".join(map(b32, xj)))
+    cpts = oracle.commit_points(b"".join(map(b32, al)), b"".join(map(b32, be)), bytes(bi))
+    basei = b"".join((R if bi[i] else Y)[64 * i:64 * i + 64] for i in range(n))
+    Bi = oracle.var_base_mul(basei, b"".join(map(b32, x)))
+    stmt = b"".join(p(Bi, i) + p(X, i) + p(R, i) + p(Bj, i) + p(Xj, i) + p(Rj, i) + cpts[192 * i:192 * i + 192] + p(Y, i) + p(Yj, i)
+                    for i in range(n))
+    sec = b"".join(b32(x[i]) + b32(xj[i]) + b32(al[i]) for i in range(n))
+    return dict(stmt=stmt, secrets=sec, ids=ids, rnd=b"".join(b32(sc()) for _ in range(11 * n)), args=(bytes(bi), bytes(bj)))
+
+
+REC = {"pokdlog": (96, 1), "powfcom": (352, 4), "stage1": (672, 8), "stage2": (1344, 16)}
+
+
+@pytest.mark.parametrize("kind", ["pokdlog", "powfcom", "stage1", "stage2"])
+def test_prove_verify_parity_and_tampering(engine, oracle, kind):
+    rnd = random.Random({"pokdlog": 1, "powfcom": 2, "stage1": 3, "stage2": 4}[kind])
+    n = 96
+    w = _random_proofs(oracle, rnd, kind, n)
+    prove_e, prove_o = getattr(engine, kind + "_prove"), getattr(oracle, kind + "_prove")
+    ver_e, ver_o = getattr(engine, kind + "_verify"), getattr(oracle, kind + "_verify")
+    proofs = prove_e(w["stmt"], w["secrets"], *w["args"], w["ids"], w["rnd"])
+    assert proofs == prove_o(w["stmt"], w["secrets"], *w["args"], w["ids"], w["rnd"])
+    assert ver_e(proofs, w["stmt"], w["ids"]) == bytes([1] * n) == ver_o(proofs, w["stmt"], w["ids"])
+    # negative tests (the reference has none): every scalar field flipped,
+    # every eps replaced by another valid point, wrong id — verdicts must agree with the oracle
+    rec, neps = REC[kind]
+    nsc = (rec - 64 * neps) // 32
+    bad = bytearray(proofs)
+    expect_fail = []
+    for i in range(n):
+        f = i % (neps + nsc + 1)
+        o = rec * i
+        if f < neps:
+            other = rec * ((i + 1) % n) + 64 * ((f + 1) % neps)
+            bad[o + 64 * f:o + 64 * f + 64] = proofs[other:other + 64]
+            expect_fail.append(True)
+        elif f < neps + nsc:
+            pos = o + 64 * neps + 32 * (f - neps) + 31
+            bad[pos] ^= 1
+            expect_fail.append(True)
+        else:
+            expect_fail.append(False)
+    got = ver_e(bytes(bad), w["stmt"], w["ids"])
+    assert got == ver_o(bytes(bad), w["stmt"], w["ids"])
+    assert [g == 0 for g in got] == expect_fail
+    wrong_ids = [i + 1 for i in w["ids"]]
+    assert ver_e(proofs, w["stmt"], wrong_ids) == bytes(n) == ver_o(proofs, w["stmt"], wrong_ids)
