@@ -15,6 +15,7 @@
  */
 #include "bidder.h"
 #include "bulletinBoard.h"
+#include "dataTracker.h"
 
 #include <chrono>
 #include <cstdio>
@@ -125,8 +126,9 @@ int main(int argc, char **argv) {
     bb.addCommitmentMsg(bidders[j].commitBid(), j);
   }
   t_prove += secs(t, now());
+  const std::vector<CommitmentPub> &all_cp = bb.getCommitments(); /* one read of the board for the dump */
   for (size_t j = 0; j < n; ++j) {
-    const CommitmentPub &cp = bb.getCommitments()[j];
+    const CommitmentPub &cp = all_cp[j];
     for (size_t i = 0; i < c; ++i) {
       put_point(cp[i].phi);
       put_point(cp[i].A);
@@ -158,8 +160,9 @@ int main(int argc, char **argv) {
       bb.addRoundOneMsg(bidders[j].roundOne(step), j);
     }
     t_prove += secs(t, now());
+    const std::vector<RoundOnePub> &all_r1 = bb.getRoundOnePubs();
     for (size_t j = 0; j < n; ++j) {
-      const RoundOnePub &p = bb.getRoundOnePubs()[j];
+      const RoundOnePub &p = all_r1[j];
       put_point(p.X);
       put_point(p.R);
       put_pok(p.pokdlogX);
@@ -180,8 +183,9 @@ int main(int argc, char **argv) {
       bb.addRoundTwoMsg(bidders[j].roundTwo(bb.getRoundOneXs(), step), j);
     }
     t_prove += secs(t, now());
+    const std::vector<RoundTwoPub> &all_r2 = bb.getRoundTwoPubs();
     for (size_t j = 0; j < n; ++j) {
-      const RoundTwoPub &p = bb.getRoundTwoPubs()[j];
+      const RoundTwoPub &p = all_r2[j];
       put_u32(p.stage == STAGE1 ? 1 : 2);
       put_point(p.b);
       if (p.stage == STAGE1) {
@@ -231,8 +235,11 @@ int main(int argc, char **argv) {
   for (int i = 0; i < 32; ++i) sprintf(hex + 2 * i, "%02x", dg[i]);
   fprintf(stderr,
           "{\"impl\":\"reference-tierA\",\"n\":%zu,\"c\":%zu,\"seed\":%llu,\"ok\":%s,\"maxbid\":%llu,"
-          "\"bytes\":%zu,\"sha256\":\"%s\",\"draws\":%llu,\"t_prove_s\":%.3f,\"t_verify_s\":%.3f,\"t_total_s\":%.3f}\n",
+          "\"bytes\":%zu,\"sha256\":\"%s\",\"draws\":%llu,\"t_prove_s\":%.3f,\"t_verify_s\":%.3f,\"t_total_s\":%.3f,"
+          "\"data_bidder\":%zu,\"data_verifier\":%zu,\"data_total\":%zu}\n",
           n, c, (unsigned long long)seed, ok ? "true" : "false", (unsigned long long)truemax, OUT.size(), hex,
-          (unsigned long long)pa_shim_draws(), t_prove, t_verify, secs(t0, now()));
+          (unsigned long long)pa_shim_draws(), t_prove, t_verify, secs(t0, now()),
+          DataTracker::getInstance().getCategoryDataSize(BIDDER_CATEGORY),
+          DataTracker::getInstance().getCategoryDataSize(VERIFIER_CATEGORY), DataTracker::getInstance().getTotalDataSize());
   return ok ? 0 : 1;
 }

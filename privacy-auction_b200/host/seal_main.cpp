@@ -1,0 +1,170 @@
+// ./SEAL <#bidders> <bit length of bids> [options]
+//
+// The reference's command line (SEAL/main.cpp:13-20): two positional arguments,
+// phases run in the same order, the same summary block, exit code 0 when every
+// verification held and every bidder computed the true maximum bid, 1 otherwise.
+// Options added here (the reference is unseeded and never serialises anything):
+//   --seed S          seed of the PA draw stream (default 1)
+//   --bids a,b,...    explicit bids instead of pseudo-random ones
+//   --transcript F    write the PASEALT1 transcript of everything published
+//   --no-verify       skip the verify* calls (ENABLE_VERIFICATION off)
+//   --device D        CUDA device ordinal
+//   --quiet           no per-object chatter
+#include "bidder.h"
+#include "bulletinBoard.h"
+#include "engine.h"
+#include "params.h"
+#include "print.h"
+#include "trackers.h"
+
+#include <algorithm>
+#include <bitset>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <vector>
+
+static std::vector<uint8_t> T;
+static void put(const void *p, size_t n) { T.insert(T.end(), (const uint8_t *)p, (const uint8_t *)p + n); }
+static void put_u64(uint64_t v) {
+  for (int i = 0; i < 8; ++i) T.push_back((uint8_t)(v >> (8 * i)));
+}
+static void put_u32(uint32_t v) {
+  for (int i = 0; i < 4; ++i) T.push_back((uint8_t)(v >> (8 * i)));
+}
+
+int main(int argc, char *argv[]) {
+  std::vector<std::string> pos;
+  std::string bidarg, transcript;
+  bool verify = true;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "--seed" && i + 1 < argc) pa_host::config().seed = std::stoull(argv[++i]);
+    else if (a == "--bids" && i + 1 < argc) bidarg = argv[++i];
+    else if (a == "--transcript" && i + 1 < argc) transcript = argv[++i];
+    else if (a == "--device" && i + 1 < argc) pa_host::config().device = std::stoi(argv[++i]);
+    else if (a == "--no-verify") verify = false;
+    else if (a == "--quiet") pa_host::quiet() = true;
+    else pos.push_back(a);
+  }
+  if (pos.size() != 2) {
+    PRINT_ERROR("Usage: " << argv[0] << " <#bidders> <bit length of bids> [--seed S] [--bids a,b,..] [--transcript F] [--no-verify]");
+    exit(1);
+  }
+  size_t n = std::stoul(pos[0]);
+  size_t c = std::stoul(pos[1]);
+  bool flag = true;
+
+  std::vector<size_t> bids;
+  std::vector<Bidder> bidders;
+  BulletinBoard bb(n, c);
+
+  PRINT_MESSAGE("#bidders: n = " << n << ", bit length of bids: c = " << c);
+
+  // =============== Initialization phase ============
+  std::vector<size_t> given;
+  for (size_t pos2 = 0; !bidarg.empty() && pos2 <= bidarg.size();) {
+    size_t e = bidarg.find(',', pos2);
+    given.push_back(std::stoull(bidarg.substr(pos2, e == std::string::npos ? e : e - pos2)));
+    if (e == std::string::npos) break;
+    pos2 = e + 1;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    bidders.push_back(given.size() == n ? Bidder(i, n, c, given[i]) : Bidder(i, n, c));
+    bids.push_back(bidders[i].getBid());
+  }
+  auto maxBid = n ? *std::max_element(bids.begin(), bids.end()) : 0;
+  PRINT_MESSAGE("Finished initialization.\nMax bid: " << maxBid << ", Max bid (in binary): "
+                                                      << std::bitset<C_MAX>(maxBid).to_string().substr(C_MAX - c));
+  put("PASEALT1", 8);
+  put_u64(n), put_u64(c), put_u64(pa_host::config().seed);
+  for (size_t b : bids) put_u64(b);
+
+  // =============== Commit phase ====================
+  for (size_t j = 0; j < n; ++j) bb.addCommitmentMsg(bidders[j].commitBid(), j);
+  for (auto &cp : bb.getCommitments())
+    for (auto &cb : cp) put(&cb, sizeof cb);
+
+  // =============== Verify commitments ==============
+  for (size_t j = 0; j < n; ++j) {
+    bool ok = verify ? bidders[j].verifyCommitment(bb.getCommitments()) : true;
+    T.push_back(ok ? 1 : 0);
+    if (!ok) {
+      PRINT_ERROR("Bidder " << j << " failed to verify commitments.");
+      exit(1);
+    }
+  }
+
+  // ===== Auction phase, i is the step, j is the bidder id =====
+  for (size_t i = 0; i < c; ++i) {
+    // =============== Round One =======================
+    for (size_t j = 0; j < n; ++j) bb.addRoundOneMsg(bidders[j].roundOne(i), j);
+    for (auto &p : bb.getRoundOnePubs()) put(&p, sizeof p);
+    for (size_t j = 0; j < n; ++j) {
+      bool ok = verify ? bidders[j].verifyRoundOne(bb.getRoundOnePubs()) : true;
+      T.push_back(ok ? 1 : 0);
+      if (!ok) {
+        PRINT_ERROR("Bidder " << j << " failed to verify round one in step " << i << ".");
+        exit(1);
+      }
+    }
+    // =============== Round Two =======================
+    for (size_t j = 0; j < n; ++j) bb.addRoundTwoMsg(bidders[j].roundTwo(bb.getRoundOneXs(), i), j);
+    for (auto &p : bb.getRoundTwoPubs()) {
+      put_u32(p.stage == STAGE1 ? 1 : 2);
+      put(&p.b, sizeof p.b);
+      if (p.stage == STAGE1) put(&p.powf.powfstage1, sizeof p.powf.powfstage1);
+      else put(&p.powf.powfstage2, sizeof p.powf.powfstage2);
+    }
+    for (size_t j = 0; j < n; ++j) {
+      bool ok = verify ? bidders[j].verifyRoundTwo(bb.getRoundTwoPubs(), i) : true;
+      T.push_back(ok ? 1 : 0);
+      if (!ok) {
+        PRINT_ERROR("Bidder " << j << " failed to verify round two in step " << i << ".");
+        exit(1);
+      }
+    }
+    // =============== Round Three =====================
+    for (size_t j = 0; j < n; ++j) T.push_back((uint8_t)bidders[j].roundThree(bb.getRoundTwoBs(), i));
+  }
+  for (size_t j = 0; j < n; ++j) put_u64(bidders[j].getMaxBid());
+
+  // =============== Print info ======================
+  PRINT_INFO("#bidders: n = " << n << ", bit length of bids: c = " << c << std::endl
+             << "Time (one bidder): " << TimeTracker::getInstance().getCategoryTimeInSeconds(BIDDER_CATEGORY) / n << " s." << std::endl
+             << "Time (one verifier): " << TimeTracker::getInstance().getCategoryTimeInSeconds(VERIFIER_CATEGORY) / n << " s." << std::endl
+             << "Data (one bidder): " << DataTracker::getInstance().getCategoryDataSizeInMB(BIDDER_CATEGORY) / n << " MB" << std::endl
+             << "Data (one verifier): " << DataTracker::getInstance().getCategoryDataSizeInMB(VERIFIER_CATEGORY) / n << " MB" << std::endl
+             << "Data (total communication, #bidders=" << n << " ,#verifiers=" << n
+             << "): " << DataTracker::getInstance().getTotalDataSizeInMB() << " MB");
+
+  // machine-readable summary on stderr (byte counts follow the reference's DataTracker rules)
+  fprintf(stderr, "{\"impl\":\"b200\",\"n\":%zu,\"c\":%zu,\"seed\":%llu,\"maxbid\":%zu,\"bytes\":%zu,\"data_bidder\":%zu,\"data_verifier\":%zu,\"data_total\":%zu,\"t_bidder_s\":%.4f,\"t_verifier_s\":%.4f}\n",
+          n, c, (unsigned long long)pa_host::config().seed, (size_t)maxBid, T.size(),
+          DataTracker::getInstance().getCategoryDataSize(BIDDER_CATEGORY), DataTracker::getInstance().getCategoryDataSize(VERIFIER_CATEGORY),
+          DataTracker::getInstance().getTotalDataSize(), TimeTracker::getInstance().getCategoryTimeInSeconds(BIDDER_CATEGORY),
+          TimeTracker::getInstance().getCategoryTimeInSeconds(VERIFIER_CATEGORY));
+
+  if (!transcript.empty()) {
+    FILE *f = fopen(transcript.c_str(), "wb");
+    if (!f) {
+      perror("fopen");
+      exit(1);
+    }
+    fwrite(T.data(), 1, T.size(), f);
+    fclose(f);
+  }
+
+  // ============== Test Correctness =================
+  for (size_t i = 0; i < n; ++i) {
+    if (bidders[i].getMaxBid() != maxBid) {
+      flag = false;
+      PRINT_ERROR("Bidder " << i << " failed to calculate max bid.");
+    }
+  }
+  if (!flag) exit(1);
+  PRINT_MESSAGE("Finished auction, all bidder calculated max bid.\nMax bid: "
+                << maxBid << ", Max bid (in binary): " << std::bitset<C_MAX>(maxBid).to_string().substr(C_MAX - c));
+  return 0;
+}

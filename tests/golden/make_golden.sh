@@ -10,3 +10,5 @@ for cfg in "3 4 42 -" "1 3 1 5" "2 3 1 -" "4 6 7 -" "5 5 11 0,0,0,0,0" "3 8 5 25
   set -- $cfg
   ./oracle/_ref/seal_ref "$1" "$2" "$3" "$4" "tests/golden/seal_n$1_c$2_s$3.bin"
 done
+# tests/golden/seal_reference_summary.json holds, per transcript, the JSON line seal_ref
+# prints on stderr (sha256 of the transcript, max bid, the reference's DataTracker byte totals).

@@ -1,0 +1,48 @@
+"""The host C++ mirror of the reference's Bidder / BulletinBoard classes and the
+`SEAL <n> <c>` command line (privacy-auction_b200/host), run as the reference's
+own tests run it (exit code, SEAL/tests/CMakeLists.txt), and compared with the
+transcripts and DataTracker byte totals of the unmodified reference."""
+import glob
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+import seal_flow
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEAL = os.path.join(ROOT, "privacy-auction_b200", "bin", "SEAL")
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "seal_*.bin")))
+SUMMARY = json.load(open(os.path.join(ROOT, "tests", "golden", "seal_reference_summary.json")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_cli_reproduces_reference(tmp_path, path):
+    gold = open(path, "rb").read()
+    t = seal_flow.parse_transcript(gold)
+    out = tmp_path / "t.bin"
+    r = subprocess.run([SEAL, str(t["n"]), str(t["c"]), "--seed", str(t["seed"]), "--bids", ",".join(map(str, t["bids"])),
+                        "--transcript", str(out), "--quiet"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert out.read_bytes() == gold
+    s = json.loads([l for l in r.stderr.splitlines() if l.startswith("{")][-1])
+    ref = SUMMARY[os.path.basename(path)]
+    assert s["maxbid"] == ref["maxbid"]
+    assert (s["data_bidder"], s["data_verifier"], s["data_total"]) == (ref["data_bidder"], ref["data_verifier"], ref["data_total"])
+
+
+def test_cli_gentests_style_sweep():
+    """the reference's own test: random `<n> <c>` pairs, pass = exit code 0 (tests/genTests.py:13-17)"""
+    rnd = random.Random(2024)
+    for _ in range(6):
+        n, c = rnd.randint(1, 8), rnd.randint(1, 12)
+        r = subprocess.run([SEAL, str(n), str(c), "--seed", str(rnd.randrange(1 << 30)), "--quiet"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (n, c, r.stderr[-1500:])
+
+
+def test_cli_usage_error():
+    r = subprocess.run([SEAL, "3"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage" in r.stderr
