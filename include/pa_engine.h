@@ -194,6 +194,54 @@ int pa_point_sum_is_inf_dev(pa_ctx *ctx, const uint8_t *d_B, const uint32_t *d_o
 int pa_rng_fill(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n);
 int pa_rng_fill_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *d_streams, uint64_t *d_counters, size_t per_item, uint8_t *d_out, size_t n);
 
+/* ---- whole auctions ------------------------------------------------------------------------
+ * pa_seal_run advances every bidder of a batch of SEAL auctions in lock step with all state
+ * resident in HBM: what the reference's main does one bidder and one EC_POINT_mul at a time
+ * (SEAL/main.cpp:32-120).  Every published proof is verified once (the reference lets each
+ * of the n bidders repeat the same deterministic checks); verdicts are the same.
+ *
+ * Bidder j of auction a draws from PA stream (seed, (auction_id[a] << 32) | j) in the
+ * reference's draw order, so the output is a function of
+ * (seed, n, c, bids) only.
+ *
+ * Partitioning over GPUs (one process per GPU):
+ *   - independent auctions: give each rank its own auctions; no exchange;
+ *   - ONE auction sharded by bidder slice: every rank passes the same n / c, its own id
+ *     range [lo, hi) and the bids of that range, plus an all-gather callback.  Once per
+ *     step the X_i and once the b_i of a slice (slice * 64 bytes, zero padded) are placed in
+ *     d_send; allgather(user, which) must leave the concatenation of all ranks' d_send, in
+ *     rank order, in d_recv (ranks own ascending id ranges of `slice` bidders each) and
+ *     return 0 when d_recv is ready.  Each rank proves and verifies its own slice.
+ *
+ * Optional host outputs ("sections", NULL to skip), m = local bidders, slot = position of a
+ * local bidder (auction-major, id order), Mb = sum over local bidders of c:
+ *   out_commit    [Mb x 736]  CommitmentPerBit records, bidder-major      out_commit_ok [Mb]
+ *   out_r1        [cmax x m x 320]  RoundOnePub records                  out_r1_ok  [cmax x m]
+ *   out_r2_tag    [cmax x m]  1 = stage 1, 2 = stage 2, 0 = auction over  out_r2_ok  [cmax x m]
+ *   out_r2_b      [cmax x m x 64]   out_r2_proof [cmax x m x 1344] (stage 1 uses 672)
+ *   out_r3        [cmax x n_auctions]  1 = deciding step
+ * tests/seal_flow.py turns sections into the PASEALT1 transcript. */
+typedef int (*pa_allgather_fn)(void *user, int which /* 0: X of round one, 1: b of round two */);
+typedef struct {
+  uint64_t seed;
+  size_t n_auctions;
+  const uint32_t *n;            /* [n_auctions] bidders per auction */
+  const uint32_t *c;            /* [n_auctions] bits per bid (<= 64) */
+  const uint64_t *auction_ids;  /* [n_auctions] or NULL for 0 .. n_auctions-1 */
+  const uint64_t *bids;         /* bids of the local bidders, auction-major, id order */
+  int verify;                   /* 0: skip verification, 1: verify every proof once */
+  /* sharding of one auction (allgather != NULL requires n_auctions == 1) */
+  uint32_t lo, hi, slice;
+  pa_allgather_fn allgather;
+  void *user;
+  uint8_t *d_send, *d_recv;     /* device buffers: slice * 64 and world * slice * 64 bytes */
+  /* outputs */
+  uint64_t *max_bid;            /* [n_auctions] */
+  uint8_t *ok;                  /* [n_auctions] 1 = every local verification held */
+  uint8_t *out_commit, *out_commit_ok, *out_r1, *out_r1_ok, *out_r2_tag, *out_r2_b, *out_r2_proof, *out_r2_ok, *out_r3;
+} pa_seal_job;
+int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job);
+
 /* ---- measurement ----------------------------------------------------------
  * Per-kernel device timing: between pa_profile_begin and pa_profile_end every
  * kernel the context launches is bracketed by CUDA events on the context's

@@ -494,32 +494,32 @@ int staged(pa_ctx *ctx, const HArg *args, int nargs, F run) {
 
 // work arena for proofs: [ Jacobian scratch | prefix | derived scalars | check bytes ]
 template <int KIND, int NCHK>
-int verify_dev(pa_ctx *ctx, const unsigned char *proofs, size_t pstride, const unsigned char *stmts, const u64 *ids,
-               unsigned char *verdict, size_t n) {
+int verify_dev(pa_ctx *ctx, const unsigned char *proofs, const unsigned char *stmts, const u64 *ids,
+               unsigned char *verdict, size_t n, pa_lay L = pa_lay_packed<KIND>()) {
   if (n == 0) return PA_OK;
   size_t need = n * 32 + n * NCHK + 512;
   int rc = ensure(ctx, &ctx->d_work, &ctx->work_bytes, need);
   if (rc) return rc;
   u32 *derived = (u32 *)ctx->d_work;
   unsigned char *chk = ctx->d_work + align_up(n * 32, 256);
-  PA_LAUNCH(ctx, PA_K_VDERIVE, (k_verify_derive<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, pstride, stmts, ids, derived, (int)n)));
-  PA_LAUNCH(ctx, PA_K_VCHECKS, (k_verify_checks<KIND, NCHK><<<grid_for(n * NCHK), PA_BLOCK, 0, ctx->stream>>>(proofs, pstride, stmts, derived, ctx->d_comb, chk, (int)n)));
+  PA_LAUNCH(ctx, PA_K_VDERIVE, (k_verify_derive<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, derived, (int)n, L)));
+  PA_LAUNCH(ctx, PA_K_VCHECKS, (k_verify_checks<KIND, NCHK><<<grid_for(n * NCHK), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, derived, ctx->d_comb, chk, (int)n, L)));
   PA_LAUNCH(ctx, PA_K_VERDICT, (k_verdict<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(chk, NCHK, (int)n, verdict)));
   return PA_OK;
 }
 
 template <int KIND>
 int prove_dev(pa_ctx *ctx, const unsigned char *stmts, const unsigned char *secrets, const unsigned char *b0,
-              const unsigned char *b1, const u64 *ids, const unsigned char *rnd, unsigned char *proofs, size_t pstride,
-              size_t n) {
+              const unsigned char *b1, const u64 *ids, const unsigned char *rnd, unsigned char *proofs, size_t n,
+              pa_lay L = pa_lay_packed<KIND>()) {
   typedef proof_kind<KIND> K;
   if (n == 0) return PA_OK;
   size_t m = n * K::NEPS;
   int rc = work_reserve(ctx, m);
   if (rc) return rc;
-  PA_LAUNCH(ctx, PA_K_POPS, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n)));
-  if ((rc = normalize_to(ctx, proofs, m, K::NEPS, pstride))) return rc;
-  PA_LAUNCH(ctx, PA_K_PRESPOND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, pstride, stmts, ids, secrets, rnd, b0, b1, (int)n)));
+  PA_LAUNCH(ctx, PA_K_POPS, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n, L)));
+  if ((rc = normalize_to(ctx, proofs, m, K::NEPS, L.proof))) return rc;
+  PA_LAUNCH(ctx, PA_K_PRESPOND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, secrets, rnd, b0, b1, (int)n, L)));
   return PA_OK;
 }
 
@@ -530,35 +530,35 @@ extern "C" {
 // ---- device-pointer entry points -------------------------------------------------------
 int pa_pokdlog_prove_dev(pa_ctx *ctx, const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (X && x && ids && rnd && proofs)) && n < (1u << 26));
-  return prove_dev<PA_POK>(ctx, X, x, nullptr, nullptr, (const u64 *)ids, rnd, proofs, 96, n);
+  return prove_dev<PA_POK>(ctx, X, x, nullptr, nullptr, (const u64 *)ids, rnd, proofs, n);
 }
 int pa_pokdlog_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *X, const uint64_t *ids, uint8_t *verdict, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && X && ids && verdict)) && n < (1u << 26));
-  return verify_dev<PA_POK, 1>(ctx, proofs, 96, X, (const u64 *)ids, verdict, n);
+  return verify_dev<PA_POK, 1>(ctx, proofs, X, (const u64 *)ids, verdict, n);
 }
 int pa_powfcom_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *alpha, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && alpha && bits && ids && rnd && proofs)) && n < (1u << 26));
-  return prove_dev<PA_COM>(ctx, stmt, alpha, bits, nullptr, (const u64 *)ids, rnd, proofs, 352, n);
+  return prove_dev<PA_COM>(ctx, stmt, alpha, bits, nullptr, (const u64 *)ids, rnd, proofs, n);
 }
 int pa_powfcom_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
-  return verify_dev<PA_COM, 4>(ctx, proofs, 352, stmt, (const u64 *)ids, verdict, n);
+  return verify_dev<PA_COM, 4>(ctx, proofs, stmt, (const u64 *)ids, verdict, n);
 }
 int pa_stage1_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)) && n < (1u << 26));
-  return prove_dev<PA_S1>(ctx, stmt, secrets, bits, nullptr, (const u64 *)ids, rnd, proofs, 672, n);
+  return prove_dev<PA_S1>(ctx, stmt, secrets, bits, nullptr, (const u64 *)ids, rnd, proofs, n);
 }
 int pa_stage1_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
-  return verify_dev<PA_S1, 8>(ctx, proofs, 672, stmt, (const u64 *)ids, verdict, n);
+  return verify_dev<PA_S1, 8>(ctx, proofs, stmt, (const u64 *)ids, verdict, n);
 }
 int pa_stage2_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bi && bj && ids && rnd && proofs)) && n < (1u << 26));
-  return prove_dev<PA_S2>(ctx, stmt, secrets, bi, bj, (const u64 *)ids, rnd, proofs, 1344, n);
+  return prove_dev<PA_S2>(ctx, stmt, secrets, bi, bj, (const u64 *)ids, rnd, proofs, n);
 }
 int pa_stage2_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
-  return verify_dev<PA_S2, 16>(ctx, proofs, 1344, stmt, (const u64 *)ids, verdict, n);
+  return verify_dev<PA_S2, 16>(ctx, proofs, stmt, (const u64 *)ids, verdict, n);
 }
 
 int pa_commit_points_dev(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n) {
@@ -575,13 +575,13 @@ int pa_y_scan_dev(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, const uint32_t *off
   if (npoints == 0) return PA_OK;
   int rc = work_reserve(ctx, npoints);
   if (rc) return rc;
-  PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)nseg, PA_SCAN_T, 0, ctx->stream>>>(X, offsets, (int)npoints, work_jac(ctx))));
+  PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)nseg, PA_SCAN_T, 0, ctx->stream>>>(X, 64, offsets, (int)npoints, work_jac(ctx))));
   return normalize_to(ctx, Y, npoints);
 }
 
 int pa_point_sum_is_inf_dev(pa_ctx *ctx, const uint8_t *B, const uint32_t *offsets, size_t nseg, size_t npoints, int32_t *flags) {
   PA_ARGCHECK(ctx, ctx && flags && (npoints == 0 || B) && nseg >= 1);
-  PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<(unsigned)nseg, PA_SCAN_T, 0, ctx->stream>>>(B, offsets, (int)npoints, flags)));
+  PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<(unsigned)nseg, PA_SCAN_T, 0, ctx->stream>>>(B, 64, offsets, (int)npoints, flags)));
   return PA_OK;
 }
 
@@ -595,7 +595,7 @@ int pa_challenge_dev(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_
 int pa_rng_fill_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
   if (n == 0 || per_item == 0) return PA_OK;
-  PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(seed, (const u64 *)streams, (u64 *)counters, (int)per_item, out, (int)n)));
+  PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(seed, (const u64 *)streams, (u64 *)counters, nullptr, (int)per_item, out, (int)n)));
   return PA_OK;
 }
 
@@ -687,3 +687,5 @@ int pa_rng_fill(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *c
 }
 
 }  // extern "C"
+
+#include "pa_seal.cuh"

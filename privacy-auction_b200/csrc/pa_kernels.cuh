@@ -285,14 +285,25 @@ __global__ void k_peak_fe(u32 *sink, int iters, int sqr) {
 
 
 // ---- proofs: one thread per operation -----------------------------------------------
+// Byte strides between consecutive items, so that proofs, statements, secrets and
+// draws can live inside larger records (e.g. the Schnorr proof of A sits at offset
+// 192 of a 736-byte commitment record whose offset 64 is its statement).
+struct pa_lay {
+  size_t proof, stmt, secret, rnd;
+};
+template <int KIND> inline pa_lay pa_lay_packed() {
+  typedef proof_kind<KIND> K;
+  return pa_lay{(size_t)K::REC, (size_t)K::NSTMT * 64, (size_t)K::NSECRET * 32, (size_t)K::NRND * 32};
+}
+
 // verifier step 1: challenge + unpublished challenge share, one thread per proof
 template <int KIND>
 __global__ void __launch_bounds__(PA_BLOCK)
-k_verify_derive(const unsigned char *proofs, size_t pstride, const unsigned char *stmts, const u64 *ids, u32 *derived, int n) {
+k_verify_derive(const unsigned char *proofs, const unsigned char *stmts, const u64 *ids, u32 *derived, int n, pa_lay L) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   sc ch1;
-  verify_derive<KIND>(ch1, proofs + pstride * i, stmts + (size_t)proof_kind<KIND>::NSTMT * 64 * i, ids[i]);
+  verify_derive<KIND>(ch1, proofs + L.proof * i, stmts + L.stmt * i, ids[i]);
 #pragma unroll
   for (int k = 0; k < 8; ++k) derived[8 * (size_t)i + k] = ch1.v[k];
 }
@@ -300,15 +311,15 @@ k_verify_derive(const unsigned char *proofs, size_t pstride, const unsigned char
 // runs the same check, hence the same shape, for 32 proofs)
 template <int KIND, int NCHK>
 __global__ void __launch_bounds__(PA_BLOCK)
-k_verify_checks(const unsigned char *proofs, size_t pstride, const unsigned char *stmts, const u32 *derived,
-                const u32 *__restrict__ comb, unsigned char *chk, int n) {
+k_verify_checks(const unsigned char *proofs, const unsigned char *stmts, const u32 *derived,
+                const u32 *__restrict__ comb, unsigned char *chk, int n, pa_lay L) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * NCHK) return;
   int j = t / n, i = t % n;
   sc ch1;
 #pragma unroll
   for (int k = 0; k < 8; ++k) ch1.v[k] = derived[8 * (size_t)i + k];
-  bool ok = verify_check_one<KIND>(j, proofs + pstride * i, stmts + (size_t)proof_kind<KIND>::NSTMT * 64 * i, ch1, comb);
+  bool ok = verify_check_one<KIND>(j, proofs + L.proof * i, stmts + L.stmt * i, ch1, comb);
   chk[t] = ok ? 1 : 0;
 }
 // verifier step 3: verdict = AND of all checks (no early exit, as SEAL/bidder.cpp:244-298)
@@ -329,27 +340,24 @@ PA_D int proof_branch(int kind, const unsigned char *b0, const unsigned char *b1
 template <int KIND>
 __global__ void __launch_bounds__(PA_BLOCK)
 k_prove_ops(const unsigned char *stmts, const unsigned char *rnd, const unsigned char *b0, const unsigned char *b1,
-            const u32 *__restrict__ comb, u32 *jout, int n) {
+            const u32 *__restrict__ comb, u32 *jout, int n, pa_lay L) {
   typedef proof_kind<KIND> K;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * K::NEPS) return;
   int j = t / n, i = t % n;
   jac r;
-  int e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + (size_t)K::NSTMT * 64 * i,
-                             rnd + (size_t)K::NRND * 32 * i, comb);
+  int e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + L.stmt * i, rnd + L.rnd * i, comb);
   st_jac(jout + 24 * ((size_t)i * K::NEPS + e), r);
 }
 // prover step 3 (after k_normalize wrote the eps points): challenge and responses
 template <int KIND>
 __global__ void __launch_bounds__(PA_BLOCK)
-k_prove_respond(unsigned char *proofs, size_t pstride, const unsigned char *stmts, const u64 *ids,
-                const unsigned char *secrets, const unsigned char *rnd, const unsigned char *b0,
-                const unsigned char *b1, int n) {
-  typedef proof_kind<KIND> K;
+k_prove_respond(unsigned char *proofs, const unsigned char *stmts, const u64 *ids, const unsigned char *secrets,
+                const unsigned char *rnd, const unsigned char *b0, const unsigned char *b1, int n, pa_lay L) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  prove_respond<KIND>(proofs + pstride * i, stmts + (size_t)K::NSTMT * 64 * i, ids[i],
-                      secrets + (size_t)K::NSECRET * 32 * i, rnd + (size_t)K::NRND * 32 * i, proof_branch(KIND, b0, b1, i));
+  prove_respond<KIND>(proofs + L.proof * i, stmts + L.stmt * i, ids[i], secrets + L.secret * i, rnd + L.rnd * i,
+                      proof_branch(KIND, b0, b1, i));
 }
 
 // ---- generic Fiat-Shamir challenge over k wire points per item ---------------------------
@@ -364,16 +372,18 @@ __global__ void k_challenge(const unsigned char *points, int k, const u64 *ids, 
 }
 
 // ---- PA stream: cnt consecutive BN_rand_range draws per item --------------------------------
-__global__ void k_rng_fill(u64 seed, const u64 *streams, u64 *ctrs, int cnt, unsigned char *out, int n) {
+// idx != NULL: item i uses stream / counter slot idx[i] (a subset of the parties draws)
+__global__ void k_rng_fill(u64 seed, const u64 *streams, u64 *ctrs, const u32 *idx, int cnt, unsigned char *out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  u64 ctr = ctrs[i];
+  int s = idx ? (int)idx[i] : i;
+  u64 ctr = ctrs[s];
   for (int k = 0; k < cnt; ++k) {
     sc r;
-    pa_stream_rand_range(r, seed, streams[i], ctr);
+    pa_stream_rand_range(r, seed, streams[s], ctr);
     st_sc(out + 32 * ((size_t)i * cnt + k), r);
   }
-  ctrs[i] = ctr;
+  ctrs[s] = ctr;
 }
 
 // ---- commitment points: phi = g^(alpha beta + bit), A = g^alpha, B = g^beta -------------------
@@ -408,7 +418,7 @@ k_commit_points(const unsigned char *alpha, const unsigned char *beta, const uns
 // whatever the association order.  offs[s] .. offs[s+1] delimit auction s.
 #define PA_SCAN_T 128
 __global__ void __launch_bounds__(PA_SCAN_T)
-k_y_scan(const unsigned char *X, const u32 *offs, int nseg_single, u32 *jout) {
+k_y_scan(const unsigned char *X, size_t xstride, const u32 *offs, int nseg_single, u32 *jout) {
   __shared__ __align__(16) u32 part[2][PA_SCAN_T][24];
   int seg = blockIdx.x;
   int lo = offs ? (int)offs[seg] : 0, hi = offs ? (int)offs[seg + 1] : nseg_single;
@@ -419,7 +429,7 @@ k_y_scan(const unsigned char *X, const u32 *offs, int nseg_single, u32 *jout) {
   jac_set_inf(s);
   for (int id = c0; id < c1; ++id) {
     aff x;
-    ld_aff(x, X + 64 * (size_t)(lo + id));
+    ld_aff(x, X + xstride * (size_t)(lo + id));
     jac_madd(s, s, x);
   }
   st_jac(part[0][t], s);
@@ -443,7 +453,7 @@ k_y_scan(const unsigned char *X, const u32 *offs, int nseg_single, u32 *jout) {
   if (t == 0) jac_set_inf(e); else ld_jac(e, part[cur][t - 1]);
   for (int id = c0; id < c1; ++id) {
     aff x;
-    ld_aff(x, X + 64 * (size_t)(lo + id));
+    ld_aff(x, X + xstride * (size_t)(lo + id));
     jac p, y;
     jac_madd(p, e, x);     // inclusive prefix
     jac_add(y, e, p);      // E + P
@@ -455,7 +465,7 @@ k_y_scan(const unsigned char *X, const u32 *offs, int nseg_single, u32 *jout) {
 
 // ---- round three: is sum_i b_i the point at infinity?  (SEAL/bidder.cpp:1393-1397) ----------------
 __global__ void __launch_bounds__(PA_SCAN_T)
-k_point_sum_is_inf(const unsigned char *B, const u32 *offs, int nseg_single, int *flags) {
+k_point_sum_is_inf(const unsigned char *B, size_t bstride, const u32 *offs, int nseg_single, int *flags) {
   __shared__ __align__(16) u32 part[PA_SCAN_T][24];
   int seg = blockIdx.x;
   int lo = offs ? (int)offs[seg] : 0, hi = offs ? (int)offs[seg + 1] : nseg_single;
@@ -464,7 +474,7 @@ k_point_sum_is_inf(const unsigned char *B, const u32 *offs, int nseg_single, int
   jac_set_inf(s);
   for (int id = t; id < m; id += PA_SCAN_T) {
     aff x;
-    ld_aff(x, B + 64 * (size_t)(lo + id));
+    ld_aff(x, B + bstride * (size_t)(lo + id));
     jac_madd(s, s, x);
   }
   st_jac(part[t], s);

@@ -71,6 +71,7 @@ SIGNATURES = {
     "pa_point_sum_is_inf_dev": (ctypes.c_int, [_ctx, _vp, _vp, _sz, _sz, _vp]),
     "pa_rng_fill": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_rng_fill_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
+    "pa_seal_run": (ctypes.c_int, [_ctx, _vp]),
     "pa_profile_begin": (ctypes.c_int, [_ctx]),
     "pa_profile_end": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.POINTER(_sz)]),
 }
@@ -78,6 +79,23 @@ SIGNATURES = {
 
 class KernelStat(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 32), ("launches", ctypes.c_uint64), ("total_ms", ctypes.c_double)]
+
+
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int)
+
+
+class SealJob(ctypes.Structure):
+    """pa_seal_job of include/pa_engine.h"""
+    _fields_ = [
+        ("seed", ctypes.c_uint64), ("n_auctions", ctypes.c_size_t), ("n", ctypes.c_void_p), ("c", ctypes.c_void_p),
+        ("auction_ids", ctypes.c_void_p), ("bids", ctypes.c_void_p), ("verify", ctypes.c_int),
+        ("lo", ctypes.c_uint32), ("hi", ctypes.c_uint32), ("slice", ctypes.c_uint32),
+        ("allgather", ALLGATHER_FN), ("user", ctypes.c_void_p), ("d_send", ctypes.c_void_p), ("d_recv", ctypes.c_void_p),
+        ("max_bid", ctypes.c_void_p), ("ok", ctypes.c_void_p),
+        ("out_commit", ctypes.c_void_p), ("out_commit_ok", ctypes.c_void_p), ("out_r1", ctypes.c_void_p),
+        ("out_r1_ok", ctypes.c_void_p), ("out_r2_tag", ctypes.c_void_p), ("out_r2_b", ctypes.c_void_p),
+        ("out_r2_proof", ctypes.c_void_p), ("out_r2_ok", ctypes.c_void_p), ("out_r3", ctypes.c_void_p),
+    ]
 
 
 class EngineError(RuntimeError):
@@ -326,6 +344,56 @@ class Engine:
         b = [_buf(struct.pack(f"<{n}Q", *streams)), _buf(ctr), _buf(out)]
         self._check(self.lib.pa_rng_fill(self.ctx, seed, b[0][0], b[1][0], per_item, b[2][0], n))
         return bytes(out), list(struct.unpack(f"<{n}Q", bytes(ctr)))
+
+    def seal_run(self, seed, n, c, bids, verify=True, sections=False, auction_ids=None, shard=None):
+        """pa_seal_run: whole SEAL auctions, device resident.
+        n, c: per-auction lists; bids: flat list of the LOCAL bidders' bids (auction-major).
+        shard = dict(lo, hi, slice, d_send, d_recv, allgather=callable(which) -> 0) for one
+        auction sharded by bidder slice.  Returns dict(max_bid, ok[, sections...])."""
+        A = len(n)
+        m = len(bids)
+        n_arr = (ctypes.c_uint32 * A)(*n)
+        c_arr = (ctypes.c_uint32 * A)(*c)
+        bid_arr = (ctypes.c_uint64 * max(m, 1))(*bids)
+        max_bid = (ctypes.c_uint64 * A)()
+        ok = (ctypes.c_uint8 * A)()
+        job = SealJob()
+        job.seed, job.n_auctions = seed, A
+        job.n, job.c, job.bids = ctypes.addressof(n_arr), ctypes.addressof(c_arr), ctypes.addressof(bid_arr)
+        keep = [n_arr, c_arr, bid_arr, max_bid, ok]
+        if auction_ids is not None:
+            aid = (ctypes.c_uint64 * A)(*auction_ids)
+            job.auction_ids = ctypes.addressof(aid)
+            keep.append(aid)
+        job.verify = 1 if verify else 0
+        job.max_bid, job.ok = ctypes.addressof(max_bid), ctypes.addressof(ok)
+        cb = None
+        if shard is not None:
+            fn = shard["allgather"]
+            cb = ALLGATHER_FN(lambda user, which: int(fn(which) or 0))
+            job.lo, job.hi, job.slice = shard["lo"], shard["hi"], shard["slice"]
+            job.allgather = cb
+            job.d_send, job.d_recv = shard["d_send"], shard["d_recv"]
+        out = {}
+        if sections:
+            cmax = max(c)
+            if shard is None:
+                per_bidder_c = [c[a] for a in range(A) for _ in range(n[a])]
+            else:
+                per_bidder_c = [c[0]] * m
+            Mb = sum(per_bidder_c)
+            sizes = {"out_commit": Mb * 736, "out_commit_ok": Mb, "out_r1": cmax * m * 320, "out_r1_ok": cmax * m,
+                     "out_r2_tag": cmax * m, "out_r2_b": cmax * m * 64, "out_r2_proof": cmax * m * 1344,
+                     "out_r2_ok": cmax * m, "out_r3": cmax * A}
+            for name, sz in sizes.items():
+                buf = (ctypes.c_uint8 * max(sz, 1))()
+                setattr(job, name, ctypes.addressof(buf))
+                out[name] = buf
+        self._check(self.lib.pa_seal_run(self.ctx, ctypes.byref(job)))
+        res = {"max_bid": list(max_bid), "ok": [bool(v) for v in ok]}
+        for name, buf in out.items():
+            res[name[4:]] = bytes(buf)
+        return res
 
     def measure_int_peak(self):
         out = (ctypes.c_double * 4)()

@@ -10,6 +10,7 @@
 //   --no-verify       skip the verify* calls (ENABLE_VERIFICATION off)
 //   --device D        CUDA device ordinal
 //   --quiet           no per-object chatter
+//   --profile         per-kernel device time of the run (CUDA events) on stderr
 #include "bidder.h"
 #include "bulletinBoard.h"
 #include "engine.h"
@@ -37,7 +38,7 @@ static void put_u32(uint32_t v) {
 int main(int argc, char *argv[]) {
   std::vector<std::string> pos;
   std::string bidarg, transcript;
-  bool verify = true;
+  bool verify = true, profile = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "--seed" && i + 1 < argc) pa_host::config().seed = std::stoull(argv[++i]);
@@ -46,6 +47,7 @@ int main(int argc, char *argv[]) {
     else if (a == "--device" && i + 1 < argc) pa_host::config().device = std::stoi(argv[++i]);
     else if (a == "--no-verify") verify = false;
     else if (a == "--quiet") pa_host::quiet() = true;
+    else if (a == "--profile") profile = true;
     else pos.push_back(a);
   }
   if (pos.size() != 2) {
@@ -80,6 +82,8 @@ int main(int argc, char *argv[]) {
   put("PASEALT1", 8);
   put_u64(n), put_u64(c), put_u64(pa_host::config().seed);
   for (size_t b : bids) put_u64(b);
+
+  if (profile) pa_profile_begin(pa_host::engine());
 
   // =============== Commit phase ====================
   for (size_t j = 0; j < n; ++j) bb.addCommitmentMsg(bidders[j].commitBid(), j);
@@ -129,6 +133,18 @@ int main(int argc, char *argv[]) {
     for (size_t j = 0; j < n; ++j) T.push_back((uint8_t)bidders[j].roundThree(bb.getRoundTwoBs(), i));
   }
   for (size_t j = 0; j < n; ++j) put_u64(bidders[j].getMaxBid());
+
+  if (profile) {  // per-kernel device time (CUDA events) of the whole auction
+    pa_kernel_stat ks[64];
+    size_t nk = 0;
+    pa_profile_end(pa_host::engine(), ks, 64, &nk);
+    double tot = 0;
+    for (size_t k = 0; k < nk && k < 64; ++k) tot += ks[k].total_ms;
+    for (size_t k = 0; k < nk && k < 64; ++k)
+      fprintf(stderr, "[profile] %-20s launches %6llu  total %9.3f ms  avg %8.4f ms\n", ks[k].name,
+              (unsigned long long)ks[k].launches, ks[k].total_ms, ks[k].total_ms / ks[k].launches);
+    fprintf(stderr, "[profile] all kernels %.3f ms, %llu launches\n", tot, (unsigned long long)pa_ctx_launches(pa_host::engine()));
+  }
 
   // =============== Print info ======================
   PRINT_INFO("#bidders: n = " << n << ", bit length of bids: c = " << c << std::endl

@@ -213,3 +213,50 @@ def parse_transcript(buf):
     t["max_bid"] = list(struct.unpack_from(f"<{n}Q", buf, off)); off += 8 * n
     assert off == len(buf), (off, len(buf))
     return t
+
+
+def sections_to_transcripts(seed, n, c, bids, res):
+    """Assemble the PASEALT1 transcript of every auction from the section arrays
+    pa_seal_run returns (unsharded run: every auction fully local)."""
+    A = len(n)
+    m = sum(n)
+    cmax = max(c)
+    first = [0]
+    for a in range(A):
+        first.append(first[-1] + n[a])
+    boff = [0]
+    for a in range(A):
+        for _ in range(n[a]):
+            boff.append(boff[-1] + c[a])
+
+    def per_verifier(okl):
+        return bytes(1 if all(okl[i] for i in range(len(okl)) if i != j) else 0 for j in range(len(okl)))
+
+    outs = []
+    for a in range(A):
+        na, ca, s0 = n[a], c[a], first[a]
+        out = bytearray(b"PASEALT1" + struct.pack("<QQQ", na, ca, seed))
+        for j in range(na):
+            out += struct.pack("<Q", bids[s0 + j])
+        ok = []
+        for j in range(na):
+            lo, hi = boff[s0 + j], boff[s0 + j + 1]
+            out += res["commit"][736 * lo:736 * hi]
+            ok.append(all(res["commit_ok"][lo:hi]))
+        out += per_verifier(ok) if na > 1 else bytes([1] * na)
+        for step in range(ca):
+            base = step * m + s0
+            for j in range(na):
+                out += res["r1"][320 * (base + j):320 * (base + j + 1)]
+            out += per_verifier([res["r1_ok"][base + j] for j in range(na)])
+            for j in range(na):
+                tag = res["r2_tag"][base + j]
+                rec = 672 if tag == 1 else 1344
+                out += struct.pack("<I", tag) + res["r2_b"][64 * (base + j):64 * (base + j + 1)]
+                out += res["r2_proof"][1344 * (base + j):1344 * (base + j) + rec]
+            out += per_verifier([res["r2_ok"][base + j] for j in range(na)])
+            out += bytes([res["r3"][step * A + a]] * na)
+        for j in range(na):
+            out += struct.pack("<Q", res["max_bid"][a])
+        outs.append(bytes(out))
+    return outs

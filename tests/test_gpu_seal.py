@@ -206,3 +206,44 @@ def test_prove_verify_parity_and_tampering(engine, oracle, kind):
     assert [g == 0 for g in got] == expect_fail
     wrong_ids = [i + 1 for i in w["ids"]]
     assert ver_e(proofs, w["stmt"], wrong_ids) == bytes(n) == ver_o(proofs, w["stmt"], wrong_ids)
+
+
+# ---- the device-resident whole-auction runner (pa_seal_run) ---------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_runner_reproduces_reference_transcript(engine, path):
+    gold = open(path, "rb").read()
+    t = seal_flow.parse_transcript(gold)
+    res = engine.seal_run(t["seed"], [t["n"]], [t["c"]], t["bids"], verify=True, sections=True)
+    assert res["max_bid"] == [max(t["bids"])] and res["ok"] == [True]
+    assert seal_flow.sections_to_transcripts(t["seed"], [t["n"]], [t["c"]], t["bids"], res)[0] == gold
+
+
+def test_runner_batch_of_ragged_auctions_matches_oracle(engine, oracle):
+    """genTests-style batch (tests/genTests.py:13-17): n ~ U{1..20}, c ~ U{1..32}, in ONE lock-step run;
+    every auction's transcript must equal the oracle's run of that auction alone."""
+    rnd = random.Random(404)
+    A = 10
+    n = [rnd.randint(1, 9) for _ in range(A)]
+    c = [rnd.randint(1, 10) for _ in range(A)]
+    n[0], c[0], n[1], c[1] = 1, 1, 1, 7           # degenerate shapes
+    bids, per = [], []
+    for a in range(A):
+        b = [rnd.randrange(1 << c[a]) for _ in range(n[a])]
+        if a == 2:
+            b = [0] * n[a]                         # nobody ever vetoes
+        per.append(b)
+        bids += b
+    ids = [1000 + a for a in range(A)]
+    res = engine.seal_run(99, n, c, bids, verify=True, sections=True, auction_ids=ids)
+    got = seal_flow.sections_to_transcripts(99, n, c, bids, res)
+    assert res["ok"] == [True] * A and res["max_bid"] == [max(b) for b in per]
+    for a in range(A):
+        want = seal_flow.SealFlow(oracle, n[a], c[a], 99, per[a], auction=ids[a]).run()
+        assert got[a] == want, f"auction {a} (n={n[a]}, c={c[a]})"
+
+
+def test_runner_32_bit_bids(engine):
+    """c = 32 with the top bit set: the reference cannot run this"""
+    bids = [0x80000001, 0xFFFFFFFF, 0x7FFFFFFF, 5]
+    res = engine.seal_run(3, [4], [32], bids, verify=True)
+    assert res["ok"] == [True] and res["max_bid"] == [0xFFFFFFFF]
