@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed over NCCL).
+
+The hot path partitions two ways:
+  * independent auctions / independent batches of scalar mults: every rank works on
+    its own share, there is NO data-path collective;
+  * ONE auction sharded by bidder slice: per step the X_i of round one and the b_i of
+    round two (64 B per bidder) are all-gathered, and one word of verdict is
+    MIN-reduced at the end.  The engine (pa_seal_run) calls back into `allgather`
+    below when a slice is ready in the send buffer.
+"""
+import torch
+import torch.distributed as dist
+
+
+def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False):
+    """Run ONE SEAL auction of n bidders sharded over the ranks of the default process group.
+    Every rank passes the same (seed, n, c, bids_all).  Returns the engine's result dict for
+    the local slice plus 'ok_all' (MIN over ranks) and 'slice' = (lo, hi)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    slice_ = (n + world - 1) // world
+    lo, hi = min(n, rank * slice_), min(n, (rank + 1) * slice_)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    send = torch.zeros(slice_ * 64, dtype=torch.uint8, device=dev)
+    recv = torch.empty(world * slice_ * 64, dtype=torch.uint8, device=dev)
+
+    def allgather(which):
+        dist.all_gather_into_tensor(recv, send)   # NCCL over NVLink; 64 B per bidder
+        torch.cuda.synchronize()
+        return 0
+
+    if hi > lo:
+        res = engine.seal_run(seed, [n], [c], list(bids_all[lo:hi]), verify=verify, sections=sections,
+                              shard=dict(lo=lo, hi=hi, slice=slice_, d_send=send.data_ptr(), d_recv=recv.data_ptr(), allgather=allgather))
+    else:  # more ranks than bidders: still take part in the exchanges
+        for _ in range(2 * c):
+            allgather(0)
+        res = {"max_bid": [0], "ok": [True]}
+    ok = torch.tensor([1 if all(res["ok"]) else 0], dtype=torch.int32, device=dev)
+    mb = torch.tensor([res["max_bid"][0]], dtype=torch.int64, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    dist.all_reduce(mb, op=dist.ReduceOp.MAX)
+    res["ok_all"] = bool(ok.item())
+    res["max_bid_all"] = int(mb.item())
+    res["slice"] = (lo, hi)
+    return res

@@ -21,18 +21,25 @@ def b32(x):
 
 
 class SealFlow:
-    def __init__(self, backend, n, c, seed, bids, verify=True, auction=0):
+    """One SEAL auction.  `mine` (default: everybody) are the bidder ids this process plays;
+    with a subset, `exchange(kind, local_bytes)` must return the concatenation over all
+    processes in id order (the all-gather of SURVEY.md section 8e) — used for the X of
+    round one and the b of round two, the only data a bidder needs from the others."""
+
+    def __init__(self, backend, n, c, seed, bids, verify=True, auction=0, mine=None, exchange=None):
         assert len(bids) == n
         self.be, self.n, self.c, self.seed, self.bids, self.verify = backend, n, c, seed, list(bids), verify
-        self.streams = [E.PaStream(seed, (auction << 32) | j) for j in range(n)]
+        self.mine = list(range(n)) if mine is None else list(mine)
+        self.exchange = exchange or (lambda kind, data: data)
+        self.streams = {j: E.PaStream(seed, (auction << 32) | j) for j in self.mine}
         # binaryBidStr: MSB first (SEAL/bidder.cpp:31, 1128)
-        self.bits = [[(bid >> (c - 1 - i)) & 1 for i in range(c)] for bid in bids]
-        self.ids = list(range(n))
+        self.bits = {j: [(bids[j] >> (c - 1 - i)) & 1 for i in range(c)] for j in self.mine}
         self.junction = False            # junctionFlag, identical for all bidders
         self.prev_step = None            # prevDecidingStep
-        self.prev_bit = [1] * n          # prevDecidingBit (private, initialised to 1, SEAL/bidder.cpp:23)
-        self.max_bid = [0] * n
-        self.out = bytearray()
+        self.prev_bit = {j: 1 for j in self.mine}   # prevDecidingBit (private, initialised to 1, SEAL/bidder.cpp:23)
+        self.max_bid = 0
+        # what gets published, keyed by bidder id
+        self.sec = {"commit": {}, "commit_ok": {}, "r1": [], "r1_ok": [], "r2": [], "r2_ok": [], "r3": []}
         self.ok = True
 
     # -- helpers ---------------------------------------------------------------------------
@@ -43,145 +50,174 @@ class SealFlow:
     def _cat(items):
         return b"".join(items)
 
-    def _ids(self, js):
-        return list(js)
-
-    def _per_verifier(self, verdict_by_prover):
-        """Reference: verifier j checks every i != j (SEAL/bidder.cpp:1178-1190).  Every
-        proof is verified once here; verifier j's answer is the AND over i != j."""
-        n = self.n
-        res = []
-        for j in range(n):
-            v = all(verdict_by_prover[i] for i in range(n) if i != j)
-            res.append(1 if v else 0)
-            self.ok &= bool(v)
-        return bytes(res)
-
     # -- phases ------------------------------------------------------------------------------
     def commit(self):
         """Bidder::commitBid for every bidder and bit (SEAL/bidder.cpp:1109-1162)."""
-        n, c, be = self.n, self.c, self.be
+        c, be, mine = self.c, self.be, self.mine
         al, bt, vA, vB, rc, bits, ids = [], [], [], [], [], [], []
-        for j in range(n):
+        for j in mine:
             for i in range(c):
                 a, b, va, vb, r1, d1, d2 = self._draw(j, 7)
                 al.append(b32(a)); bt.append(b32(b)); vA.append(b32(va)); vB.append(b32(vb))
                 rc.append(b32(r1) + b32(d1) + b32(d2))
                 bits.append(self.bits[j][i]); ids.append(j)
+        m = len(ids)
         alpha, beta = self._cat(al), self._cat(bt)
         pts = be.commit_points(alpha, beta, bytes(bits))                      # phi, A, B
-        A = self._cat(pts[192 * k + 64:192 * k + 128] for k in range(n * c))
-        B = self._cat(pts[192 * k + 128:192 * k + 192] for k in range(n * c))
+        A = self._cat(pts[192 * k + 64:192 * k + 128] for k in range(m))
+        B = self._cat(pts[192 * k + 128:192 * k + 192] for k in range(m))
         pokA = be.pokdlog_prove(A, alpha, ids, self._cat(vA))
         pokB = be.pokdlog_prove(B, beta, ids, self._cat(vB))
         com = be.powfcom_prove(pts, alpha, bytes(bits), ids, self._cat(rc))
-        self.alpha = [[al[j * c + i] for i in range(c)] for j in range(n)]
-        self.cpts = [[pts[192 * (j * c + i):192 * (j * c + i + 1)] for i in range(c)] for j in range(n)]
-        for k in range(n * c):
-            self.out += pts[192 * k:192 * k + 192] + pokA[96 * k:96 * k + 96] + pokB[96 * k:96 * k + 96] + com[352 * k:352 * k + 352]
-        # Bidder::verifyCommitment (SEAL/bidder.cpp:1171-1195)
-        if self.verify and n > 1:
+        self.alpha = {j: [al[q * c + i] for i in range(c)] for q, j in enumerate(mine)}
+        self.cpts = {j: [pts[192 * (q * c + i):192 * (q * c + i + 1)] for i in range(c)] for q, j in enumerate(mine)}
+        # Bidder::verifyCommitment (SEAL/bidder.cpp:1171-1195): every proof once
+        if self.verify and self.n > 1:
             vA_ = be.pokdlog_verify(pokA, A, ids)
             vB_ = be.pokdlog_verify(pokB, B, ids)
             vC_ = be.powfcom_verify(com, pts, ids)
-            per_prover = [all(vA_[j * c + i] and vB_[j * c + i] and vC_[j * c + i] for i in range(c)) for j in range(n)]
         else:
-            per_prover = [True] * n
-        self.out += self._per_verifier(per_prover)
+            vA_ = vB_ = vC_ = bytes([1] * m)
+        for q, j in enumerate(mine):
+            rec = bytearray()
+            for k in range(q * c, (q + 1) * c):
+                rec += pts[192 * k:192 * k + 192] + pokA[96 * k:96 * k + 96] + pokB[96 * k:96 * k + 96] + com[352 * k:352 * k + 352]
+            self.sec["commit"][j] = bytes(rec)
+            self.sec["commit_ok"][j] = all(vA_[k] and vB_[k] and vC_[k] for k in range(q * c, (q + 1) * c))
 
     def round_one(self, step):
         """Bidder::roundOne (SEAL/bidder.cpp:1203-1236) + verifyRoundOne (:1245-1262)."""
-        n, be = self.n, self.be
+        be, mine = self.be, self.mine
         xs, rs, vx, vr = [], [], [], []
-        for j in range(n):
+        for j in mine:
             x, r, a, b = self._draw(j, 4)
             xs.append(b32(x)); rs.append(b32(r)); vx.append(b32(a)); vr.append(b32(b))
         x_b, r_b = self._cat(xs), self._cat(rs)
         X = be.fixed_base_mul(x_b)
         R = be.fixed_base_mul(r_b)
-        pokX = be.pokdlog_prove(X, x_b, self.ids, self._cat(vx))
-        pokR = be.pokdlog_prove(R, r_b, self.ids, self._cat(vr))
+        pokX = be.pokdlog_prove(X, x_b, mine, self._cat(vx))
+        pokR = be.pokdlog_prove(R, r_b, mine, self._cat(vr))
         self.x, self.X, self.R = xs, X, R
-        for j in range(n):
-            self.out += X[64 * j:64 * j + 64] + R[64 * j:64 * j + 64] + pokX[96 * j:96 * j + 96] + pokR[96 * j:96 * j + 96]
-        if self.verify and n > 1:
-            v1 = be.pokdlog_verify(pokX, X, self.ids)
-            v2 = be.pokdlog_verify(pokR, R, self.ids)
-            per_prover = [bool(v1[j] and v2[j]) for j in range(n)]
+        if self.verify and self.n > 1:
+            v1 = be.pokdlog_verify(pokX, X, mine)
+            v2 = be.pokdlog_verify(pokR, R, mine)
         else:
-            per_prover = [True] * n
-        self.out += self._per_verifier(per_prover)
+            v1 = v2 = bytes([1] * len(mine))
+        self.sec["r1"].append({j: X[64 * q:64 * q + 64] + R[64 * q:64 * q + 64] + pokX[96 * q:96 * q + 96] + pokR[96 * q:96 * q + 96]
+                               for q, j in enumerate(mine)})
+        self.sec["r1_ok"].append({j: bool(v1[q] and v2[q]) for q, j in enumerate(mine)})
 
     def round_two(self, step):
         """Bidder::roundTwo (SEAL/bidder.cpp:1271-1336) + verifyRoundTwo (:1346-1377)."""
-        n, be = self.n, self.be
-        Y = be.y_scan(self.X)                                             # :1286-1299
+        be, mine = self.be, self.mine
+        X_all = self.exchange("X", self.X)
+        Y_all = be.y_scan(X_all)                                          # :1286-1299
+        Y = self._cat(Y_all[64 * j:64 * j + 64] for j in mine)
         base, ebit = [], []
-        for j in range(n):
+        for q, j in enumerate(mine):
             bit = self.bits[j][step]
             if (not self.junction and bit == 0) or (self.junction and (bit == 0 or self.prev_bit[j] == 0)):
-                base.append(Y[64 * j:64 * j + 64]); ebit.append(0)        # b = Y^x   :1303
+                base.append(Y[64 * q:64 * q + 64]); ebit.append(0)        # b = Y^x   :1303
             else:
-                base.append(self.R[64 * j:64 * j + 64]); ebit.append(1)   # b = R^x   :1307
+                base.append(self.R[64 * q:64 * q + 64]); ebit.append(1)   # b = R^x   :1307
         b = be.var_base_mul(self._cat(base), self._cat(self.x))
-        pt = lambda buf, j: buf[64 * j:64 * j + 64]
+        pt = lambda buf, q: buf[64 * q:64 * q + 64]
+        stmt, sec, rnd = [], [], []
         if not self.junction:
-            stmt, sec, rnd = [], [], []
-            for j in range(n):
-                stmt.append(pt(b, j) + pt(self.X, j) + pt(Y, j) + pt(self.R, j) + self.cpts[j][step])
-                sec.append(self.x[j] + self.alpha[j][step])
+            for q, j in enumerate(mine):
+                stmt.append(pt(b, q) + pt(self.X, q) + pt(Y, q) + pt(self.R, q) + self.cpts[j][step])
+                sec.append(self.x[q] + self.alpha[j][step])
                 rnd.append(self._cat(b32(v) for v in self._draw(j, 5)))
             stmt_b = self._cat(stmt)
-            proofs = be.stage1_prove(stmt_b, self._cat(sec), bytes(ebit), self.ids, self._cat(rnd))
-            rec = 672
-            tag = 1
+            proofs = be.stage1_prove(stmt_b, self._cat(sec), bytes(ebit), mine, self._cat(rnd))
+            rec, tag = 672, 1
         else:
-            stmt, sec, rnd = [], [], []
             P = self.prev
-            for j in range(n):
-                stmt.append(pt(b, j) + pt(self.X, j) + pt(self.R, j) + pt(P["b"], j) + pt(P["X"], j) + pt(P["R"], j) +
-                            self.cpts[j][step] + pt(Y, j) + pt(P["Y"], j))
-                sec.append(self.x[j] + P["x"][j] + self.alpha[j][step])
+            for q, j in enumerate(mine):
+                stmt.append(pt(b, q) + pt(self.X, q) + pt(self.R, q) + pt(P["b"], q) + pt(P["X"], q) + pt(P["R"], q) +
+                            self.cpts[j][step] + pt(Y, q) + pt(P["Y"], q))
+                sec.append(self.x[q] + P["x"][q] + self.alpha[j][step])
                 rnd.append(self._cat(b32(v) for v in self._draw(j, 11)))
             stmt_b = self._cat(stmt)
-            proofs = be.stage2_prove(stmt_b, self._cat(sec), bytes(ebit), bytes(self.prev_bit), self.ids, self._cat(rnd))
-            rec = 1344
-            tag = 2
-        for j in range(n):
-            self.out += struct.pack("<I", tag) + pt(b, j) + proofs[rec * j:rec * (j + 1)]
-        if self.verify and n > 1:
-            v = be.stage1_verify(proofs, stmt_b, self.ids) if tag == 1 else be.stage2_verify(proofs, stmt_b, self.ids)
-            per_prover = [bool(v[j]) for j in range(n)]
+            proofs = be.stage2_prove(stmt_b, self._cat(sec), bytes(ebit), bytes(self.prev_bit[j] for j in mine), mine, self._cat(rnd))
+            rec, tag = 1344, 2
+        if self.verify and self.n > 1:
+            v = be.stage1_verify(proofs, stmt_b, mine) if tag == 1 else be.stage2_verify(proofs, stmt_b, mine)
         else:
-            per_prover = [True] * n
-        self.out += self._per_verifier(per_prover)
+            v = bytes([1] * len(mine))
+        self.sec["r2"].append({j: struct.pack("<I", tag) + pt(b, q) + proofs[rec * q:rec * (q + 1)] for q, j in enumerate(mine)})
+        self.sec["r2_ok"].append({j: bool(v[q]) for q, j in enumerate(mine)})
         self.Y, self.b = Y, b
 
     def round_three(self, step):
         """Bidder::roundThree (SEAL/bidder.cpp:1386-1421)."""
-        deciding = not self.be.point_sum_is_inf(self.b)                  # :1393-1397
+        b_all = self.exchange("b", self.b)
+        deciding = not self.be.point_sum_is_inf(b_all)                   # :1393-1397
         if deciding:
             self.junction = True
             self.prev_step = step
-            for j in range(self.n):
+            for j in self.mine:
                 self.prev_bit[j] &= self.bits[j][step]                    # :1402 (true bit, SURVEY Q6)
-                self.max_bid[j] |= 1 << (self.c - step - 1)               # :1403 (64-bit shift here, SURVEY Q2)
+            self.max_bid |= 1 << (self.c - step - 1)                      # :1403 (64-bit shift here, SURVEY Q2)
             self.prev = {"X": self.X, "R": self.R, "Y": self.Y, "b": self.b, "x": list(self.x)}   # :1406-1411
-        self.out += bytes([1 if deciding else 0] * self.n)
+        self.sec["r3"].append(1 if deciding else 0)
 
-    def run(self):
-        self.out += b"PASEALT1" + struct.pack("<QQQ", self.n, self.c, self.seed)
-        for bid in self.bids:
-            self.out += struct.pack("<Q", bid)
+    def run_sections(self):
         self.commit()
         for step in range(self.c):
             self.round_one(step)
             self.round_two(step)
             self.round_three(step)
-        for j in range(self.n):
-            self.out += struct.pack("<Q", self.max_bid[j])
-        self.ok &= all(m == max(self.bids) for m in self.max_bid)
-        return bytes(self.out)
+        return self.sec
+
+    def run(self):
+        out = assemble_transcript(self.n, self.c, self.seed, self.bids, [self.run_sections()])
+        self.ok = transcript_ok(out) and self.max_bid == max(self.bids)
+        return out
+
+
+def assemble_transcript(n, c, seed, bids, section_list):
+    """PASEALT1 from the sections of one or several processes (each holding a subset of the bidders)."""
+    def merged(key, step=None):
+        d = {}
+        for sec in section_list:
+            d.update(sec[key] if step is None else sec[key][step])
+        return d
+
+    def per_verifier(ok):
+        # reference: verifier j checks every i != j (SEAL/bidder.cpp:1178-1190); verifier j's answer is
+        # the AND over i != j of the once-computed verdicts
+        return bytes(1 if all(ok[i] for i in range(n) if i != j) else 0 for j in range(n))
+
+    out = bytearray(b"PASEALT1" + struct.pack("<QQQ", n, c, seed))
+    for bid in bids:
+        out += struct.pack("<Q", bid)
+    cm, cok = merged("commit"), merged("commit_ok")
+    for j in range(n):
+        out += cm[j]
+    out += per_verifier(cok)
+    r3 = section_list[0]["r3"]
+    maxbid = 0
+    for step in range(c):
+        r1, r1ok, r2, r2ok = merged("r1", step), merged("r1_ok", step), merged("r2", step), merged("r2_ok", step)
+        for j in range(n):
+            out += r1[j]
+        out += per_verifier(r1ok)
+        for j in range(n):
+            out += r2[j]
+        out += per_verifier(r2ok)
+        out += bytes([r3[step]] * n)
+        if r3[step]:
+            maxbid |= 1 << (c - step - 1)
+    for j in range(n):
+        out += struct.pack("<Q", maxbid)
+    return bytes(out)
+
+
+def transcript_ok(buf):
+    t = parse_transcript(buf)
+    v = t["commit_verdict"] + b"".join(s["r1_verdict"] + s["r2_verdict"] for s in t["steps"])
+    return all(v)
 
 
 def parse_transcript(buf):
