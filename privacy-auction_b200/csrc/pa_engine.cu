@@ -30,14 +30,19 @@ struct pa_ctx {
 
 enum {
   PA_K_COMB = 0, PA_K_FIXED, PA_K_VAR, PA_K_DOUBLE, PA_K_LINCOMB2, PA_K_POINT_ADD, PA_K_NORMALIZE, PA_K_ENCODE,
-  PA_K_PEAK, PA_K_VDERIVE, PA_K_VCHECKS, PA_K_VERDICT, PA_K_POPS, PA_K_PRESPOND, PA_K_CHALLENGE, PA_K_RNG,
-  PA_K_COMMIT, PA_K_YSCAN, PA_K_SUMINF, PA_K_COUNT
+  PA_K_PEAK, PA_K_VERDICT, PA_K_CHALLENGE, PA_K_RNG, PA_K_COMMIT, PA_K_YSCAN, PA_K_SUMINF,
+  // per proof kind (+ PA_POK / PA_COM / PA_S1 / PA_S2)
+  PA_K_VDERIVE, PA_K_VCHECKS = PA_K_VDERIVE + 4, PA_K_POPS = PA_K_VCHECKS + 4, PA_K_PRESPOND = PA_K_POPS + 4,
+  PA_K_COUNT = PA_K_PRESPOND + 4
 };
 static const char *const PA_K_NAMES[PA_K_COUNT] = {"k_comb", "k_fixed_base", "k_var_base", "k_double_mul", "k_lincomb2",
-                                                   "k_point_add", "k_normalize", "k_encode", "k_peak", "k_verify_derive",
-                                                   "k_verify_checks", "k_verdict", "k_prove_ops", "k_prove_respond",
+                                                   "k_point_add", "k_normalize", "k_encode", "k_peak", "k_verdict",
                                                    "k_challenge", "k_rng_fill", "k_commit_points", "k_y_scan",
-                                                   "k_point_sum_is_inf"};
+                                                   "k_point_sum_is_inf",
+                                                   "k_verify_derive<pok>", "k_verify_derive<com>", "k_verify_derive<s1>", "k_verify_derive<s2>",
+                                                   "k_verify_checks<pok>", "k_verify_checks<com>", "k_verify_checks<s1>", "k_verify_checks<s2>",
+                                                   "k_prove_ops<pok>", "k_prove_ops<com>", "k_prove_ops<s1>", "k_prove_ops<s2>",
+                                                   "k_prove_respond<pok>", "k_prove_respond<com>", "k_prove_respond<s1>", "k_prove_respond<s2>"};
 
 static cudaEvent_t ev_get(pa_ctx *ctx) {
   if (!ctx->ev_pool.empty()) {
@@ -502,8 +507,8 @@ int verify_dev(pa_ctx *ctx, const unsigned char *proofs, const unsigned char *st
   if (rc) return rc;
   u32 *derived = (u32 *)ctx->d_work;
   unsigned char *chk = ctx->d_work + align_up(n * 32, 256);
-  PA_LAUNCH(ctx, PA_K_VDERIVE, (k_verify_derive<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, derived, (int)n, L)));
-  PA_LAUNCH(ctx, PA_K_VCHECKS, (k_verify_checks<KIND, NCHK><<<grid_for(n * NCHK), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, derived, ctx->d_comb, chk, (int)n, L)));
+  PA_LAUNCH(ctx, PA_K_VDERIVE + KIND, (k_verify_derive<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, derived, (int)n, L)));
+  PA_LAUNCH(ctx, PA_K_VCHECKS + KIND, (k_verify_checks<KIND, NCHK><<<grid_for(n * NCHK), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, derived, ctx->d_comb, chk, (int)n, L)));
   PA_LAUNCH(ctx, PA_K_VERDICT, (k_verdict<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(chk, NCHK, (int)n, verdict)));
   return PA_OK;
 }
@@ -517,9 +522,9 @@ int prove_dev(pa_ctx *ctx, const unsigned char *stmts, const unsigned char *secr
   size_t m = n * K::NEPS;
   int rc = work_reserve(ctx, m);
   if (rc) return rc;
-  PA_LAUNCH(ctx, PA_K_POPS, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n, L)));
+  PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n, L)));
   if ((rc = normalize_to(ctx, proofs, m, K::NEPS, L.proof))) return rc;
-  PA_LAUNCH(ctx, PA_K_PRESPOND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, secrets, rnd, b0, b1, (int)n, L)));
+  PA_LAUNCH(ctx, PA_K_PRESPOND + KIND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, secrets, rnd, b0, b1, (int)n, L)));
   return PA_OK;
 }
 
