@@ -184,6 +184,19 @@ int pa_point_sum_is_inf(pa_ctx *ctx, const uint8_t *B, size_t n, int *is_inf);
 int pa_point_sum_is_inf_batch(pa_ctx *ctx, const uint8_t *B, const uint32_t *offsets, size_t nseg, int32_t *flags);
 int pa_point_sum_is_inf_dev(pa_ctx *ctx, const uint8_t *d_B, const uint32_t *d_offsets, size_t nseg, size_t npoints, int32_t *d_flags);
 
+/* ---- CCS22 -------------------------------------------------------------------------------
+ * The CCS22 protocol's curve work (CCS22/bidder.cpp:48-198, CCS22/evaluator.cpp:22-156) is made
+ * of the call shapes above: X_i = g^x (pa_fixed_base_mul); Com = g^bid g1^H + h^R (pa_double_mul,
+ * pa_var_base_mul, pa_point_add); own Y (pa_y_scan); B = Y^x | g^r; T2 = g^k, G = g^beta g1^alpha
+ * (pa_double_mul), H = T2^alpha + h^beta (pa_lincomb2); z = g^s h^t, C0 = G^s + H^t + B,
+ * C1 = (G - g1)^s + (H - T2)^t + M1 (pa_lincomb2 + pa_point_add); sum_j (C0_j - beta_j z_j) + B
+ * (pa_var_base_mul, pa_point_add, pa_point_sum_is_inf).  The one operation of its own is the
+ * setup hash:
+ *   out[i] = SHA-256(minimal big-endian bytes of scalars[i][0..k)) mod order; a zero scalar takes
+ *   the reference's error path and yields 0.   SHA256inSetup, CCS22/hash.cpp:9-57 */
+int pa_ccs22_setup_hash(pa_ctx *ctx, const uint8_t *scalars, size_t k, uint8_t *out, size_t n);
+int pa_ccs22_setup_hash_dev(pa_ctx *ctx, const uint8_t *d_scalars, size_t k, uint8_t *d_out, size_t n);
+
 /* ---- seeded randomness ------------------------------------------------------------------
  * The reference draws from OpenSSL's DRBG and is not reproducible.
  * The PA stream replaces BN_rand_range(., order) (SEAL/bidder.cpp:97 and 44 more sites):

@@ -677,3 +677,34 @@ int po_point_sum_is_inf(const uint8_t *b, size_t n, int *is_inf) {
   env_free(&e);
   return rc;
 }
+
+/* ================================ CCS22 ==================================== */
+
+int po_ccs22_setup_hash(const uint8_t *scalars, size_t k, uint8_t *out, size_t n) {
+  po_env e;
+  if (env_init(&e)) return -1;
+  for (size_t i = 0; i < n; ++i) {
+    EVP_MD_CTX *md = EVP_MD_CTX_new();
+    unsigned char buf[32], dg[32];
+    BIGNUM *h = BN_new(); /* stays 0 on the error path, CCS22/hash.cpp:31-35 */
+    int failed = 0;
+    EVP_DigestInit_ex(md, EVP_sha256(), NULL);
+    for (size_t j = 0; j < k && !failed; ++j) {
+      BIGNUM *b = sc_in(scalars + 32 * (i * k + j));
+      int len = BN_bn2bin(b, buf); /* minimal length, CCS22/hash.cpp:26-31 */
+      if (len == 0) failed = 1;    /* zero bignum: handelSHA256Error + return */
+      else EVP_DigestUpdate(md, buf, (size_t)len);
+      BN_free(b);
+    }
+    if (!failed) {
+      EVP_DigestFinal_ex(md, dg, NULL);
+      BN_bin2bn(dg, 32, h);
+      BN_mod(h, h, e.order, e.ctx); /* CCS22/hash.cpp:53-54 */
+    }
+    BN_bn2binpad(h, out + 32 * i, 32);
+    BN_free(h);
+    EVP_MD_CTX_free(md);
+  }
+  env_free(&e);
+  return 0;
+}

@@ -70,6 +70,12 @@ int po_y_scan(const uint8_t *X, uint8_t *Y, size_t n);
 /* *is_inf = (sum_i b_i == infinity).  SEAL/bidder.cpp:1393-1397 */
 int po_point_sum_is_inf(const uint8_t *b, size_t n, int *is_inf);
 
+
+/* ---- CCS22 */
+/* H = SHA-256(minimal big-endian bytes of k scalars) mod order; a zero scalar takes the reference's
+ * error path and leaves H = 0.  SHA256inSetup, CCS22/hash.cpp:9-57 */
+int po_ccs22_setup_hash(const uint8_t *scalars, size_t k, uint8_t *out, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

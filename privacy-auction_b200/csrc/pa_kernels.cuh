@@ -371,6 +371,32 @@ __global__ void k_challenge(const unsigned char *points, int k, const u64 *ids, 
   st_sc(out + 32 * (size_t)i, h);
 }
 
+// ---- CCS22 setup hash: SHA-256 over the minimal big-endian bytes of k scalars, mod n ----------
+// SHA256inSetup, CCS22/hash.cpp:9-57.  A zero scalar takes the reference's error path, which
+// leaves H = 0.
+__global__ void k_ccs22_setup_hash(const unsigned char *scalars, int k, unsigned char *out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sha256_state s;
+  sha256_init(s);
+  bool failed = false;
+  for (int j = 0; j < k && !failed; ++j) {
+    const unsigned char *p = scalars + 32 * ((size_t)i * k + j);
+    int lead = 0;
+    while (lead < 32 && p[lead] == 0) ++lead;
+    if (lead == 32) failed = true;
+    for (int b = lead; b < 32; ++b) sha256_put(s, p[b]);
+  }
+  sc h;
+  sc_set_zero(h);
+  if (!failed) {
+    u32 d[8];
+    sha256_final(s, d);
+    sc_from_digest(h, d);
+  }
+  st_sc(out + 32 * (size_t)i, h);
+}
+
 // ---- PA stream: cnt consecutive BN_rand_range draws per item --------------------------------
 // idx != NULL: item i uses stream / counter slot idx[i] (a subset of the parties draws)
 __global__ void k_rng_fill(u64 seed, const u64 *streams, u64 *ctrs, const u32 *idx, int cnt, unsigned char *out, int n) {

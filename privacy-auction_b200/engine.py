@@ -72,6 +72,8 @@ SIGNATURES = {
     "pa_rng_fill": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_rng_fill_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_seal_run": (ctypes.c_int, [_ctx, _vp]),
+    "pa_ccs22_setup_hash": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _sz]),
+    "pa_ccs22_setup_hash_dev": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _sz]),
     "pa_profile_begin": (ctypes.c_int, [_ctx]),
     "pa_profile_end": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.POINTER(_sz)]),
 }
@@ -394,6 +396,13 @@ class Engine:
         for name, buf in out.items():
             res[name[4:]] = bytes(buf)
         return res
+
+    def ccs22_setup_hash(self, scalars, k):
+        n = len(scalars) // (32 * k)
+        out = bytearray(32 * n)
+        b = [_buf(scalars), _buf(out)]
+        self._check(self.lib.pa_ccs22_setup_hash(self.ctx, b[0][0], k, b[1][0], n))
+        return bytes(out)
 
     def measure_int_peak(self):
         out = (ctypes.c_double * 4)()

@@ -12,3 +12,8 @@ for cfg in "3 4 42 -" "1 3 1 5" "2 3 1 -" "4 6 7 -" "5 5 11 0,0,0,0,0" "3 8 5 25
 done
 # tests/golden/seal_reference_summary.json holds, per transcript, the JSON line seal_ref
 # prints on stderr (sha256 of the transcript, max bid, the reference's DataTracker byte totals).
+# CCS22: ccs22_ref <n> <c> <seed> <evaluatorId> <bids|-> <out>
+for cfg in "4 5 9 2 -" "2 3 1 0 -" "3 6 4 1 0,0,0" "5 4 8 4 -" "1 3 2 0 5" "4 8 3 0 200,7,200,13"; do
+  set -- $cfg
+  ./oracle/_ref/ccs22_ref "$1" "$2" "$3" "$4" "$5" "tests/golden/ccs22_n$1_c$2_s$3_e$4.bin"
+done

@@ -147,6 +147,12 @@ def _add_protocol_methods(cls):
         self._call("po_stage2_verify", _p(proofs), _p(stmt), _ids(ids), _p(out), ctypes.c_size_t(n))
         return bytes(out)
 
+    def ccs22_setup_hash(self, scalars, k):
+        n = len(scalars) // (32 * k)
+        out = bytearray(32 * n)
+        self._call("po_ccs22_setup_hash", _p(scalars), ctypes.c_size_t(k), _p(out), ctypes.c_size_t(n))
+        return bytes(out)
+
     def y_scan(self, X):
         n = len(X) // 64
         out = bytearray(64 * n)

@@ -1,0 +1,64 @@
+"""CCS22: the oracle port against the transcripts of the
+unmodified reference (CPU), and the CUDA engine against both (GPU)."""
+import glob
+import os
+import random
+import struct
+
+import pytest
+
+import ccs22_flow
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ccs22_*.bin")))
+
+
+def _hdr(gold):
+    n, c, seed, ev = struct.unpack_from("<QQQQ", gold, 8)
+    return n, c, seed, ev, list(struct.unpack_from(f"<{n}Q", gold, 40))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_reproduces_reference_ccs22(oracle, path):
+    gold = open(path, "rb").read()
+    n, c, seed, ev, bids = _hdr(gold)
+    fl = ccs22_flow.Ccs22Flow(oracle, n, c, seed, ev, bids)
+    assert fl.run() == gold and fl.max_bid == [max(bids)] * n
+
+
+def test_setup_hash_zero_scalar_path(oracle):
+    import hashlib
+    import secp256k1_py as E
+    ks = [5, 0x1234, 1 << 200]
+    want = int.from_bytes(hashlib.sha256(b"\x05" + b"\x12\x34" + (1 << 200).to_bytes(26, "big")).digest(), "big") % E.N
+    assert oracle.ccs22_setup_hash(b"".join(k.to_bytes(32, "big") for k in ks), 3) == want.to_bytes(32, "big")
+    assert oracle.ccs22_setup_hash(b"".join(k.to_bytes(32, "big") for k in [5, 0, 7]), 3) == bytes(32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_engine_reproduces_reference_ccs22(engine, path):
+    gold = open(path, "rb").read()
+    n, c, seed, ev, bids = _hdr(gold)
+    fl = ccs22_flow.Ccs22Flow(engine, n, c, seed, ev, bids)
+    assert fl.run() == gold and fl.max_bid == [max(bids)] * n
+
+
+@pytest.mark.gpu
+def test_engine_ccs22_config2_matches_oracle(engine, oracle):
+    """BASELINE config 2 shape: 20 bidders, 32-bit bids (the reference itself degenerates to all-zero
+    bids at c = 32; here once all-zero and once uniform < 2^31)"""
+    rnd = random.Random(22)
+    for bids in ([0] * 20, [rnd.randrange(1 << 31) for _ in range(20)]):
+        a = ccs22_flow.Ccs22Flow(engine, 20, 32, 5, 7, bids)
+        b = ccs22_flow.Ccs22Flow(oracle, 20, 32, 5, 7, bids)
+        assert a.run() == b.run() and a.max_bid == [max(bids)] * 20
+
+
+@pytest.mark.gpu
+def test_engine_setup_hash_parity(engine, oracle):
+    rnd = random.Random(23)
+    for k in (4, 17, 128, 21 * 32):
+        sc = bytearray(b"".join(rnd.getrandbits(rnd.choice([256, 250, 200, 64, 8])).to_bytes(32, "big") for _ in range(9 * k)))
+        sc[32 * (3 * k + 1):32 * (3 * k + 2)] = bytes(32)     # item 3 has a zero scalar
+        assert engine.ccs22_setup_hash(bytes(sc), k) == oracle.ccs22_setup_hash(bytes(sc), k)
