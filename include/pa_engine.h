@@ -206,6 +206,10 @@ int pa_ccs22_setup_hash_dev(pa_ctx *ctx, const uint8_t *d_scalars, size_t k, uin
  * counters[i] is advanced. */
 int pa_rng_fill(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n);
 int pa_rng_fill_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *d_streams, uint64_t *d_counters, size_t per_item, uint8_t *d_out, size_t n);
+/* same stream with BN_rand(., 256, -1, 0) semantics: the 256-bit value unreduced, never redrawn
+ * (CCS22/bidder.cpp:170, CCS22/evaluator.cpp:97, CCS22/bulletinBoard.cpp:33, 45) */
+int pa_rng_fill256(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n);
+int pa_rng_fill256_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *d_streams, uint64_t *d_counters, size_t per_item, uint8_t *d_out, size_t n);
 
 /* ---- whole auctions ------------------------------------------------------------------------
  * pa_seal_run advances every bidder of a batch of SEAL auctions in lock step with all state

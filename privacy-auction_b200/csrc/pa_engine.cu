@@ -597,6 +597,13 @@ int pa_challenge_dev(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_
   return PA_OK;
 }
 
+int pa_rng_fill256_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
+  if (n == 0 || per_item == 0) return PA_OK;
+  PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(seed, (const u64 *)streams, (u64 *)counters, nullptr, (int)per_item, out, (int)n, 1)));
+  return PA_OK;
+}
+
 int pa_ccs22_setup_hash_dev(pa_ctx *ctx, const uint8_t *scalars, size_t k, uint8_t *out, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (scalars && out)) && k < (1u << 24));
   if (n == 0) return PA_OK;
@@ -692,6 +699,12 @@ int pa_challenge(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_t *i
   HArg a[] = {{points, 0, n * k * 64}, {ids, 0, n * 8}, {0, out, n * 32}};
   return staged(ctx, a, 3, [&](unsigned char **d) { return pa_challenge_dev(ctx, d[0], k, (const uint64_t *)d[1], d[2], n); });
 }
+int pa_rng_fill256(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
+  HArg a[] = {{streams, 0, n * 8}, {counters, counters, n * 8}, {0, out, n * per_item * 32}};
+  return staged(ctx, a, 3, [&](unsigned char **d) { return pa_rng_fill256_dev(ctx, seed, (const uint64_t *)d[0], (uint64_t *)d[1], per_item, d[2], n); });
+}
+
 int pa_ccs22_setup_hash(pa_ctx *ctx, const uint8_t *scalars, size_t k, uint8_t *out, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (scalars && out)));
   HArg a[] = {{scalars, 0, n * k * 32}, {0, out, n * 32}};

@@ -399,14 +399,23 @@ __global__ void k_ccs22_setup_hash(const unsigned char *scalars, int k, unsigned
 
 // ---- PA stream: cnt consecutive BN_rand_range draws per item --------------------------------
 // idx != NULL: item i uses stream / counter slot idx[i] (a subset of the parties draws)
-__global__ void k_rng_fill(u64 seed, const u64 *streams, u64 *ctrs, const u32 *idx, int cnt, unsigned char *out, int n) {
+// raw != 0: BN_rand(., 256, -1, 0) semantics, the 256-bit value unreduced and never redrawn
+__global__ void k_rng_fill(u64 seed, const u64 *streams, u64 *ctrs, const u32 *idx, int cnt, unsigned char *out, int n,
+                           int raw = 0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int s = idx ? (int)idx[i] : i;
   u64 ctr = ctrs[s];
   for (int k = 0; k < cnt; ++k) {
     sc r;
-    pa_stream_rand_range(r, seed, streams[s], ctr);
+    if (raw) {
+      u32 d[8];
+      pa_stream_draw(d, seed, streams[s], ctr++);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) r.v[w] = d[7 - w];
+    } else {
+      pa_stream_rand_range(r, seed, streams[s], ctr);
+    }
     st_sc(out + 32 * ((size_t)i * cnt + k), r);
   }
   ctrs[s] = ctr;

@@ -72,6 +72,8 @@ SIGNATURES = {
     "pa_rng_fill": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_rng_fill_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_seal_run": (ctypes.c_int, [_ctx, _vp]),
+    "pa_rng_fill256": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
+    "pa_rng_fill256_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_ccs22_setup_hash": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _sz]),
     "pa_ccs22_setup_hash_dev": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _sz]),
     "pa_profile_begin": (ctypes.c_int, [_ctx]),

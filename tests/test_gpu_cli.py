@@ -46,3 +46,32 @@ def test_cli_gentests_style_sweep():
 def test_cli_usage_error():
     r = subprocess.run([SEAL, "3"], capture_output=True, text=True)
     assert r.returncode == 1 and "Usage" in r.stderr
+
+
+# ---- CCS22 command line ------------------------------------------------------------------------
+CCS22 = os.path.join(ROOT, "privacy-auction_b200", "bin", "CCS22")
+GOLDEN_CCS = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ccs22_*.bin")))
+
+
+@pytest.mark.parametrize("path", GOLDEN_CCS, ids=[os.path.basename(p) for p in GOLDEN_CCS])
+def test_ccs22_cli_reproduces_reference(tmp_path, path):
+    import struct
+    gold = open(path, "rb").read()
+    n, c, seed, ev = struct.unpack_from("<QQQQ", gold, 8)
+    bids = struct.unpack_from(f"<{n}Q", gold, 40)
+    out = tmp_path / "t.bin"
+    r = subprocess.run([CCS22, str(n), str(c), "--seed", str(seed), "--evaluator", str(ev), "--bids", ",".join(map(str, bids)),
+                        "--transcript", str(out), "--quiet"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert out.read_bytes() == gold
+
+
+def test_ccs22_cli_config2_and_sweep():
+    """BASELINE config 2 (20 bidders, 32-bit bids) and a few genTests-style pairs: exit code 0"""
+    r = subprocess.run([CCS22, "20", "32", "--seed", "4", "--quiet"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    rnd = random.Random(77)
+    for _ in range(4):
+        n, c = rnd.randint(1, 10), rnd.randint(1, 16)
+        r = subprocess.run([CCS22, str(n), str(c), "--seed", str(rnd.randrange(1 << 30)), "--quiet"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (n, c, r.stderr[-1500:])
