@@ -9,10 +9,11 @@
 // w < 32, d < 256 (512 KiB, L2-resident, built once per context on the GPU);
 // g^k is 32 mixed additions and no doublings.
 //
-// Variable base: signed 4-bit fixed windows over a per-thread table of
-// 1P..8P, one or two bases sharing the 256 doublings (Strauss).  The signed
-// digits come from k' = k + 0x88..8: nibble_i(k') - 8 is digit i, so no
-// per-digit carry has to be tracked while walking from the top.
+// Variable base: GLV split (128 doublings instead of 256), signed 4-bit fixed
+// windows over a per-thread co-Z table of 1P..8P (mixed additions), one or two
+// bases sharing the doublings (Strauss).  The signed digits come from
+// k' = |k| + 0x88..8: nibble_i(k') - 8 is digit i, so no per-digit carry has to
+// be tracked while walking from the top.
 #pragma once
 #include "pa_ec.cuh"
 #include "pa_sc.cuh"
@@ -52,63 +53,262 @@ PA_HD void fixed_base_mul(jac &r, const sc &k, const u32 *tab) {
   }
 }
 
-// T[i] = (i + 1) * P
-PA_HD void smul_table8(jac *T, const jac &P) {
-  T[0] = P;
-  jac_dbl(T[1], P);
-#pragma unroll 1
-  for (int i = 2; i < 8; ++i) jac_add(T[i], T[i - 1], P);
+// ---- variable base: GLV + co-Z window tables -------------------------------------------------
+// secp256k1 has the endomorphism lambda * (x, y) = (beta * x, y).  A scalar k is split as
+// k = k1 + k2 * lambda (mod n) with |k1|, |k2| < 2^128 (lattice reduction with the basis
+// (a1, b1), (a2, b2) below), so only 128 doublings are needed instead of 256 and the two halves
+// share them.  Per base a table 1P'..8P' is built by a chain of mixed additions and rescaled to a
+// COMMON Z: on the curve isomorphic by that Z the entries are affine, so every addition in the main
+// loop is a mixed addition (8M+3S instead of 12M+4S); the result's Z is multiplied by the common Z
+// at the end (the formulas for a = 0 do not involve the curve constant b).
+// Work per variable-base mult: ~1,800 field mults (nominal double-and-add with 4-bit windows: 2,900).
+struct glv_split {
+  u32 k1[5], k2[5];  // |k1|, |k2| (< 2^129), little-endian limbs
+  bool neg1, neg2;
+};
+
+// acc (9 limbs, two's complement) += / -= x[0..nx) * y[0..ny)
+template <int NX, int NY>
+PA_HD void mp9_mac(u32 acc[9], const u32 *x, const u32 *y, bool subtract) {
+  u32 prod[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) prod[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    u64 c = 0;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+      if (i + j < 9) {
+        u64 t = (u64)x[i] * y[j] + prod[i + j] + c;
+        prod[i + j] = (u32)t;
+        c = t >> 32;
+      }
+    }
+    if (i + NY < 9) prod[i + NY] += (u32)c;
+  }
+  u64 c = subtract ? 1 : 0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    u64 t = (u64)acc[i] + (subtract ? ~prod[i] : prod[i]) + c;
+    acc[i] = (u32)t;
+    c = t >> 32;
+  }
 }
 
-// kp = k + 0x8888...8  (9 limbs)
-PA_HD void smul_recode(u32 kp[9], const sc &k) {
+// c = round(k * g / 2^384): the top 4 limbs of the 16-limb product, rounded
+PA_HD void glv_mulshift384(u32 c[5], const u32 k[8], const u32 g[8]) {
+  u32 t[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t[i] = 0;
+  mp_addmul<16, 8, 8>(t, k, g);
+  u64 carry = (t[11] >> 31) & 1u;  // bit 383
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    u64 v = (u64)t[12 + i] + carry;
+    c[i] = (u32)v;
+    carry = v >> 32;
+  }
+  c[4] = (u32)carry;
+}
+
+PA_HD void glv_decompose(glv_split &o, const sc &k) {
+  // lattice basis: a1 + b1*lambda = a2 + b2*lambda = 0 (mod n); b1 < 0, a1 = b2
+  const u32 A1[4] = {0x9284EB15u, 0xE86C90E4u, 0xA7D46BCDu, 0x3086D221u};
+  const u32 NB1[4] = {0x0ABFE4C3u, 0x6F547FA9u, 0x010E8828u, 0xE4437ED6u};  // -b1
+  const u32 A2[5] = {0x9D44CFD8u, 0x57C1108Du, 0xA8E2F3F6u, 0x14CA50F7u, 0x1u};
+  // g1 = round(2^384 * b2 / n), g2 = round(2^384 * (-b1) / n)
+  const u32 G1[8] = {0x45DBB031u, 0xE893209Au, 0x71E8CA7Fu, 0x3DAA8A14u, 0x9284EB15u, 0xE86C90E4u, 0xA7D46BCDu, 0x3086D221u};
+  const u32 G2[8] = {0x8AC47F71u, 0x1571B4AEu, 0x9DF506C6u, 0x221208ACu, 0x0ABFE4C4u, 0x6F547FA9u, 0x010E8828u, 0xE4437ED6u};
+  u32 c1[5], c2[5];
+  glv_mulshift384(c1, k.v, G1);
+  glv_mulshift384(c2, k.v, G2);
+  // k1 = k - c1*a1 - c2*a2 ; k2 = c1*(-b1) - c2*b2   (b2 = a1), both small signed integers
+  u32 r1[9], r2[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    r1[i] = i < 8 ? k.v[i] : 0;
+    r2[i] = 0;
+  }
+  mp9_mac<5, 4>(r1, c1, A1, true);
+  mp9_mac<5, 5>(r1, c2, A2, true);
+  mp9_mac<5, 4>(r2, c1, NB1, false);
+  mp9_mac<5, 4>(r2, c2, A1, true);
+  o.neg1 = (r1[8] >> 31) != 0;
+  o.neg2 = (r2[8] >> 31) != 0;
+  u64 c = o.neg1 ? 1 : 0, d = o.neg2 ? 1 : 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    u64 t = (u64)(o.neg1 ? ~r1[i] : r1[i]) + c;
+    o.k1[i] = (u32)t;
+    c = t >> 32;
+    u64 u = (u64)(o.neg2 ? ~r2[i] : r2[i]) + d;
+    o.k2[i] = (u32)u;
+    d = u >> 32;
+  }
+}
+
+#define PA_GLV_WINDOWS 33  // 4-bit windows over 132 bits, plus one carry digit
+
+// kp = |k| + 0x888...8 (33 nibbles): digit i = nibble_i(kp) - 8, digit 33 = the carry out
+PA_HD void glv_recode(u32 kp[5], const u32 k[5]) {
+  const u32 add[5] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x8u};
   u64 c = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    u64 s = (u64)k.v[i] + 0x88888888u + c;
-    kp[i] = (u32)s;
-    c = s >> 32;
+  for (int i = 0; i < 5; ++i) {
+    u64 t = (u64)k[i] + add[i] + c;
+    kp[i] = (u32)t;
+    c = t >> 32;
   }
-  kp[8] = (u32)c;
 }
-PA_HD int smul_digit(const u32 kp[9], int i) {  // i in [0, 64]
-  if (i == 64) return (int)kp[8];
+PA_HD int glv_digit(const u32 kp[5], int i) {  // i in [0, 33]
+  if (i == PA_GLV_WINDOWS) return (int)((kp[4] >> 4) & 1u);
   return (int)((kp[i >> 3] >> ((i & 7) * 4)) & 15u) - 8;
 }
 
-PA_HD void smul_add_digit(jac &r, const jac *T, int d) {
-  if (d > 0) {
-    jac_add(r, r, T[d - 1]);
-  } else if (d < 0) {
-    jac t;
-    jac_neg(t, T[-d - 1]);
-    jac_add(r, r, t);
+struct glv_table {  // 1P'..8P' affine on the curve isomorphic by a common Z; bx = beta * x
+  fe x[8], y[8], bx[8];
+};
+
+PA_HD void fe_set_beta(fe &b) {
+  const u32 B[8] = {0x719501EEu, 0xC1396C28u, 0x12F58995u, 0x9CF04975u, 0xAC3434E9u, 0x6E64479Eu, 0x657C0710u, 0x7AE96A2Bu};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b.v[i] = B[i];
+}
+
+// r = p + q, q affine, p not infinity and p != +-q (table construction); zr = Z3 / Z1
+PA_HD void jac_madd_zr(jac &r, fe &zr, const jac &p, const fe &qx, const fe &qy) {
+  fe zz, u2, s2, h, rr, hh, hhh, v, t;
+  fe_sqr(zz, p.Z);
+  fe_mul(u2, qx, zz);
+  fe_mul(s2, p.Z, zz);
+  fe_mul(s2, qy, s2);
+  fe_sub(h, u2, p.X);
+  fe_sub(rr, s2, p.Y);
+  fe_sqr(hh, h);
+  fe_mul(hhh, h, hh);
+  fe_mul(v, p.X, hh);
+  fe_mul(r.Z, p.Z, h);
+  fe_sqr(t, rr);
+  fe_sub(t, t, hhh);
+  fe_sub(t, t, v);
+  fe_sub(t, t, v);
+  fe_mul(hhh, p.Y, hhh);
+  r.X = t;
+  fe_sub(v, v, t);
+  fe_mul(v, rr, v);
+  fe_sub(r.Y, v, hhh);
+  zr = h;
+}
+
+// Table of a base given as Jacobian (X, Y, Z0), not infinity.  On return zeta is the common Z
+// INCLUDING Z0: the true points are (x[i], y[i], zeta).
+PA_HD void glv_build_table(glv_table &T, fe &zeta, const jac &P) {
+  // work on the curve isomorphic by Z0, where P is the affine point (X, Y)
+  jac acc;
+  fe zr[8];
+  acc.X = P.X;
+  acc.Y = P.Y;
+  fe_set_one(acc.Z);
+  jac pts[8];
+  pts[0] = acc;
+  jac_dbl(acc, acc);  // 2P: Z = 2Y
+  pts[1] = acc;
+  zr[1] = acc.Z;  // Z2 / Z1
+#pragma unroll 1
+  for (int i = 2; i < 8; ++i) {
+    jac_madd_zr(acc, zr[i], acc, P.X, P.Y);
+    pts[i] = acc;
   }
+  // bring everything to Z8: ratio_i = Z8 / Z_i = zr[i+1] * ... * zr[7]
+  fe ratio, r2, r3, beta;
+  fe_set_beta(beta);
+  T.x[7] = pts[7].X;
+  T.y[7] = pts[7].Y;
+  ratio = zr[7];
+#pragma unroll 1
+  for (int i = 6; i >= 0; --i) {
+    fe_sqr(r2, ratio);
+    fe_mul(r3, r2, ratio);
+    fe_mul(T.x[i], pts[i].X, r2);
+    fe_mul(T.y[i], pts[i].Y, r3);
+    if (i > 0) fe_mul(ratio, ratio, zr[i]);
+  }
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) fe_mul(T.bx[i], T.x[i], beta);
+  fe_mul(zeta, pts[7].Z, P.Z);
+}
+
+// rescale a table from its common Z to (its common Z) * f
+PA_HD void glv_scale_table(glv_table &T, const fe &f) {
+  fe f2, f3;
+  fe_sqr(f2, f);
+  fe_mul(f3, f2, f);
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    fe_mul(T.x[i], T.x[i], f2);
+    fe_mul(T.bx[i], T.bx[i], f2);
+    fe_mul(T.y[i], T.y[i], f3);
+  }
+}
+
+PA_HD void glv_add_digit(jac &r, const glv_table &T, int d, bool neg, bool lam) {
+  if (d == 0) return;
+  int idx = (d > 0 ? d : -d) - 1;
+  aff q;
+  q.x = lam ? T.bx[idx] : T.x[idx];
+  if ((d < 0) != neg) fe_neg(q.y, T.y[idx]); else q.y = T.y[idx];
+  jac_madd(r, r, q);
 }
 
 // r = a*P (+ b*Q when NB == 2), scalars < n, bases Jacobian (may be infinity)
 template <int NB>
 PA_HD void strauss(jac &r, const jac &P, const sc &a, const jac &Q, const sc &b) {
-  jac TP[8], TQ[NB == 2 ? 8 : 1];
-  u32 ka[9], kb[9];
-  smul_table8(TP, P);
-  smul_recode(ka, a);
-  if (NB == 2) {
-    smul_table8(TQ, Q);
-    smul_recode(kb, b);
+  glv_table TP, TQ;
+  glv_split sa, sb;
+  u32 a1[5], a2[5], b1[5], b2[5];
+  fe zeta, zq;
+  bool useP = !jac_is_inf(P) && !sc_is_zero(a);
+  bool useQ = NB == 2 && !jac_is_inf(Q) && !sc_is_zero(b);
+  fe_set_one(zeta);
+  if (useP) {
+    glv_build_table(TP, zeta, P);
+    glv_decompose(sa, a);
+    glv_recode(a1, sa.k1);
+    glv_recode(a2, sa.k2);
+  }
+  if (useQ) {
+    glv_build_table(TQ, zq, Q);
+    glv_decompose(sb, b);
+    glv_recode(b1, sb.k1);
+    glv_recode(b2, sb.k2);
+    if (useP) {  // one common Z for both tables: zeta_P * zeta_Q
+      glv_scale_table(TP, zq);
+      glv_scale_table(TQ, zeta);
+      fe_mul(zeta, zeta, zq);
+    } else {
+      zeta = zq;
+    }
   }
   jac_set_inf(r);
+  if (!useP && !useQ) return;
 #pragma unroll 1
-  for (int i = 64; i >= 0; --i) {
-    if (i != 64) {
+  for (int i = PA_GLV_WINDOWS; i >= 0; --i) {
+    if (i != PA_GLV_WINDOWS) {
       jac_dbl(r, r);
       jac_dbl(r, r);
       jac_dbl(r, r);
       jac_dbl(r, r);
     }
-    smul_add_digit(r, TP, smul_digit(ka, i));
-    if (NB == 2) smul_add_digit(r, TQ, smul_digit(kb, i));
+    if (useP) {
+      glv_add_digit(r, TP, glv_digit(a1, i), sa.neg1, false);
+      glv_add_digit(r, TP, glv_digit(a2, i), sa.neg2, true);
+    }
+    if (useQ) {
+      glv_add_digit(r, TQ, glv_digit(b1, i), sb.neg1, false);
+      glv_add_digit(r, TQ, glv_digit(b2, i), sb.neg2, true);
+    }
   }
+  if (!jac_is_inf(r)) fe_mul(r.Z, r.Z, zeta);  // back from the isomorphic curve
 }
 
 PA_HD void var_base_mul(jac &r, const jac &P, const sc &k) { strauss<1>(r, P, k, P, k); }
