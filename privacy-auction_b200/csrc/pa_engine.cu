@@ -213,14 +213,15 @@ static int work_reserve(pa_ctx *ctx, size_t n) { return ensure(ctx, &ctx->d_work
 static u32 *work_jac(pa_ctx *ctx) { return (u32 *)ctx->d_work; }
 static u32 *work_prefix(pa_ctx *ctx, size_t n) { return (u32 *)(ctx->d_work + n * 96); }
 
-static int normalize_to(pa_ctx *ctx, unsigned char *d_out, size_t n, int nper = 1, size_t stride = 64) {
+static int normalize_to(pa_ctx *ctx, unsigned char *d_out, size_t n, int nper = 1, size_t stride = 64, int inner = 1,
+                        size_t stride_in = 0) {
   // points per thread: amortise the ~270-multiplication inversion once the
   // batch is large enough to keep every SM busy anyway
   size_t per = n / (148 * 1024);
   if (per < 1) per = 1;
   if (per > 16) per = 16;
   size_t T = (n + per - 1) / per;
-  PA_LAUNCH(ctx, PA_K_NORMALIZE, k_normalize<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(work_jac(ctx), work_prefix(ctx, n), d_out, (int)n, (int)T, nper, stride));
+  PA_LAUNCH(ctx, PA_K_NORMALIZE, k_normalize<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(work_jac(ctx), work_prefix(ctx, n), d_out, (int)n, (int)T, nper, stride, inner, stride_in));
   return PA_OK;
 }
 
@@ -523,7 +524,7 @@ int prove_dev(pa_ctx *ctx, const unsigned char *stmts, const unsigned char *secr
   int rc = work_reserve(ctx, m);
   if (rc) return rc;
   PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n, L)));
-  if ((rc = normalize_to(ctx, proofs, m, K::NEPS, L.proof))) return rc;
+  if ((rc = normalize_to(ctx, proofs, m, K::NEPS, L.proof, L.inner, L.proof_in))) return rc;
   PA_LAUNCH(ctx, PA_K_PRESPOND + KIND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, secrets, rnd, b0, b1, (int)n, L)));
   return PA_OK;
 }

@@ -173,7 +173,8 @@ k_point_add(const unsigned char *p, const unsigned char *q, u32 *jout, int n, in
 // same kernel writes plain arrays (nper = 1, stride = 64) and the eps fields of
 // proof records (nper = eps per proof, stride = record size).
 __global__ void __launch_bounds__(PA_BLOCK)
-k_normalize(const u32 *jin, u32 *prefix, unsigned char *out, int n, int T, int nper, size_t stride) {
+k_normalize(const u32 *jin, u32 *prefix, unsigned char *out, int n, int T, int nper, size_t stride, int inner = 1,
+            size_t stride_in = 0) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   fe acc, z;
@@ -206,7 +207,8 @@ k_normalize(const u32 *jin, u32 *prefix, unsigned char *out, int n, int T, int n
       fe_mul(inv, inv, p.Z);
       jac_to_aff_with_zinv(a, p, zi);
     }
-    st_aff(out + (size_t)(idx / nper) * stride + (size_t)(idx % nper) * 64, a);
+    int item = idx / nper;
+    st_aff(out + (size_t)(item / inner) * stride + (size_t)(item % inner) * stride_in + (size_t)(idx % nper) * 64, a);
   }
 }
 
@@ -288,12 +290,21 @@ __global__ void k_peak_fe(u32 *sink, int iters, int sqr) {
 // Byte strides between consecutive items, so that proofs, statements, secrets and
 // draws can live inside larger records (e.g. the Schnorr proof of A sits at offset
 // 192 of a 736-byte commitment record whose offset 64 is its statement).
+// A record may hold `inner` proofs of the same kind at a fixed inner stride (the Schnorr
+// proofs of A and B in a commitment record, of X and R in a round-one record): item i is
+// proof i % inner of record i / inner, and ids are per record.
 struct pa_lay {
-  size_t proof, stmt, secret, rnd;
+  size_t proof, stmt, secret, rnd;           // strides between records
+  int inner;                                 // proofs per record
+  size_t proof_in, stmt_in, secret_in, rnd_in;  // strides between the proofs of one record
+  PA_HD size_t P(int i) const { return proof * (size_t)(i / inner) + proof_in * (size_t)(i % inner); }
+  PA_HD size_t S(int i) const { return stmt * (size_t)(i / inner) + stmt_in * (size_t)(i % inner); }
+  PA_HD size_t X(int i) const { return secret * (size_t)(i / inner) + secret_in * (size_t)(i % inner); }
+  PA_HD size_t R(int i) const { return rnd * (size_t)(i / inner) + rnd_in * (size_t)(i % inner); }
 };
 template <int KIND> inline pa_lay pa_lay_packed() {
   typedef proof_kind<KIND> K;
-  return pa_lay{(size_t)K::REC, (size_t)K::NSTMT * 64, (size_t)K::NSECRET * 32, (size_t)K::NRND * 32};
+  return pa_lay{(size_t)K::REC, (size_t)K::NSTMT * 64, (size_t)K::NSECRET * 32, (size_t)K::NRND * 32, 1, 0, 0, 0, 0};
 }
 
 // verifier step 1: challenge + unpublished challenge share, one thread per proof
@@ -303,7 +314,7 @@ k_verify_derive(const unsigned char *proofs, const unsigned char *stmts, const u
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   sc ch1;
-  verify_derive<KIND>(ch1, proofs + L.proof * i, stmts + L.stmt * i, ids[i]);
+  verify_derive<KIND>(ch1, proofs + L.P(i), stmts + L.S(i), ids[i / L.inner]);
 #pragma unroll
   for (int k = 0; k < 8; ++k) derived[8 * (size_t)i + k] = ch1.v[k];
 }
@@ -319,7 +330,7 @@ k_verify_checks(const unsigned char *proofs, const unsigned char *stmts, const u
   sc ch1;
 #pragma unroll
   for (int k = 0; k < 8; ++k) ch1.v[k] = derived[8 * (size_t)i + k];
-  bool ok = verify_check_one<KIND>(j, proofs + L.proof * i, stmts + L.stmt * i, ch1, comb);
+  bool ok = verify_check_one<KIND>(j, proofs + L.P(i), stmts + L.S(i), ch1, comb);
   chk[t] = ok ? 1 : 0;
 }
 // verifier step 3: verdict = AND of all checks (no early exit, as SEAL/bidder.cpp:244-298)
@@ -346,7 +357,7 @@ k_prove_ops(const unsigned char *stmts, const unsigned char *rnd, const unsigned
   if (t >= n * K::NEPS) return;
   int j = t / n, i = t % n;
   jac r;
-  int e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + L.stmt * i, rnd + L.rnd * i, comb);
+  int e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + L.S(i), rnd + L.R(i), comb);
   st_jac(jout + 24 * ((size_t)i * K::NEPS + e), r);
 }
 // prover step 3 (after k_normalize wrote the eps points): challenge and responses
@@ -356,7 +367,7 @@ k_prove_respond(unsigned char *proofs, const unsigned char *stmts, const u64 *id
                 const unsigned char *rnd, const unsigned char *b0, const unsigned char *b1, int n, pa_lay L) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  prove_respond<KIND>(proofs + L.proof * i, stmts + L.stmt * i, ids[i], secrets + L.secret * i, rnd + L.rnd * i,
+  prove_respond<KIND>(proofs + L.P(i), stmts + L.S(i), ids[i / L.inner], secrets + L.X(i), rnd + L.R(i),
                       proof_branch(KIND, b0, b1, i));
 }
 

@@ -137,9 +137,10 @@ __global__ void k_seal_update(const u32 *act, const u32 *pseg, const u32 *pauc, 
   junc[pauc[p]] = 1;
 }
 
-__global__ void k_seal_and3(const unsigned char *a, const unsigned char *b, const unsigned char *c, unsigned char *o, int n) {
+// o[i] = pair[2i] & pair[2i+1] (& c[i])
+__global__ void k_seal_and_pairs(const unsigned char *pair, const unsigned char *c, unsigned char *o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) o[i] = a[i] & b[i] & c[i];
+  if (i < n) o[i] = pair[2 * i] & pair[2 * i + 1] & (c ? c[i] : 1);
 }
 __global__ void k_seal_scatter_u8(const u32 *g, const unsigned char *src, unsigned char *dst, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,7 +258,9 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
 
   std::vector<unsigned char> junction(A, 0), okv(A, 1);
   std::vector<u64> maxbid(A, 0);
-  const pa_lay LC{736, 736, 224, 224}, LR{320, 320, 128, 128};
+  // strides of the records the proofs live in; LC2 / LR2: the two Schnorr proofs of a record in one batch
+  const pa_lay LC{736, 736, 224, 224, 1, 0, 0, 0, 0}, LC2{736, 736, 224, 224, 2, 96, 64, 32, 32};
+  const pa_lay LR2{320, 320, 128, 128, 2, 96, 64, 32, 32};
   auto d2h = [&](void *h, const void *d, size_t bytes) -> int {
     if (h && bytes) PA_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return PA_OK;
@@ -296,14 +299,13 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     if ((rc = work_reserve(ctx, 3 * Mb))) return rc;
     PA_LAUNCH(ctx, PA_K_COMMIT, (k_seal_commit_points<<<grid_for(3 * Mb), PA_BLOCK, 0, ctx->stream>>>(d_rndc, d_bits, ctx->d_comb, work_jac(ctx), (int)Mb)));
     if ((rc = normalize_to(ctx, d_crec, 3 * Mb, 3, 736))) return rc;
-    if ((rc = prove_dev<PA_POK>(ctx, d_crec + 64, d_rndc, nullptr, nullptr, d_cid, d_rndc + 64, d_crec + 192, Mb, LC))) return rc;
-    if ((rc = prove_dev<PA_POK>(ctx, d_crec + 128, d_rndc + 32, nullptr, nullptr, d_cid, d_rndc + 96, d_crec + 288, Mb, LC))) return rc;
+    // Schnorr proofs of A (alpha, v_A) and B (beta, v_B): 2 per record, one batch
+    if ((rc = prove_dev<PA_POK>(ctx, d_crec + 64, d_rndc, nullptr, nullptr, d_cid, d_rndc + 64, d_crec + 192, 2 * Mb, LC2))) return rc;
     if ((rc = prove_dev<PA_COM>(ctx, d_crec, d_rndc, d_bits, nullptr, d_cid, d_rndc + 128, d_crec + 384, Mb, LC))) return rc;
     if (verify) {
-      if ((rc = verify_dev<PA_POK, 1>(ctx, d_crec + 192, d_crec + 64, d_cid, d_cv, Mb, LC))) return rc;
-      if ((rc = verify_dev<PA_POK, 1>(ctx, d_crec + 288, d_crec + 128, d_cid, d_cv + Mb, Mb, LC))) return rc;
+      if ((rc = verify_dev<PA_POK, 1>(ctx, d_crec + 192, d_crec + 64, d_cid, d_cv, 2 * Mb, LC2))) return rc;  // verdicts interleaved A, B
       if ((rc = verify_dev<PA_COM, 4>(ctx, d_crec + 384, d_crec, d_cid, d_cv + 2 * Mb, Mb, LC))) return rc;
-      PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and3<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(d_cv, d_cv + Mb, d_cv + 2 * Mb, d_cv + 3 * Mb, (int)Mb)));
+      PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(d_cv, d_cv + 2 * Mb, d_cv + 3 * Mb, (int)Mb)));
     } else {
       PA_CUDA(ctx, cudaMemsetAsync(d_cv + 3 * Mb, 1, Mb, ctx->stream));
     }
@@ -345,12 +347,11 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     if ((rc = work_reserve(ctx, 2 * ma))) return rc;
     PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * ma), PA_BLOCK, 0, ctx->stream>>>(d_rnd1, ctx->d_comb, work_jac(ctx), (int)ma)));
     if ((rc = normalize_to(ctx, d_r1, 2 * ma, 2, 320))) return rc;
-    if ((rc = prove_dev<PA_POK>(ctx, d_r1, d_rnd1, nullptr, nullptr, d_pid, d_rnd1 + 64, d_r1 + 128, ma, LR))) return rc;
-    if ((rc = prove_dev<PA_POK>(ctx, d_r1 + 64, d_rnd1 + 32, nullptr, nullptr, d_pid, d_rnd1 + 96, d_r1 + 224, ma, LR))) return rc;
+    // Schnorr proofs of X (x, v_X) and R (r, v_R): 2 per record, one batch
+    if ((rc = prove_dev<PA_POK>(ctx, d_r1, d_rnd1, nullptr, nullptr, d_pid, d_rnd1 + 64, d_r1 + 128, 2 * ma, LR2))) return rc;
     if (verify) {
-      if ((rc = verify_dev<PA_POK, 1>(ctx, d_r1 + 128, d_r1, d_pid, d_r1v, ma, LR))) return rc;
-      if ((rc = verify_dev<PA_POK, 1>(ctx, d_r1 + 224, d_r1 + 64, d_pid, d_r1v + ma, ma, LR))) return rc;
-      PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and3<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(d_r1v, d_r1v + ma, d_r1v + ma, d_r1v + 2 * ma, (int)ma)));
+      if ((rc = verify_dev<PA_POK, 1>(ctx, d_r1 + 128, d_r1, d_pid, d_r1v, 2 * ma, LR2))) return rc;
+      PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(d_r1v, nullptr, d_r1v + 2 * ma, (int)ma)));
     } else {
       PA_CUDA(ctx, cudaMemsetAsync(d_r1v + 2 * ma, 1, ma, ctx->stream));
     }
