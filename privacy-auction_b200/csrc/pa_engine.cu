@@ -19,6 +19,8 @@ struct pa_ctx {
   size_t work_bytes = 0;
   unsigned char *d_stage = nullptr;  // staging for the host-buffer entry points
   size_t stage_bytes = 0;
+  unsigned char *d_pool = nullptr;  // state of the whole-auction runner (pa_seal_run)
+  size_t pool_bytes = 0;
   uint64_t launches = 0;
   std::string err;
   // optional per-kernel CUDA-event timing (pa_profile_begin / pa_profile_end)
@@ -165,6 +167,7 @@ int pa_ctx_destroy(pa_ctx *ctx) {
   cudaFree(ctx->d_comb);
   cudaFree(ctx->d_work);
   cudaFree(ctx->d_stage);
+  cudaFree(ctx->d_pool);
   for (auto &sp : ctx->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);

@@ -12,6 +12,9 @@
 #include "pa_proof.cuh"
 
 #define PA_BLOCK 128
+#ifndef PA_VAR_MINBLOCKS
+#define PA_VAR_MINBLOCKS 3
+#endif
 
 // ---- loads / stores ---------------------------------------------------------
 PA_D u32 pa_bswap(u32 x) { return __byte_perm(x, 0, 0x0123); }
@@ -111,7 +114,7 @@ k_fixed_base(const unsigned char *scalars, const u32 *__restrict__ tab, u32 *jou
   st_jac(jout + 24 * (size_t)i, r);
 }
 
-__global__ void __launch_bounds__(PA_BLOCK)
+__global__ void __launch_bounds__(PA_BLOCK, PA_VAR_MINBLOCKS)
 k_var_base(const unsigned char *points, const unsigned char *scalars, u32 *jout, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

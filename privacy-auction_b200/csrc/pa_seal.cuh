@@ -150,20 +150,18 @@ __global__ void k_seal_scatter_u8(const u32 *g, const unsigned char *src, unsign
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
 
-struct DevPool {  // everything the runner allocates, freed together
-  std::vector<void *> ptrs;
+// Everything the runner needs on the device is carved out of ONE grow-only arena owned by the
+// context (no cudaMalloc / cudaFree per run once it has reached its high-water mark).
+struct DevPool {
   pa_ctx *ctx;
-  explicit DevPool(pa_ctx *c) : ctx(c) {}
-  ~DevPool() {
-    cudaStreamSynchronize(ctx->stream);
-    for (void *p : ptrs) cudaFree(p);
-  }
+  size_t off = 0;
+  bool sizing;  // first pass: only add up sizes
+  explicit DevPool(pa_ctx *c, bool sizing_pass) : ctx(c), sizing(sizing_pass) {}
   template <class T> T *alloc(size_t count, bool zero = false) {
-    void *p = nullptr;
-    size_t bytes = (count ? count : 1) * sizeof(T);
-    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
-    ptrs.push_back(p);
-    if (zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
+    size_t bytes = align_up((count ? count : 1) * sizeof(T), 256);
+    unsigned char *p = sizing ? (unsigned char *)0x100 : ctx->d_pool + off;
+    off += bytes;
+    if (!sizing && zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
     return (T *)p;
   }
 };
@@ -208,10 +206,13 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   for (size_t s = 0; s < m; ++s)
     for (u32 k = boff[s]; k < boff[s + 1]; ++k) cid[k] = ids[s];
 
-  DevPool pool(ctx);
-#define PA_ALLOC(var, T, count, zero)              \
-  T *var = pool.alloc<T>(count, zero);             \
-  if (!var) return pa_fail(ctx, PA_ENOMEM, "pa_seal_run: cudaMalloc failed for " #var)
+  unsigned char *d_bits, *d_rndc, *d_crec, *d_cv, *d_junc, *d_prevbit, *d_prevpts, *d_prevx, *d_rnd1, *d_r1, *d_r1v, *d_Y, *d_b,
+      *d_ebit, *d_stmt, *d_sec, *d_bi, *d_bj, *d_rnd2, *d_proof, *d_pv, *d_r2v;
+  u32 *d_boff, *d_act, *d_pauc, *d_pseg, *d_soff, *d_g, *d_gslot;
+  u64 *d_ids, *d_streams, *d_ctr, *d_cid, *d_pid, *d_gid, *d_sstream, *d_sctr;
+  int *d_isinf;
+  auto carve = [&](DevPool &pool) {
+#define PA_ALLOC(var, T, count, zero) var = pool.alloc<T>(count, zero)
   PA_ALLOC(d_bits, unsigned char, Mb, false);
   PA_ALLOC(d_boff, u32, m + 1, false);
   PA_ALLOC(d_ids, u64, m, false);
@@ -249,7 +250,18 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   PA_ALLOC(d_proof, unsigned char, m * 1344, false);
   PA_ALLOC(d_pv, unsigned char, m, false);
   PA_ALLOC(d_r2v, unsigned char, m, false);
+  PA_ALLOC(d_sstream, u64, Mb, false);
+  PA_ALLOC(d_sctr, u64, Mb, false);
 #undef PA_ALLOC
+  };
+  {
+    DevPool sizing(ctx, true);
+    carve(sizing);
+    int rc0 = ensure(ctx, &ctx->d_pool, &ctx->pool_bytes, sizing.off + 4096);
+    if (rc0) return rc0;
+    DevPool real(ctx, false);
+    carve(real);
+  }
   int rc;
   if ((rc = up(ctx, d_bits, bits)) || (rc = up(ctx, d_boff, boff)) || (rc = up(ctx, d_ids, ids)) ||
       (rc = up(ctx, d_streams, streams)) || (rc = up(ctx, d_cid, cid)))
@@ -276,8 +288,6 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     std::vector<u64> sstream(Mb), sctr(Mb);
     for (size_t s = 0; s < m; ++s)
       for (u32 k = boff[s]; k < boff[s + 1]; ++k) sstream[k] = streams[s], sctr[k] = 7ull * (k - boff[s]);
-    u64 *d_sstream = pool.alloc<u64>(Mb), *d_sctr = pool.alloc<u64>(Mb);
-    if (!d_sstream || !d_sctr) return pa_fail(ctx, PA_ENOMEM, "pa_seal_run: cudaMalloc failed");
     if ((rc = up(ctx, d_sstream, sstream)) || (rc = up(ctx, d_sctr, sctr))) return rc;
     PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_sstream, d_sctr, nullptr, 7, d_rndc, (int)Mb)));
     // every slot must have consumed exactly 7 counters; otherwise redo that bidder sequentially

@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpa_engine.so")
+# PA_ENGINE_LIB overrides the library path (kernel-variant experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("PA_ENGINE_LIB") or os.path.join(_HERE, "libpa_engine.so")
 
 PA_OK, PA_EINVAL, PA_ENODEV, PA_ECUDA, PA_ENOMEM = 0, -1, -2, -3, -4
 POINT_BYTES, SCALAR_BYTES = 64, 32
