@@ -21,6 +21,9 @@ struct pa_ctx {
   size_t stage_bytes = 0;
   unsigned char *d_pool = nullptr;  // state of the whole-auction runner (pa_seal_run)
   size_t pool_bytes = 0;
+  // copy streams + events of the chunked host-buffer pipeline (created on first use)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_comp[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   std::string err;
   // optional per-kernel CUDA-event timing (pa_profile_begin / pa_profile_end)
@@ -151,7 +154,7 @@ int pa_ctx_create(pa_ctx **out, int device) {
   if ((e = cudaMalloc((void **)&ctx->d_comb, PA_COMB_WORDS * sizeof(u32))) != cudaSuccess) return fail("cudaMalloc(comb)", e);
   u32 *d_bases = nullptr;
   if ((e = cudaMalloc((void **)&d_bases, PA_COMB_WINDOWS * 16 * sizeof(u32))) != cudaSuccess) return fail("cudaMalloc(bases)", e);
-  k_comb_base<<<1, PA_COMB_WINDOWS, 0, ctx->stream>>>(d_bases);
+  k_comb_base<<<1, 32, 0, ctx->stream>>>(d_bases);
   k_comb_entries<<<PA_COMB_WINDOWS * PA_COMB_ENTRIES / PA_BLOCK, PA_BLOCK, 0, ctx->stream>>>(d_bases, ctx->d_comb);
   ctx->launches += 2;
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("comb table build", e);
@@ -168,6 +171,11 @@ int pa_ctx_destroy(pa_ctx *ctx) {
   cudaFree(ctx->d_work);
   cudaFree(ctx->d_stage);
   cudaFree(ctx->d_pool);
+  if (ctx->s_in) {
+    cudaStreamDestroy(ctx->s_in);
+    cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(ctx->ev_in[i]), cudaEventDestroy(ctx->ev_comp[i]), cudaEventDestroy(ctx->ev_out[i]);
+  }
   for (auto &sp : ctx->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
@@ -294,70 +302,94 @@ struct Stage {
 int stage_reserve(pa_ctx *ctx, size_t bytes) { return ensure(ctx, &ctx->d_stage, &ctx->stage_bytes, bytes); }
 }  // namespace
 
+namespace {
+// Large host-buffer batches are processed in chunks so that the host->device copy of chunk
+// k+1 and the device->host copy of chunk k-1 overlap the kernels of chunk k (three streams,
+// three staging slots).  `per` = bytes per item of each argument.
+struct PArg {
+  const void *in;
+  void *out;
+  size_t per;
+};
+const size_t PA_PIPE_CHUNK = 1u << 17;
+
+template <typename F>
+int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
+  if (!ctx->s_in) {
+    PA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    PA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+      PA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      PA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+      PA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t CH = n < PA_PIPE_CHUNK ? n : PA_PIPE_CHUNK;
+  size_t slot_bytes = 1024;
+  for (int i = 0; i < nargs; ++i) slot_bytes += align_up(args[i].per * CH, 256);
+  const int slots = n > CH ? 3 : 1;
+  int rc = stage_reserve(ctx, slot_bytes * slots + 1024);
+  if (rc) return rc;
+  if ((rc = work_reserve(ctx, CH))) return rc;  // no arena growth (= sync) inside the pipeline
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += CH, ++k) {
+    const size_t cnt = n - off < CH ? n - off : CH;
+    const int slot = (int)(k % slots);
+    unsigned char *base = ctx->d_stage + slot_bytes * slot, *d[16];
+    size_t o = 0;
+    for (int i = 0; i < nargs; ++i) {
+      d[i] = base + o;
+      o += align_up(args[i].per * CH, 256);
+    }
+    if (k >= (size_t)slots) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[slot], 0));  // slot free again
+    for (int i = 0; i < nargs; ++i)
+      if (args[i].in)
+        PA_CUDA(ctx, cudaMemcpyAsync(d[i], (const unsigned char *)args[i].in + args[i].per * off, args[i].per * cnt, cudaMemcpyHostToDevice, ctx->s_in));
+    PA_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+    PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
+    if ((rc = run(d, cnt))) return rc;
+    PA_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->stream));
+    PA_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0));
+    for (int i = 0; i < nargs; ++i)
+      if (args[i].out)
+        PA_CUDA(ctx, cudaMemcpyAsync((unsigned char *)args[i].out + args[i].per * off, d[i], args[i].per * cnt, cudaMemcpyDeviceToHost, ctx->s_out));
+    PA_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
+  }
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int pa_fixed_base_mul(pa_ctx *ctx, const uint8_t *scalars, uint8_t *out, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (scalars && out)));
   if (n == 0) return PA_OK;
-  int rc = stage_reserve(ctx, n * 96 + 1024);
-  if (rc) return rc;
-  Stage s(ctx);
-  unsigned char *d_k = s.take(n * 32), *d_o = s.take(n * 64);
-  PA_CUDA(ctx, cudaMemcpyAsync(d_k, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = pa_fixed_base_mul_dev(ctx, d_k, d_o, n))) return rc;
-  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
-  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return PA_OK;
+  PArg a[] = {{scalars, 0, 32}, {0, out, 64}};
+  return pipelined(ctx, n, a, 2, [&](unsigned char **d, size_t cnt) { return pa_fixed_base_mul_dev(ctx, d[0], d[1], cnt); });
 }
 
 int pa_var_base_mul(pa_ctx *ctx, const uint8_t *points, const uint8_t *scalars, uint8_t *out, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (points && scalars && out)));
   if (n == 0) return PA_OK;
-  int rc = stage_reserve(ctx, n * 160 + 1024);
-  if (rc) return rc;
-  Stage s(ctx);
-  unsigned char *d_p = s.take(n * 64), *d_k = s.take(n * 32), *d_o = s.take(n * 64);
-  PA_CUDA(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-  PA_CUDA(ctx, cudaMemcpyAsync(d_k, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = pa_var_base_mul_dev(ctx, d_p, d_k, d_o, n))) return rc;
-  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
-  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return PA_OK;
+  PArg a[] = {{points, 0, 64}, {scalars, 0, 32}, {0, out, 64}};
+  return pipelined(ctx, n, a, 3, [&](unsigned char **d, size_t cnt) { return pa_var_base_mul_dev(ctx, d[0], d[1], d[2], cnt); });
 }
 
 int pa_double_mul(pa_ctx *ctx, const uint8_t *a, const uint8_t *points, const uint8_t *b, uint8_t *out, size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (a && points && b && out)));
   if (n == 0) return PA_OK;
-  int rc = stage_reserve(ctx, n * 192 + 1024);
-  if (rc) return rc;
-  Stage s(ctx);
-  unsigned char *d_a = s.take(n * 32), *d_p = s.take(n * 64), *d_b = s.take(n * 32), *d_o = s.take(n * 64);
-  PA_CUDA(ctx, cudaMemcpyAsync(d_a, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  PA_CUDA(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-  PA_CUDA(ctx, cudaMemcpyAsync(d_b, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = pa_double_mul_dev(ctx, d_a, d_p, d_b, d_o, n))) return rc;
-  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
-  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return PA_OK;
+  PArg g[] = {{a, 0, 32}, {points, 0, 64}, {b, 0, 32}, {0, out, 64}};
+  return pipelined(ctx, n, g, 4, [&](unsigned char **d, size_t cnt) { return pa_double_mul_dev(ctx, d[0], d[1], d[2], d[3], cnt); });
 }
 
 int pa_lincomb2(pa_ctx *ctx, const uint8_t *p, const uint8_t *a, const uint8_t *q, const uint8_t *b, uint8_t *out,
                 size_t n) {
   PA_ARGCHECK(ctx, ctx && (n == 0 || (p && a && q && b && out)));
   if (n == 0) return PA_OK;
-  int rc = stage_reserve(ctx, n * 256 + 2048);
-  if (rc) return rc;
-  Stage s(ctx);
-  unsigned char *d_p = s.take(n * 64), *d_a = s.take(n * 32), *d_q = s.take(n * 64), *d_b = s.take(n * 32),
-                *d_o = s.take(n * 64);
-  PA_CUDA(ctx, cudaMemcpyAsync(d_p, p, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-  PA_CUDA(ctx, cudaMemcpyAsync(d_a, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  PA_CUDA(ctx, cudaMemcpyAsync(d_q, q, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-  PA_CUDA(ctx, cudaMemcpyAsync(d_b, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = pa_lincomb2_dev(ctx, d_p, d_a, d_q, d_b, d_o, n))) return rc;
-  PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
-  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return PA_OK;
+  PArg g[] = {{p, 0, 64}, {a, 0, 32}, {q, 0, 64}, {b, 0, 32}, {0, out, 64}};
+  return pipelined(ctx, n, g, 5, [&](unsigned char **d, size_t cnt) { return pa_lincomb2_dev(ctx, d[0], d[1], d[2], d[3], d[4], cnt); });
 }
 
 int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, int sub) {

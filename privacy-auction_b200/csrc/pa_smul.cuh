@@ -5,9 +5,9 @@
 //   double       g^a P^b    EC_POINT_mul(group, r, a, P, b, ctx)         SEAL/bidder.cpp:175
 //   a check      P^a Q^b    two EC_POINT_mul + EC_POINT_add              SEAL/bidder.cpp:266-268
 //
-// Fixed base: 8-bit comb.  TAB[w][d] = d * 2^(8w) * G in affine form for
-// w < 32, d < 256 (512 KiB, L2-resident, built once per context on the GPU);
-// g^k is 32 mixed additions and no doublings.
+// Fixed base: 12-bit comb.  TAB[w][d] = d * 2^(12w) * G in affine form for
+// w < 22, d < 4096 (5.5 MiB, resident in the 126 MB L2, built once per context
+// on the GPU); g^k is 22 mixed additions and no doublings.
 //
 // Variable base: GLV split (128 doublings instead of 256), signed 4-bit fixed
 // windows over a per-thread co-Z table of 1P..8P (mixed additions), one or two
@@ -18,9 +18,10 @@
 #include "pa_ec.cuh"
 #include "pa_sc.cuh"
 
-#define PA_COMB_WINDOWS 32
-#define PA_COMB_ENTRIES 256
-#define PA_COMB_WORDS (PA_COMB_WINDOWS * PA_COMB_ENTRIES * 16)  // u32 words
+#define PA_COMB_BITS 12
+#define PA_COMB_WINDOWS ((256 + PA_COMB_BITS - 1) / PA_COMB_BITS)  // 22
+#define PA_COMB_ENTRIES (1 << PA_COMB_BITS)                        // 4096
+#define PA_COMB_WORDS (PA_COMB_WINDOWS * PA_COMB_ENTRIES * 16)     // u32 words (5.5 MiB)
 
 PA_HD void comb_load(aff &q, const u32 *tab, int w, u32 d) {
   const u32 *e = tab + ((size_t)(w * PA_COMB_ENTRIES) + d) * 16;
@@ -44,7 +45,10 @@ PA_HD void fixed_base_mul(jac &r, const sc &k, const u32 *tab) {
   jac_set_inf(r);
 #pragma unroll 1
   for (int w = 0; w < PA_COMB_WINDOWS; ++w) {
-    u32 d = (k.v[w >> 2] >> ((w & 3) * 8)) & 0xFFu;
+    int bit = w * PA_COMB_BITS, limb = bit >> 5, sh = bit & 31;
+    u32 d = k.v[limb] >> sh;
+    if (sh + PA_COMB_BITS > 32 && limb < 7) d |= k.v[limb + 1] << (32 - sh);
+    d &= (u32)(PA_COMB_ENTRIES - 1);
     if (d) {
       aff q;
       comb_load(q, tab, w, d);
@@ -209,33 +213,33 @@ PA_HD void glv_build_table(glv_table &T, fe &zeta, const jac &P) {
   acc.X = P.X;
   acc.Y = P.Y;
   fe_set_one(acc.Z);
-  jac pts[8];
-  pts[0] = acc;
+  T.x[0] = acc.X;
+  T.y[0] = acc.Y;
   jac_dbl(acc, acc);  // 2P: Z = 2Y
-  pts[1] = acc;
+  T.x[1] = acc.X;
+  T.y[1] = acc.Y;
   zr[1] = acc.Z;  // Z2 / Z1
 #pragma unroll 1
   for (int i = 2; i < 8; ++i) {
     jac_madd_zr(acc, zr[i], acc, P.X, P.Y);
-    pts[i] = acc;
+    T.x[i] = acc.X;
+    T.y[i] = acc.Y;
   }
   // bring everything to Z8: ratio_i = Z8 / Z_i = zr[i+1] * ... * zr[7]
   fe ratio, r2, r3, beta;
   fe_set_beta(beta);
-  T.x[7] = pts[7].X;
-  T.y[7] = pts[7].Y;
   ratio = zr[7];
 #pragma unroll 1
   for (int i = 6; i >= 0; --i) {
     fe_sqr(r2, ratio);
     fe_mul(r3, r2, ratio);
-    fe_mul(T.x[i], pts[i].X, r2);
-    fe_mul(T.y[i], pts[i].Y, r3);
+    fe_mul(T.x[i], T.x[i], r2);
+    fe_mul(T.y[i], T.y[i], r3);
     if (i > 0) fe_mul(ratio, ratio, zr[i]);
   }
 #pragma unroll 1
   for (int i = 0; i < 8; ++i) fe_mul(T.bx[i], T.x[i], beta);
-  fe_mul(zeta, pts[7].Z, P.Z);
+  fe_mul(zeta, acc.Z, P.Z);
 }
 
 // rescale a table from its common Z to (its common Z) * f
@@ -314,18 +318,18 @@ PA_HD void strauss(jac &r, const jac &P, const sc &a, const jac &Q, const sc &b)
 PA_HD void var_base_mul(jac &r, const jac &P, const sc &k) { strauss<1>(r, P, k, P, k); }
 
 // ---- comb table construction (GPU, once per context; also host-checked) ----
-// phase 1: B_w = 2^(8w) G, affine, for w in [0, 32)
+// phase 1: B_w = 2^(PA_COMB_BITS * w) G, affine, for every window w
 PA_HD void comb_base(aff &out, int w, const aff &G) {
   jac p;
   jac_from_aff(p, G);
-  for (int i = 0; i < 8 * w; ++i) jac_dbl(p, p);
+  for (int i = 0; i < PA_COMB_BITS * w; ++i) jac_dbl(p, p);
   jac_to_aff(out, p);
 }
 // phase 2: entry d of window w from B_w
 PA_HD void comb_entry(aff &out, u32 d, const aff &Bw) {
   jac r;
   jac_set_inf(r);
-  for (int bit = 7; bit >= 0; --bit) {
+  for (int bit = PA_COMB_BITS - 1; bit >= 0; --bit) {
     jac_dbl(r, r);
     if ((d >> bit) & 1u) jac_madd(r, r, Bw);
   }
