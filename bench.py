@@ -377,7 +377,8 @@ def main():
                     "steps": e2e_steps, "bytes_match_device_run": same},
             "gpu_launches": int(launches),
             "roofline": {"bound": "imad", "kernel": "k_var_base", "achieved": achieved / 1e12, "peak": peak_imad / 1e12,
-                         "unit": "TIMAD/s", "frac": achieved / peak_imad, "traffic": None,
+                         "unit": "TIMAD/s", "frac": achieved / peak_imad,
+                         "traffic": 1.80e9,  # dram read + write per launch, ncu --set full (profiles/r01b_ncu_full_k_var_base_glv_summary.csv)
                          "peak_source": "measured on this GPU by pa_measure_int_peak (register-only 32-bit IMAD loop); not in MEASURED_PEAKS.json",
                          "nominal_peak": nominal_peak / 1e12, "frac_of_nominal": achieved / nominal_peak,
                          "algorithmic": f"{FM_VAR} field mults x {IMAD_PER_FM} IMAD per variable-base mult (SURVEY.md 8d) x {n} per launch",

@@ -17,3 +17,6 @@ for cfg in "4 5 9 2 -" "2 3 1 0 -" "3 6 4 1 0,0,0" "5 4 8 4 -" "1 3 2 0 5" "4 8 
   set -- $cfg
   ./oracle/_ref/ccs22_ref "$1" "$2" "$3" "$4" "$5" "tests/golden/ccs22_n$1_c$2_s$3_e$4.bin"
 done
+# BASELINE configs 1 and 2 at full size (digests only, tests/golden/baseline_config_digests.json):
+#   ./oracle/_ref/seal_ref 10 20 2024 - /tmp/seal_10_20.bin          (~52 s)
+#   ./oracle/_ref/ccs22_ref 20 32 2024 7 - /tmp/ccs22_20_32.bin ; ./oracle/_ref/ccs22_ref 20 31 2025 3 - /tmp/ccs22_20_31.bin
