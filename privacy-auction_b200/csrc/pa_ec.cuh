@@ -68,25 +68,23 @@ PA_HD void jac_dbl(jac &r, const jac &p) { jac_dbl_inl(r, p); }
 #endif
 
 // r = 2p   (dbl-2009-l, 2M + 5S).  No point of order 2 exists (prime order).
+// Arranged as three stages of two independent products plus one final product.
 PA_HD void jac_dbl_inl(jac &r, const jac &p) {
   if (jac_is_inf(p)) {
     jac_set_inf(r);
     return;
   }
-  fe A, B, C, D, E, F, t;
-  fe_sqr(A, p.X);
-  fe_sqr(B, p.Y);
-  fe_sqr(C, B);
+  fe A, B, C, D, E, F, t, yz;
+  fe_sqr2(A, p.X, B, p.Y);  // A = X^2, B = Y^2
   fe_add(t, p.X, B);
-  fe_sqr(t, t);
+  fe_sqr2(C, B, t, t);  // C = B^2, t = (X + B)^2
   fe_sub(t, t, A);
   fe_sub(t, t, C);
   fe_dbl(D, t);  // D = 2((X+B)^2 - A - C)
   fe_dbl(E, A);
   fe_add(E, E, A);  // E = 3A
-  fe_sqr(F, E);
-  fe_mul(t, p.Y, p.Z);
-  fe_dbl(r.Z, t);  // Z3 = 2YZ
+  fe_sqrmul(F, E, yz, p.Y, p.Z);  // F = E^2, yz = Y*Z
+  fe_dbl(r.Z, yz);  // Z3 = 2YZ
   fe_dbl(t, D);
   fe_sub(r.X, F, t);  // X3 = F - 2D
   fe_sub(t, D, r.X);
@@ -97,7 +95,7 @@ PA_HD void jac_dbl_inl(jac &r, const jac &p) {
   fe_sub(r.Y, t, C);  // Y3 = E(D - X3) - 8C
 }
 
-// r = p + q, q affine   (8M + 3S)
+// r = p + q, q affine   (8M + 3S), in six stages of (mostly) two independent products
 PA_HD void jac_madd_inl(jac &r, const jac &p, const aff &q) {
   if (aff_is_inf(q)) {
     r = p;
@@ -109,12 +107,11 @@ PA_HD void jac_madd_inl(jac &r, const jac &p, const aff &q) {
     fe_set_one(r.Z);
     return;
   }
-  fe zz, u2, s2, h, rr, hh, hhh, v, t;
+  fe zz, u2, zzz, s2, z3, h, rr, hh, r2, hhh, v, t, yh;
   fe_sqr(zz, p.Z);
-  fe_mul(u2, q.x, zz);
-  fe_mul(s2, p.Z, zz);
-  fe_mul(s2, q.y, s2);
+  fe_mul2(u2, q.x, zz, zzz, p.Z, zz);  // U2 = x2 Z1^2, Z1^3
   fe_sub(h, u2, p.X);
+  fe_mul2(s2, q.y, zzz, z3, p.Z, h);  // S2 = y2 Z1^3, Z3 = Z1 H
   fe_sub(rr, s2, p.Y);
   if (fe_is_zero(h)) {
     if (fe_is_zero(rr)) {
@@ -124,19 +121,16 @@ PA_HD void jac_madd_inl(jac &r, const jac &p, const aff &q) {
     }
     return;
   }
-  fe_sqr(hh, h);
-  fe_mul(hhh, h, hh);
-  fe_mul(v, p.X, hh);
-  fe_mul(r.Z, p.Z, h);
-  fe_sqr(t, rr);
-  fe_sub(t, t, hhh);
+  fe_sqr2(hh, h, r2, rr);              // H^2, R^2
+  fe_mul2(hhh, h, hh, v, p.X, hh);     // H^3, V = X1 H^2
+  fe_sub(t, r2, hhh);
   fe_sub(t, t, v);
   fe_sub(t, t, v);  // X3 = R^2 - H^3 - 2V
-  fe_mul(hhh, p.Y, hhh);
-  r.X = t;
   fe_sub(v, v, t);
-  fe_mul(v, rr, v);
-  fe_sub(r.Y, v, hhh);  // Y3 = R(V - X3) - Y1 H^3
+  fe_mul2(yh, p.Y, hhh, v, rr, v);     // Y1 H^3, R (V - X3)
+  r.X = t;
+  r.Z = z3;
+  fe_sub(r.Y, v, yh);  // Y3 = R(V - X3) - Y1 H^3
 }
 
 // r = p + q   (12M + 4S)

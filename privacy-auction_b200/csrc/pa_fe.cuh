@@ -313,6 +313,100 @@ PA_HD void fe_mul(fe &r, const fe &a, const fe &b) { fe_mul_inl(r, a, b); }
 PA_HD void fe_sqr(fe &r, const fe &a) { fe_sqr_inl(r, a); }
 #endif
 
+// Two independent products per call.  The point formulas (pa_ec.cuh) are arranged in stages of
+// two independent products.  Computing a pair inside ONE non-inlined function (PA_FE_PAIRS) lets
+// ptxas interleave the two multiply-add chains; measured on B200 this lowers the lone-warp latency
+// a little (n = 1000 auction 204 -> 191 ms of kernel time) but costs throughput (2^20 variable-base
+// mults 19.9 -> 22.1 ms, more registers live), so the default issues the two calls back to back.
+struct fe2 {
+  fe a, b;
+};
+#if defined(__CUDA_ARCH__) && !defined(PA_FE_PAIRS)  // default: the two products as two calls
+PA_D void fe_mul2(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1) {
+  fe x = fe_mul_call(a0, b0), y = fe_mul_call(a1, b1);
+  r0 = x;
+  r1 = y;
+}
+PA_D void fe_sqr2(fe &r0, const fe &a0, fe &r1, const fe &a1) {
+  fe x = fe_sqr_call(a0), y = fe_sqr_call(a1);
+  r0 = x;
+  r1 = y;
+}
+PA_D void fe_sqrmul(fe &r0, const fe &a0, fe &r1, const fe &a1, const fe &b1) {
+  fe x = fe_sqr_call(a0), y = fe_mul_call(a1, b1);
+  r0 = x;
+  r1 = y;
+}
+#elif defined(__CUDA_ARCH__) && !defined(PA_FE_INLINE)
+static __device__ __noinline__ fe2 fe_mul2_call(fe a0, fe b0, fe a1, fe b1) {
+  fe2 r;
+  u32 t0[16], t1[16];
+  mp_mul8(t0, a0.v, b0.v);
+  mp_mul8(t1, a1.v, b1.v);
+  fe_reduce512(r.a, t0);
+  fe_reduce512(r.b, t1);
+  return r;
+}
+static __device__ __noinline__ fe2 fe_sqr2_call(fe a0, fe a1) {
+  fe2 r;
+  u32 t0[16], t1[16];
+  mp_sqr8(t0, a0.v);
+  mp_sqr8(t1, a1.v);
+  fe_reduce512(r.a, t0);
+  fe_reduce512(r.b, t1);
+  return r;
+}
+static __device__ __noinline__ fe2 fe_sqrmul_call(fe a0, fe a1, fe b1) {
+  fe2 r;
+  u32 t0[16], t1[16];
+  mp_sqr8(t0, a0.v);
+  mp_mul8(t1, a1.v, b1.v);
+  fe_reduce512(r.a, t0);
+  fe_reduce512(r.b, t1);
+  return r;
+}
+// r0 = a0*b0, r1 = a1*b1
+PA_D void fe_mul2(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1) {
+  fe2 t = fe_mul2_call(a0, b0, a1, b1);
+  r0 = t.a;
+  r1 = t.b;
+}
+// r0 = a0^2, r1 = a1^2
+PA_D void fe_sqr2(fe &r0, const fe &a0, fe &r1, const fe &a1) {
+  fe2 t = fe_sqr2_call(a0, a1);
+  r0 = t.a;
+  r1 = t.b;
+}
+// r0 = a0^2, r1 = a1*b1
+PA_D void fe_sqrmul(fe &r0, const fe &a0, fe &r1, const fe &a1, const fe &b1) {
+  fe2 t = fe_sqrmul_call(a0, a1, b1);
+  r0 = t.a;
+  r1 = t.b;
+}
+#else
+PA_HD void fe_mul2(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1) {
+  fe x, y;
+  fe_mul_inl(x, a0, b0);
+  fe_mul_inl(y, a1, b1);
+  r0 = x;
+  r1 = y;
+}
+PA_HD void fe_sqr2(fe &r0, const fe &a0, fe &r1, const fe &a1) {
+  fe x, y;
+  fe_sqr_inl(x, a0);
+  fe_sqr_inl(y, a1);
+  r0 = x;
+  r1 = y;
+}
+PA_HD void fe_sqrmul(fe &r0, const fe &a0, fe &r1, const fe &a1, const fe &b1) {
+  fe x, y;
+  fe_sqr_inl(x, a0);
+  fe_mul_inl(y, a1, b1);
+  r0 = x;
+  r1 = y;
+}
+#endif
+
 PA_HD void fe_sqr_n(fe &r, const fe &a, int n) {
   fe t = a;
   for (int i = 0; i < n; ++i) fe_sqr(t, t);
