@@ -148,14 +148,15 @@ def proof_throughput(eng, torch, n=1 << 15, seed=77):
     bj = rng.integers(0, 2, size=n, dtype=np.uint8)
     bi = bit & bj
     ids = [int(v) for v in rng.integers(0, 1 << 20, size=n)]
-    X, R, Y = P(eng.fixed_base_mul(x)), P(eng.fixed_base_mul(r)), P(eng.fixed_base_mul(sc()))
-    Xj, Rj, Yj = P(eng.fixed_base_mul(xj)), P(eng.fixed_base_mul(rj)), P(eng.fixed_base_mul(sc()))
+    B = lambda a: np.ascontiguousarray(a).tobytes()   # the ctypes binding takes flat byte strings
+    X, R, Y = P(eng.fixed_base_mul(B(x))), P(eng.fixed_base_mul(B(r))), P(eng.fixed_base_mul(B(sc())))
+    Xj, Rj, Yj = P(eng.fixed_base_mul(B(xj))), P(eng.fixed_base_mul(B(rj))), P(eng.fixed_base_mul(B(sc())))
     pick = lambda m, a, b: np.where(m[:, None].astype(bool), a, b)
-    c1 = P(eng.commit_points(al, be, bit))
-    b1 = P(eng.var_base_mul(pick(bit, R, Y), x))
-    c2 = P(eng.commit_points(al, be, bi))
-    Bi = P(eng.var_base_mul(pick(bi, R, Y), x))
-    Bj = P(eng.var_base_mul(pick(bj, Rj, Yj), xj))
+    c1 = P(eng.commit_points(B(al), B(be), B(bit)))
+    b1 = P(eng.var_base_mul(B(pick(bit, R, Y)), B(x)))
+    c2 = P(eng.commit_points(B(al), B(be), B(bi)))
+    Bi = P(eng.var_base_mul(B(pick(bi, R, Y)), B(x)))
+    Bj = P(eng.var_base_mul(B(pick(bj, Rj, Yj)), B(xj)))
     cases = {
         "pok": dict(stmt=X, sec=x, args=(), rnd=sc(1), rec=96, mults=2),
         "com": dict(stmt=c1, sec=al, args=(bit,), rnd=sc(3), rec=352, mults=8),
@@ -167,7 +168,7 @@ def proof_throughput(eng, torch, n=1 << 15, seed=77):
     t_ids = torch.tensor(ids, dtype=torch.int64, device="cuda")
     out = {}
     for kind, cs in cases.items():
-        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        dev = lambda a: torch.from_numpy(np.array(a, copy=True)).cuda()
         d_stmt, d_sec, d_rnd = dev(cs["stmt"]), dev(cs["sec"]), dev(cs["rnd"])
         d_args = [dev(a) for a in cs["args"]]
         d_proofs = torch.empty(n * cs["rec"], dtype=torch.uint8, device="cuda")
