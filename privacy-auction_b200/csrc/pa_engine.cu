@@ -21,6 +21,13 @@ struct pa_ctx {
   size_t stage_bytes = 0;
   unsigned char *d_pool = nullptr;  // state of the whole-auction runner (pa_seal_run)
   size_t pool_bytes = 0;
+  // side lanes of the whole-auction runner: a stream with its own work arena each (created on first use)
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    unsigned char *work = nullptr;
+    size_t work_bytes = 0;
+  } lanes[3];
+  cudaEvent_t lane_ev[10] = {};
   // copy streams + events of the chunked host-buffer pipeline (created on first use)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_comp[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
@@ -171,6 +178,12 @@ int pa_ctx_destroy(pa_ctx *ctx) {
   cudaFree(ctx->d_work);
   cudaFree(ctx->d_stage);
   cudaFree(ctx->d_pool);
+  for (auto &l : ctx->lanes) {
+    if (l.stream) cudaStreamDestroy(l.stream);
+    cudaFree(l.work);
+  }
+  for (auto e : ctx->lane_ev)
+    if (e) cudaEventDestroy(e);
   if (ctx->s_in) {
     cudaStreamDestroy(ctx->s_in);
     cudaStreamDestroy(ctx->s_out);

@@ -171,6 +171,45 @@ template <class T> int up(pa_ctx *ctx, T *d, const std::vector<T> &h) {
   return PA_OK;
 }
 
+// A lane = a stream with its own work arena.  Within a step only a short chain is truly
+// sequential (keys -> Y scan -> cryptogram -> round three); the Schnorr proofs of round one, the
+// OR proofs of round two and all verification hang off that chain.  They run in three side lanes
+// so that kernels of ~10^3..10^4 threads from different phases and steps share the 148 SMs.
+// While a LaneScope is alive, ctx->stream / ctx->d_work ARE the lane's.
+struct LaneScope {
+  pa_ctx *ctx;
+  pa_ctx::Lane *lane;
+  cudaStream_t s0;
+  unsigned char *w0;
+  size_t b0;
+  LaneScope(pa_ctx *c, pa_ctx::Lane *l) : ctx(c), lane(l), s0(c->stream), w0(c->d_work), b0(c->work_bytes) {
+    ctx->stream = lane->stream;
+    ctx->d_work = lane->work;
+    ctx->work_bytes = lane->work_bytes;
+  }
+  ~LaneScope() {
+    lane->work = ctx->d_work;  // may have grown
+    lane->work_bytes = ctx->work_bytes;
+    ctx->stream = s0;
+    ctx->d_work = w0;
+    ctx->work_bytes = b0;
+  }
+};
+
+int lanes_init(pa_ctx *ctx) {
+  if (ctx->lanes[0].stream) return PA_OK;
+  for (int i = 0; i < 3; ++i) PA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lanes[i].stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 10; ++i) PA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_ev[i], cudaEventDisableTiming));
+  return PA_OK;
+}
+
+struct StepBufs {  // per-step device buffers; two sets, used alternately
+  u32 *act, *pauc, *pseg, *soff, *g, *gslot;
+  u64 *pid, *gid;
+  unsigned char *rnd1, *r1, *pokv, *Y, *b, *ebit, *stmt, *sec, *bi, *bj, *rnd2, *proof, *pv;
+  int *isinf;
+};
+
 }  // namespace
 
 extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
@@ -179,6 +218,12 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   const bool sharded = job->allgather != nullptr;
   PA_ARGCHECK(ctx, !sharded || (A == 1 && job->hi > job->lo && job->hi <= job->n[0] && job->d_send && job->d_recv && job->slice >= job->hi - job->lo));
   const bool verify = job->verify != 0;
+  const bool want_r1 = job->out_r1 != nullptr, want_b = job->out_r2_b != nullptr, want_proof = job->out_r2_proof != nullptr;
+  int rc;
+  if ((rc = lanes_init(ctx))) return rc;
+  pa_ctx::Lane *L_pok = &ctx->lanes[0], *L_prove = &ctx->lanes[1], *L_verify = &ctx->lanes[2];
+  cudaEvent_t *ev_r1 = &ctx->lane_ev[0], *ev_pok = &ctx->lane_ev[2], *ev_enc = &ctx->lane_ev[4], *ev_proved = &ctx->lane_ev[6],
+              *ev_verified = &ctx->lane_ev[8];
 
   // ---- host-side index: local bidder slots, auction-major in id order ------------------
   std::vector<u32> auc, boff(1, 0), aoff(A + 1, 0);  // aoff: first local slot of auction a
@@ -206,91 +251,93 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   for (size_t s = 0; s < m; ++s)
     for (u32 k = boff[s]; k < boff[s + 1]; ++k) cid[k] = ids[s];
 
-  unsigned char *d_bits, *d_rndc, *d_crec, *d_cv, *d_junc, *d_prevbit, *d_prevpts, *d_prevx, *d_rnd1, *d_r1, *d_r1v, *d_Y, *d_b,
-      *d_ebit, *d_stmt, *d_sec, *d_bi, *d_bj, *d_rnd2, *d_proof, *d_pv, *d_r2v;
-  u32 *d_boff, *d_act, *d_pauc, *d_pseg, *d_soff, *d_g, *d_gslot;
-  u64 *d_ids, *d_streams, *d_ctr, *d_cid, *d_pid, *d_gid, *d_sstream, *d_sctr;
-  int *d_isinf;
+  // ---- device state --------------------------------------------------------------------------
+  unsigned char *d_bits, *d_rndc, *d_crec, *d_cv, *d_junc, *d_prevbit, *d_prevpts, *d_prevx, *d_r1ok, *d_r2ok;
+  u32 *d_boff;
+  u64 *d_ids, *d_streams, *d_ctr, *d_cid, *d_sstream, *d_sctr;
+  StepBufs SB[2];
+  const size_t nY = sharded ? (size_t)job->n[0] : m;
   auto carve = [&](DevPool &pool) {
-#define PA_ALLOC(var, T, count, zero) var = pool.alloc<T>(count, zero)
-  PA_ALLOC(d_bits, unsigned char, Mb, false);
-  PA_ALLOC(d_boff, u32, m + 1, false);
-  PA_ALLOC(d_ids, u64, m, false);
-  PA_ALLOC(d_streams, u64, m, false);
-  PA_ALLOC(d_ctr, u64, m, true);
-  PA_ALLOC(d_cid, u64, Mb, false);
-  PA_ALLOC(d_rndc, unsigned char, Mb * 224, false);
-  PA_ALLOC(d_crec, unsigned char, Mb * 736, false);
-  PA_ALLOC(d_cv, unsigned char, Mb * 4, false);
-  PA_ALLOC(d_junc, unsigned char, A, true);
-  PA_ALLOC(d_prevbit, unsigned char, m, false);
-  PA_ALLOC(d_prevpts, unsigned char, m * 256, true);
-  PA_ALLOC(d_prevx, unsigned char, m * 32, true);
-  // per-step (sized for all local bidders)
-  PA_ALLOC(d_act, u32, m, false);
-  PA_ALLOC(d_pauc, u32, m, false);
-  PA_ALLOC(d_pseg, u32, m, false);
-  PA_ALLOC(d_pid, u64, m, false);
-  PA_ALLOC(d_soff, u32, A + 1, false);
-  PA_ALLOC(d_isinf, int, A, false);
-  PA_ALLOC(d_rnd1, unsigned char, m * 128, false);
-  PA_ALLOC(d_r1, unsigned char, m * 320, false);
-  PA_ALLOC(d_r1v, unsigned char, m * 3, false);
-  PA_ALLOC(d_Y, unsigned char, (sharded ? (size_t)job->n[0] : m) * 64, false);
-  PA_ALLOC(d_b, unsigned char, m * 64, false);
-  PA_ALLOC(d_ebit, unsigned char, m, false);
-  PA_ALLOC(d_g, u32, 2 * m, false);       // group member positions: stage 1 first, then stage 2
-  PA_ALLOC(d_gslot, u32, 2 * m, false);   // their bidder slots (for the draw counters)
-  PA_ALLOC(d_gid, u64, 2 * m, false);
-  PA_ALLOC(d_stmt, unsigned char, m * 704, false);
-  PA_ALLOC(d_sec, unsigned char, m * 96, false);
-  PA_ALLOC(d_bi, unsigned char, m, false);
-  PA_ALLOC(d_bj, unsigned char, m, false);
-  PA_ALLOC(d_rnd2, unsigned char, m * 352, false);
-  PA_ALLOC(d_proof, unsigned char, m * 1344, false);
-  PA_ALLOC(d_pv, unsigned char, m, false);
-  PA_ALLOC(d_r2v, unsigned char, m, false);
-  PA_ALLOC(d_sstream, u64, Mb, false);
-  PA_ALLOC(d_sctr, u64, Mb, false);
-#undef PA_ALLOC
+    d_bits = pool.alloc<unsigned char>(Mb);
+    d_boff = pool.alloc<u32>(m + 1);
+    d_ids = pool.alloc<u64>(m);
+    d_streams = pool.alloc<u64>(m);
+    d_ctr = pool.alloc<u64>(m, true);
+    d_cid = pool.alloc<u64>(Mb);
+    d_rndc = pool.alloc<unsigned char>(Mb * 224);
+    d_crec = pool.alloc<unsigned char>(Mb * 736);
+    d_cv = pool.alloc<unsigned char>(Mb * 4);
+    d_junc = pool.alloc<unsigned char>(A, true);
+    d_prevbit = pool.alloc<unsigned char>(m);
+    d_prevpts = pool.alloc<unsigned char>(m * 256, true);
+    d_prevx = pool.alloc<unsigned char>(m * 32, true);
+    d_r1ok = pool.alloc<unsigned char>(cmax * m);
+    d_r2ok = pool.alloc<unsigned char>(cmax * m);
+    d_sstream = pool.alloc<u64>(Mb);
+    d_sctr = pool.alloc<u64>(Mb);
+    for (int k = 0; k < 2; ++k) {
+      StepBufs &B = SB[k];
+      B.act = pool.alloc<u32>(m); B.pauc = pool.alloc<u32>(m); B.pseg = pool.alloc<u32>(m); B.soff = pool.alloc<u32>(A + 1);
+      B.g = pool.alloc<u32>(m); B.gslot = pool.alloc<u32>(m);
+      B.pid = pool.alloc<u64>(m); B.gid = pool.alloc<u64>(m);
+      B.rnd1 = pool.alloc<unsigned char>(m * 128); B.r1 = pool.alloc<unsigned char>(m * 320); B.pokv = pool.alloc<unsigned char>(m * 2);
+      B.Y = pool.alloc<unsigned char>(nY * 64); B.b = pool.alloc<unsigned char>(m * 64); B.ebit = pool.alloc<unsigned char>(m);
+      // stage-1 members first, stage-2 members behind them (256-byte aligned)
+      B.stmt = pool.alloc<unsigned char>(m * 704 + 256); B.sec = pool.alloc<unsigned char>(m * 96 + 256);
+      B.bi = pool.alloc<unsigned char>(m + 256); B.bj = pool.alloc<unsigned char>(m + 256);
+      B.rnd2 = pool.alloc<unsigned char>(m * 352 + 256); B.proof = pool.alloc<unsigned char>(m * 1344 + 256);
+      B.pv = pool.alloc<unsigned char>(m + 256);
+      B.isinf = pool.alloc<int>(A);
+    }
   };
   {
     DevPool sizing(ctx, true);
     carve(sizing);
-    int rc0 = ensure(ctx, &ctx->d_pool, &ctx->pool_bytes, sizing.off + 4096);
-    if (rc0) return rc0;
+    if ((rc = ensure(ctx, &ctx->d_pool, &ctx->pool_bytes, sizing.off + 4096))) return rc;
     DevPool real(ctx, false);
     carve(real);
   }
-  int rc;
   if ((rc = up(ctx, d_bits, bits)) || (rc = up(ctx, d_boff, boff)) || (rc = up(ctx, d_ids, ids)) ||
       (rc = up(ctx, d_streams, streams)) || (rc = up(ctx, d_cid, cid)))
     return rc;
   PA_CUDA(ctx, cudaMemsetAsync(d_prevbit, 1, m, ctx->stream));  // prevDecidingBit(1), SEAL/bidder.cpp:23
+  PA_CUDA(ctx, cudaMemsetAsync(d_r1ok, 1, cmax * m, ctx->stream));
+  PA_CUDA(ctx, cudaMemsetAsync(d_r2ok, 1, cmax * m, ctx->stream));
+
+  // pinned staging for the optional section outputs (written asynchronously by the lanes)
+  unsigned char *h_stage = nullptr;
+  size_t off_r1 = 0, off_b = 0, off_pf = 0, stage_bytes = 0;
+  if (want_r1) off_r1 = stage_bytes, stage_bytes += cmax * m * 320;
+  if (want_b) off_b = stage_bytes, stage_bytes += cmax * m * 64;
+  if (want_proof) off_pf = stage_bytes, stage_bytes += cmax * m * 1344;
+  if (stage_bytes) PA_CUDA(ctx, cudaMallocHost((void **)&h_stage, stage_bytes));
+  struct HostFree {
+    unsigned char *p;
+    ~HostFree() { if (p) cudaFreeHost(p); }
+  } host_free{h_stage};
+  // whatever happens, leave no lane running when we return
+  struct LaneDrain {
+    pa_ctx *c;
+    ~LaneDrain() { for (int i = 0; i < 3; ++i) cudaStreamSynchronize(c->lanes[i].stream); cudaStreamSynchronize(c->stream); }
+  } drain{ctx};
 
   std::vector<unsigned char> junction(A, 0), okv(A, 1);
   std::vector<u64> maxbid(A, 0);
+  std::vector<std::vector<u32>> acts(cmax), g1s_pos(cmax), g2s_pos(cmax);  // per step: slot of position p; group members
   // strides of the records the proofs live in; LC2 / LR2: the two Schnorr proofs of a record in one batch
   const pa_lay LC{736, 736, 224, 224, 1, 0, 0, 0, 0}, LC2{736, 736, 224, 224, 2, 96, 64, 32, 32};
   const pa_lay LR2{320, 320, 128, 128, 2, 96, 64, 32, 32};
-  auto d2h = [&](void *h, const void *d, size_t bytes) -> int {
-    if (h && bytes) PA_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    return PA_OK;
-  };
 
   // ================= commit phase ===================================================
   {
-    // 7 draws per bit, sequentially per bidder (thread per bidder walks its c bits)
-    // draws of bidder s land at rndc + 224 * boff[s]: one launch per distinct c would need
-    // compaction; instead draw bit-slot by bit-slot with per-slot (stream, counter = 7 * bit index).
-    // The counter arithmetic is exact unless a draw is rejected (probability 2^-128 per draw);
-    // rejections are handled by the sequential fallback below.
+    // 7 draws per (bidder, bit): slot k of bidder s starts at counter 7 * (k - boff[s]) of the bidder's
+    // stream.  That arithmetic is exact unless a draw is rejected (probability 2^-128 per draw); if the
+    // counters show a rejection, that bidder's draws are regenerated sequentially.
     std::vector<u64> sstream(Mb), sctr(Mb);
     for (size_t s = 0; s < m; ++s)
       for (u32 k = boff[s]; k < boff[s + 1]; ++k) sstream[k] = streams[s], sctr[k] = 7ull * (k - boff[s]);
     if ((rc = up(ctx, d_sstream, sstream)) || (rc = up(ctx, d_sctr, sctr))) return rc;
     PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_sstream, d_sctr, nullptr, 7, d_rndc, (int)Mb)));
-    // every slot must have consumed exactly 7 counters; otherwise redo that bidder sequentially
     std::vector<u64> after(Mb);
     PA_CUDA(ctx, cudaMemcpyAsync(after.data(), d_sctr, Mb * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -298,7 +345,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       bool clean = true;
       for (u32 k = boff[s]; k < boff[s + 1]; ++k) clean &= after[k] == sctr[k] + 7;
       u64 cnt = 7ull * (boff[s + 1] - boff[s]);
-      if (!clean) {  // a rejected draw shifted the stream: regenerate this bidder's draws in order
+      if (!clean) {
         u64 zero = 0;
         PA_CUDA(ctx, cudaMemcpyAsync(d_ctr + s, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
         PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<1, 1, 0, ctx->stream>>>(job->seed, d_streams + s, d_ctr + s, nullptr, (int)cnt, d_rndc + 224 * (size_t)boff[s], 1)));
@@ -321,7 +368,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     }
     std::vector<unsigned char> cv(Mb);
     PA_CUDA(ctx, cudaMemcpyAsync(cv.data(), d_cv + 3 * Mb, Mb, cudaMemcpyDeviceToHost, ctx->stream));
-    if ((rc = d2h(job->out_commit, d_crec, Mb * 736))) return rc;
+    if (job->out_commit) PA_CUDA(ctx, cudaMemcpyAsync(job->out_commit, d_crec, Mb * 736, cudaMemcpyDeviceToHost, ctx->stream));
     PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (job->out_commit_ok) memcpy(job->out_commit_ok, cv.data(), Mb);
     for (size_t s = 0; s < m; ++s)
@@ -329,138 +376,142 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   }
 
   // ================= auction steps =====================================================
+  size_t steps_run = 0;
   for (size_t step = 0; step < cmax; ++step) {
-    // active bidders and their per-auction segments
-    std::vector<u32> act, pauc, pseg, soff(1, 0), g1, g2, g1s, g2s, actauc;
-    std::vector<u64> pid, g1id, g2id;
+    const int par = (int)(step & 1);
+    StepBufs &B = SB[par];
+    // active bidders, their per-auction segments, and the two proof groups
+    std::vector<u32> &act = acts[step], &g1 = g1s_pos[step], &g2 = g2s_pos[step];
+    std::vector<u32> pauc, pseg, soff(1, 0), g, gslot, actauc;
+    std::vector<u64> pid, gid;
     for (size_t a = 0; a < A; ++a) {
       if (job->c[a] <= step) continue;
       for (u32 s = aoff[a]; s < aoff[a + 1]; ++s) {
         u32 p = (u32)act.size();
         act.push_back(s), pauc.push_back((u32)a), pseg.push_back((u32)actauc.size()), pid.push_back(ids[s]);
         (junction[a] ? g2 : g1).push_back(p);
-        (junction[a] ? g2s : g1s).push_back(s);
-        (junction[a] ? g2id : g1id).push_back(ids[s]);
       }
       actauc.push_back((u32)a);
       soff.push_back((u32)act.size());
     }
     const size_t ma = act.size(), na = actauc.size(), n1 = g1.size(), n2 = g2.size();
     if (ma == 0) break;
-    if ((rc = up(ctx, d_act, act)) || (rc = up(ctx, d_pauc, pauc)) || (rc = up(ctx, d_pseg, pseg)) || (rc = up(ctx, d_pid, pid)) ||
-        (rc = up(ctx, d_soff, soff)) || (rc = up(ctx, d_g, g1)) || (rc = up(ctx, d_g + m, g2)) || (rc = up(ctx, d_gslot, g1s)) ||
-        (rc = up(ctx, d_gslot + m, g2s)) || (rc = up(ctx, d_gid, g1id)) || (rc = up(ctx, d_gid + m, g2id)))
+    steps_run = step + 1;
+    for (u32 p : g1) g.push_back(p), gslot.push_back(act[p]), gid.push_back(ids[act[p]]);
+    for (u32 p : g2) g.push_back(p), gslot.push_back(act[p]), gid.push_back(ids[act[p]]);
+    // offsets of the stage-2 group inside the shared per-step arrays
+    const size_t o_stmt = align_up(n1 * 448, 256), o_sec = align_up(n1 * 64, 256), o_b = align_up(n1, 256),
+                 o_rnd = align_up(n1 * 160, 256), o_proof = align_up(n1 * 672, 256);
+
+    // this buffer set was last used two steps ago: its side lanes must have drained
+    if (step >= 2) {
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[par], 0));
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_proved[par], 0));
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_verified[par], 0));
+    }
+    if ((rc = up(ctx, B.act, act)) || (rc = up(ctx, B.pauc, pauc)) || (rc = up(ctx, B.pseg, pseg)) || (rc = up(ctx, B.pid, pid)) ||
+        (rc = up(ctx, B.soff, soff)) || (rc = up(ctx, B.g, g)) || (rc = up(ctx, B.gslot, gslot)) || (rc = up(ctx, B.gid, gid)))
       return rc;
 
-    // ---- round one: x, r, X = g^x, R = g^r, two Schnorr proofs ---------------------
-    PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, d_act, 4, d_rnd1, (int)ma)));
+    // ---- main lane: x, r, X = g^x, R = g^r ------------------------------------------------
+    PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.act, 4, B.rnd1, (int)ma)));
     if ((rc = work_reserve(ctx, 2 * ma))) return rc;
-    PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * ma), PA_BLOCK, 0, ctx->stream>>>(d_rnd1, ctx->d_comb, work_jac(ctx), (int)ma)));
-    if ((rc = normalize_to(ctx, d_r1, 2 * ma, 2, 320))) return rc;
-    // Schnorr proofs of X (x, v_X) and R (r, v_R): 2 per record, one batch
-    if ((rc = prove_dev<PA_POK>(ctx, d_r1, d_rnd1, nullptr, nullptr, d_pid, d_rnd1 + 64, d_r1 + 128, 2 * ma, LR2))) return rc;
-    if (verify) {
-      if ((rc = verify_dev<PA_POK, 1>(ctx, d_r1 + 128, d_r1, d_pid, d_r1v, 2 * ma, LR2))) return rc;
-      PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(d_r1v, nullptr, d_r1v + 2 * ma, (int)ma)));
-    } else {
-      PA_CUDA(ctx, cudaMemsetAsync(d_r1v + 2 * ma, 1, ma, ctx->stream));
+    PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * ma), PA_BLOCK, 0, ctx->stream>>>(B.rnd1, ctx->d_comb, work_jac(ctx), (int)ma)));
+    if ((rc = normalize_to(ctx, B.r1, 2 * ma, 2, 320))) return rc;
+    PA_CUDA(ctx, cudaEventRecord(ev_r1[par], ctx->stream));
+
+    // ---- lane 1: the Schnorr proofs of X (x, v_X) and R (r, v_R) and their verification -------
+    {
+      LaneScope ls(ctx, L_pok);
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[par], 0));
+      if ((rc = prove_dev<PA_POK>(ctx, B.r1, B.rnd1, nullptr, nullptr, B.pid, B.rnd1 + 64, B.r1 + 128, 2 * ma, LR2))) return rc;
+      if (verify) {
+        if ((rc = verify_dev<PA_POK, 1>(ctx, B.r1 + 128, B.r1, B.pid, B.pokv, 2 * ma, LR2))) return rc;
+        PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.pokv, nullptr, d_r1ok + step * m, (int)ma)));
+      }
+      if (want_r1) PA_CUDA(ctx, cudaMemcpyAsync(h_stage + off_r1 + step * m * 320, B.r1, ma * 320, cudaMemcpyDeviceToHost, ctx->stream));
+      PA_CUDA(ctx, cudaEventRecord(ev_pok[par], ctx->stream));
     }
 
-    // ---- Y reconstruction -------------------------------------------------------------
-    const unsigned char *Yloc = d_Y;
+    // ---- main lane: Y reconstruction ----------------------------------------------------------
+    const unsigned char *Yloc = B.Y;
     if (!sharded) {
       if ((rc = work_reserve(ctx, ma))) return rc;
-      PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)na, PA_SCAN_T, 0, ctx->stream>>>(d_r1, 320, d_soff, (int)ma, work_jac(ctx))));
-      if ((rc = normalize_to(ctx, d_Y, ma))) return rc;
+      PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)na, PA_SCAN_T, 0, ctx->stream>>>(B.r1, 320, B.soff, (int)ma, work_jac(ctx))));
+      if ((rc = normalize_to(ctx, B.Y, ma))) return rc;
     } else {
       // all-gather the X_i of every slice, then every rank scans the whole auction
       const size_t nall = job->n[0];
       PA_CUDA(ctx, cudaMemsetAsync(job->d_send, 0, (size_t)job->slice * 64, ctx->stream));
-      PA_CUDA(ctx, cudaMemcpy2DAsync(job->d_send, 64, d_r1, 320, 64, ma, cudaMemcpyDeviceToDevice, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpy2DAsync(job->d_send, 64, B.r1, 320, 64, ma, cudaMemcpyDeviceToDevice, ctx->stream));
       PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       if (job->allgather(job->user, 0) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (X)");
       if ((rc = work_reserve(ctx, nall))) return rc;
       PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<1, PA_SCAN_T, 0, ctx->stream>>>(job->d_recv, 64, nullptr, (int)nall, work_jac(ctx))));
-      if ((rc = normalize_to(ctx, d_Y, nall))) return rc;
-      Yloc = d_Y + 64 * (size_t)job->lo;
+      if ((rc = normalize_to(ctx, B.Y, nall))) return rc;
+      Yloc = B.Y + 64 * (size_t)job->lo;
     }
 
-    // ---- round two: cryptogram b and its OR proof ---------------------------------------
+    // ---- main lane: cryptogram b, statements and draws of the OR proofs --------------------------
     if ((rc = work_reserve(ctx, ma))) return rc;
-    PA_LAUNCH(ctx, PA_K_VAR, (k_seal_encode<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(d_act, d_pauc, d_bits, d_boff, (int)step, d_junc, d_prevbit, d_r1, Yloc, d_rnd1, d_ebit, work_jac(ctx), (int)ma)));
-    if ((rc = normalize_to(ctx, d_b, ma))) return rc;
-    PA_CUDA(ctx, cudaMemsetAsync(d_r2v, 1, ma, ctx->stream));
+    PA_LAUNCH(ctx, PA_K_VAR, (k_seal_encode<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.act, B.pauc, d_bits, d_boff, (int)step, d_junc, d_prevbit, B.r1, Yloc, B.rnd1, B.ebit, work_jac(ctx), (int)ma)));
+    if ((rc = normalize_to(ctx, B.b, ma))) return rc;
     if (n1) {
-      PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(1, d_g, d_act, d_boff, (int)step, d_b, d_r1, Yloc, d_rnd1, d_crec, d_rndc, d_prevpts, d_prevx, d_ebit, d_prevbit, d_stmt, d_sec, d_bi, d_bj, (int)n1)));
-      PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, d_gslot, 5, d_rnd2, (int)n1)));
-      if ((rc = prove_dev<PA_S1>(ctx, d_stmt, d_sec, d_bi, nullptr, d_gid, d_rnd2, d_proof, n1))) return rc;
-      if (verify) {
-        if ((rc = verify_dev<PA_S1, 8>(ctx, d_proof, d_stmt, d_gid, d_pv, n1))) return rc;
-        PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_scatter_u8<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(d_g, d_pv, d_r2v, (int)n1)));
-      }
-      // group-compact proofs go back to the host per group (stage-1 members first)
-      if (job->out_r2_proof) {
-        std::vector<unsigned char> tmp(n1 * 672);
-        PA_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_proof, tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (size_t q = 0; q < n1; ++q)
-          memcpy(job->out_r2_proof + (step * m + act[g1[q]]) * 1344, tmp.data() + 672 * q, 672);
-      }
+      PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(1, B.g, B.act, d_boff, (int)step, B.b, B.r1, Yloc, B.rnd1, d_crec, d_rndc, d_prevpts, d_prevx, B.ebit, d_prevbit, B.stmt, B.sec, B.bi, B.bj, (int)n1)));
+      PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.gslot, 5, B.rnd2, (int)n1)));
     }
     if (n2) {
-      PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(2, d_g + m, d_act, d_boff, (int)step, d_b, d_r1, Yloc, d_rnd1, d_crec, d_rndc, d_prevpts, d_prevx, d_ebit, d_prevbit, d_stmt, d_sec, d_bi, d_bj, (int)n2)));
-      PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, d_gslot + m, 11, d_rnd2, (int)n2)));
-      if ((rc = prove_dev<PA_S2>(ctx, d_stmt, d_sec, d_bi, d_bj, d_gid + m, d_rnd2, d_proof, n2))) return rc;
+      PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(2, B.g + n1, B.act, d_boff, (int)step, B.b, B.r1, Yloc, B.rnd1, d_crec, d_rndc, d_prevpts, d_prevx, B.ebit, d_prevbit, B.stmt + o_stmt, B.sec + o_sec, B.bi + o_b, B.bj + o_b, (int)n2)));
+      PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.gslot + n1, 11, B.rnd2 + o_rnd, (int)n2)));
+    }
+    if (want_b) PA_CUDA(ctx, cudaMemcpyAsync(h_stage + off_b + step * m * 64, B.b, ma * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    PA_CUDA(ctx, cudaEventRecord(ev_enc[par], ctx->stream));
+
+    // ---- lane 2: the OR proofs -----------------------------------------------------------------------
+    {
+      LaneScope ls(ctx, L_prove);
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[par], 0));
+      if (n1 && (rc = prove_dev<PA_S1>(ctx, B.stmt, B.sec, B.bi, nullptr, B.gid, B.rnd2, B.proof, n1))) return rc;
+      if (n2 && (rc = prove_dev<PA_S2>(ctx, B.stmt + o_stmt, B.sec + o_sec, B.bi + o_b, B.bj + o_b, B.gid + n1, B.rnd2 + o_rnd, B.proof + o_proof, n2))) return rc;
+      if (want_proof) {  // group-compact: stage-1 members first, then stage-2 members
+        if (n1) PA_CUDA(ctx, cudaMemcpyAsync(h_stage + off_pf + step * m * 1344, B.proof, n1 * 672, cudaMemcpyDeviceToHost, ctx->stream));
+        if (n2) PA_CUDA(ctx, cudaMemcpyAsync(h_stage + off_pf + step * m * 1344 + o_proof, B.proof + o_proof, n2 * 1344, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      PA_CUDA(ctx, cudaEventRecord(ev_proved[par], ctx->stream));
+    }
+    // ---- lane 3: their verification -----------------------------------------------------------------
+    {
+      LaneScope ls(ctx, L_verify);
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_proved[par], 0));
       if (verify) {
-        if ((rc = verify_dev<PA_S2, 16>(ctx, d_proof, d_stmt, d_gid + m, d_pv, n2))) return rc;
-        PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_scatter_u8<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(d_g + m, d_pv, d_r2v, (int)n2)));
+        if (n1) {
+          if ((rc = verify_dev<PA_S1, 8>(ctx, B.proof, B.stmt, B.gid, B.pv, n1))) return rc;
+          PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_scatter_u8<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(B.g, B.pv, d_r2ok + step * m, (int)n1)));
+        }
+        if (n2) {
+          if ((rc = verify_dev<PA_S2, 16>(ctx, B.proof + o_proof, B.stmt + o_stmt, B.gid + n1, B.pv + o_b, n2))) return rc;
+          PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_scatter_u8<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(B.g + n1, B.pv + o_b, d_r2ok + step * m, (int)n2)));
+        }
       }
-      if (job->out_r2_proof) {
-        std::vector<unsigned char> tmp(n2 * 1344);
-        PA_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_proof, tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (size_t q = 0; q < n2; ++q)
-          memcpy(job->out_r2_proof + (step * m + act[g2[q]]) * 1344, tmp.data() + 1344 * q, 1344);
-      }
+      PA_CUDA(ctx, cudaEventRecord(ev_verified[par], ctx->stream));
     }
 
-    // ---- round three: is the sum of the cryptograms the point at infinity? ------------------
+    // ---- main lane, round three: is the sum of the cryptograms the point at infinity? ------------------
     if (!sharded) {
-      PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<(unsigned)na, PA_SCAN_T, 0, ctx->stream>>>(d_b, 64, d_soff, (int)ma, d_isinf)));
+      PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<(unsigned)na, PA_SCAN_T, 0, ctx->stream>>>(B.b, 64, B.soff, (int)ma, B.isinf)));
     } else {
       PA_CUDA(ctx, cudaMemsetAsync(job->d_send, 0, (size_t)job->slice * 64, ctx->stream));
-      PA_CUDA(ctx, cudaMemcpyAsync(job->d_send, d_b, ma * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpyAsync(job->d_send, B.b, ma * 64, cudaMemcpyDeviceToDevice, ctx->stream));
       PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       if (job->allgather(job->user, 1) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (b)");
-      PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<1, PA_SCAN_T, 0, ctx->stream>>>(job->d_recv, 64, nullptr, (int)job->n[0], d_isinf)));
+      PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<1, PA_SCAN_T, 0, ctx->stream>>>(job->d_recv, 64, nullptr, (int)job->n[0], B.isinf)));
     }
-    PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_update<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(d_act, d_pseg, d_pauc, d_isinf, d_bits, d_boff, (int)step, d_r1, Yloc, d_b, d_rnd1, d_prevpts, d_prevx, d_prevbit, d_junc, (int)ma)));
-
-    // ---- results of the step back to the host ---------------------------------------------------
+    PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_update<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.act, B.pseg, B.pauc, B.isinf, d_bits, d_boff, (int)step, B.r1, Yloc, B.b, B.rnd1, d_prevpts, d_prevx, d_prevbit, d_junc, (int)ma)));
     std::vector<int> isinf(na);
-    std::vector<unsigned char> r1v(ma), r2v(ma), ebit(ma);
-    PA_CUDA(ctx, cudaMemcpyAsync(isinf.data(), d_isinf, na * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PA_CUDA(ctx, cudaMemcpyAsync(r1v.data(), d_r1v + 2 * ma, ma, cudaMemcpyDeviceToHost, ctx->stream));
-    PA_CUDA(ctx, cudaMemcpyAsync(r2v.data(), d_r2v, ma, cudaMemcpyDeviceToHost, ctx->stream));
-    std::vector<unsigned char> r1h, bh;
-    if (job->out_r1) {
-      r1h.resize(ma * 320);
-      PA_CUDA(ctx, cudaMemcpyAsync(r1h.data(), d_r1, ma * 320, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    if (job->out_r2_b) {
-      bh.resize(ma * 64);
-      PA_CUDA(ctx, cudaMemcpyAsync(bh.data(), d_b, ma * 64, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (size_t p = 0; p < ma; ++p) {
-      size_t o = step * m + act[p];
-      okv[pauc[p]] &= r1v[p] & r2v[p];
-      if (job->out_r1) memcpy(job->out_r1 + o * 320, r1h.data() + 320 * p, 320);
-      if (job->out_r2_b) memcpy(job->out_r2_b + o * 64, bh.data() + 64 * p, 64);
-      if (job->out_r1_ok) job->out_r1_ok[o] = r1v[p];
-      if (job->out_r2_ok) job->out_r2_ok[o] = r2v[p];
-      if (job->out_r2_tag) job->out_r2_tag[o] = junction[pauc[p]] ? 2 : 1;
-    }
+    PA_CUDA(ctx, cudaMemcpyAsync(isinf.data(), B.isinf, na * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only per-step host wait: the junction decides the next step's proof kind
+    for (size_t p = 0; p < ma; ++p)
+      if (job->out_r2_tag) job->out_r2_tag[step * m + act[p]] = junction[pauc[p]] ? 2 : 1;
     for (size_t k = 0; k < na; ++k) {
       u32 a = actauc[k];
       bool deciding = !isinf[k];
@@ -469,6 +520,30 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
         junction[a] = 1;                                              // SEAL/bidder.cpp:1400
         maxbid[a] |= (u64)1 << (job->c[a] - step - 1);                 // :1403, 64-bit shift
       }
+    }
+  }
+
+  // ================= drain the lanes, collect verdicts and sections ====================================
+  for (int i = 0; i < 3; ++i) PA_CUDA(ctx, cudaStreamSynchronize(ctx->lanes[i].stream));
+  std::vector<unsigned char> r1ok(cmax * m), r2ok(cmax * m);
+  PA_CUDA(ctx, cudaMemcpyAsync(r1ok.data(), d_r1ok, cmax * m, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyAsync(r2ok.data(), d_r2ok, cmax * m, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t step = 0; step < steps_run; ++step) {
+    const std::vector<u32> &act = acts[step], &g1 = g1s_pos[step], &g2 = g2s_pos[step];
+    const size_t n1 = g1.size(), o_proof = align_up(n1 * 672, 256);
+    for (size_t p = 0; p < act.size(); ++p) {
+      size_t o = step * m + act[p];
+      okv[auc[act[p]]] &= r1ok[step * m + p] & r2ok[step * m + p];
+      if (job->out_r1_ok) job->out_r1_ok[o] = r1ok[step * m + p];
+      if (job->out_r2_ok) job->out_r2_ok[o] = r2ok[step * m + p];
+      if (want_r1) memcpy(job->out_r1 + o * 320, h_stage + off_r1 + (step * m + p) * 320, 320);
+      if (want_b) memcpy(job->out_r2_b + o * 64, h_stage + off_b + (step * m + p) * 64, 64);
+    }
+    if (want_proof) {
+      const unsigned char *base = h_stage + off_pf + step * m * 1344;
+      for (size_t q = 0; q < n1; ++q) memcpy(job->out_r2_proof + (step * m + act[g1[q]]) * 1344, base + 672 * q, 672);
+      for (size_t q = 0; q < g2.size(); ++q) memcpy(job->out_r2_proof + (step * m + act[g2[q]]) * 1344, base + o_proof + 1344 * q, 1344);
     }
   }
   for (size_t a = 0; a < A; ++a) {
