@@ -25,7 +25,9 @@ def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False):
 
     def allgather(which):
         dist.all_gather_into_tensor(recv, send)   # NCCL over NVLink; 64 B per bidder
-        torch.cuda.synchronize()
+        # wait for the collective only: a device-wide synchronize would also wait for the engine's side
+        # lanes (proofs / verification of earlier steps) and serialise them with the exchange
+        torch.cuda.current_stream().synchronize()
         return 0
 
     if hi > lo:
