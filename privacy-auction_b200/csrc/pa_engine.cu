@@ -239,9 +239,9 @@ static u32 *work_prefix(pa_ctx *ctx, size_t n) { return (u32 *)(ctx->d_work + n 
 
 static int normalize_to(pa_ctx *ctx, unsigned char *d_out, size_t n, int nper = 1, size_t stride = 64, int inner = 1,
                         size_t stride_in = 0) {
-  // points per thread: amortise the ~270-multiplication inversion once the
-  // batch is large enough to keep every SM busy anyway
-  size_t per = n / (148 * 1024);
+  // points per thread: share the ~270-multiplication inversion among up to 16 points as soon as
+  // that still leaves >= 16 k threads (one lone warp per SM sub-partition is latency-bound anyway)
+  size_t per = n / 16384;
   if (per < 1) per = 1;
   if (per > 16) per = 16;
   size_t T = (n + per - 1) / per;

@@ -110,7 +110,10 @@ __global__ void k_comb_entries(const u32 *bases, u32 *tab) {  // one thread per 
 }
 
 // ---- scalar multiplication -----------------------------------------------------
-__global__ void __launch_bounds__(PA_BLOCK)
+#ifndef PA_FIX_MINBLOCKS
+#define PA_FIX_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(PA_BLOCK, PA_FIX_MINBLOCKS)
 k_fixed_base(const unsigned char *scalars, const u32 *__restrict__ tab, u32 *jout, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -247,3 +247,13 @@ def test_runner_32_bit_bids(engine):
     bids = [0x80000001, 0xFFFFFFFF, 0x7FFFFFFF, 5]
     res = engine.seal_run(3, [4], [32], bids, verify=True)
     assert res["ok"] == [True] and res["max_bid"] == [0xFFFFFFFF]
+
+
+def test_runner_matches_oracle_n64_c12(engine, oracle):
+    """a mid-size auction (64 bidders x 12 bits, ~67 k scalar mults on the oracle's single core)"""
+    rnd = random.Random(6412)
+    bids = [rnd.randrange(1 << 12) for _ in range(64)]
+    res = engine.seal_run(64012, [64], [12], bids, verify=True, sections=True)
+    got = seal_flow.sections_to_transcripts(64012, [64], [12], bids, res)[0]
+    fl = seal_flow.SealFlow(oracle, 64, 12, 64012, bids)
+    assert got == fl.run() and fl.ok and res["ok"] == [True] and res["max_bid"] == [max(bids)]
