@@ -134,6 +134,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm), "how": self.how}
 
 
+def point_stream_roofline(kstats, n):
+    """HBM roofline of the one point-stream kernel (north_star: HBM GB/s only for table / point-stream
+    kernels): k_normalize reads a 96-B Jacobian triple twice (Z, then X Y Z), writes and re-reads a
+    32-B prefix product and writes the 64-B affine point = 320 B per point."""
+    nz = kstats.get("k_normalize")
+    if not nz:
+        return None
+    ms = nz["total_ms"] / max(nz["launches"], 1)
+    peak, src = 6650.0, "fallback of B200_PROFILING.md"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    achieved = 320.0 * n / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_normalize", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": src, "avg_launch_ms": ms,
+            "note": "not HBM-bound: one 270-multiplication field inversion per 16 points dominates (integer pipe)"}
+
+
 def proof_throughput(eng, torch, n=1 << 15, seed=77):
     """proof-verifies/s and proofs/s per NIZK kind at a batch large enough to fill the GPU
     (n proofs per kind, device-resident, CUDA events on the engine's stream).  Statements are
@@ -452,6 +472,7 @@ def main():
             "roofline_fixed_base": {"bound": "imad", "kernel": "k_fixed_base", "achieved": n * FM_FIXED * IMAD_PER_FM / (fix_ms * 1e-3) / 1e12,
                                     "peak": peak_imad / 1e12, "unit": "TIMAD/s", "frac": n * FM_FIXED * IMAD_PER_FM / (fix_ms * 1e-3) / peak_imad,
                                     "avg_launch_ms": fix_ms},
+            "roofline_point_stream": point_stream_roofline(kstats, n),
             "kernels": {k: {"launches": v["launches"], "avg_ms": v["total_ms"] / max(v["launches"], 1)} for k, v in kstats.items()},
             "int_peak_measured": peak,
             "rates": {"fixed_base_per_s_per_gpu": n / (fix_ms * 1e-3), "var_base_per_s_per_gpu": n / (var_ms * 1e-3)},

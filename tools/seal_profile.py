@@ -18,7 +18,7 @@ if which == "config4":
     bids = [rnd.randrange(1 << 31) for _ in range(1000)]
     ids = None
 else:
-    A = 1024
+    A = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
     r5 = random.Random(5000)
     n = [r5.randint(1, 20) for _ in range(A)]
     c = [r5.randint(1, 32) for _ in range(A)]
