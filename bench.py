@@ -271,7 +271,7 @@ def seal_figures(eng, pa, rank, world, dist, torch):
     out["config4_kernels_ms"] = {k: round(v["total_ms"], 3) for k, v in ks.items()}
 
     # config 5 sample: independent auctions, each rank its own batch
-    A = 1024
+    A = 4096
     r5 = random.Random(5000 + rank)
     n5 = [r5.randint(1, 20) for _ in range(A)]
     c5 = [r5.randint(1, 32) for _ in range(A)]
