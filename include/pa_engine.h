@@ -259,6 +259,25 @@ typedef struct {
 } pa_seal_job;
 int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job);
 
+/* pa_ccs22_run: the same for the CCS22 protocol (CCS22/main.cpp:16-130): every party of a batch of
+ * auctions in lock step, no zero-knowledge proofs (the reference's verification phase is a TODO,
+ * CCS22/main.cpp:132-134).  Party i of auction a draws from PA stream (seed, (auction_id << 32) | i),
+ * the bulletin board's g1, h from (seed, (auction_id << 32) | 0xFFFFFFFF).  Independent auctions only
+ * (partition them over GPUs; no exchange).
+ * m = sum n, Mb = sum n*c, ms = sum (n-1) ("slots": the non-evaluator bidders, auction-major in id order).
+ * Optional host outputs: out_params [A x 128] (g1, h), out_com [m x 64], out_pub [Mb x 64] (party-major),
+ *   out_r1 [cmax x ms x 192] (T2, G, H), out_ots [cmax x ms x 192] (z, C0, C1), out_d [cmax x A]. */
+typedef struct {
+  uint64_t seed;
+  size_t n_auctions;
+  const uint32_t *n, *c, *evaluator; /* [n_auctions] parties, bits, id of the evaluator */
+  const uint64_t *auction_ids;       /* [n_auctions] or NULL */
+  const uint64_t *bids;              /* all parties, auction-major, id order */
+  uint64_t *max_bid;                 /* [m] the maximum each party computed */
+  uint8_t *out_params, *out_com, *out_pub, *out_r1, *out_ots, *out_d;
+} pa_ccs22_job;
+int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job);
+
 /* ---- measurement ----------------------------------------------------------
  * Per-kernel device timing: between pa_profile_begin and pa_profile_end every
  * kernel the context launches is bracketed by CUDA events on the context's

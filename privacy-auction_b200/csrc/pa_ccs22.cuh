@@ -1,0 +1,396 @@
+// Whole-auction runner for the CCS22 protocol: every party of every auction of a batch advances
+// in lock step; the curve work of each phase is one batched launch over all auctions.  This is
+// what the reference's main (CCS22/main.cpp:16-130) does one party and one EC_POINT_mul at a time.
+//
+//   setup      Bidder::setupInner / Evaluator::setupInner     CCS22/bidder.cpp:48-89, evaluator.cpp:22-63
+//   per step   BESEncode -> OTReceive1 -> OTSend -> OTReceive2 -> checkIfEnterDeciderRound
+//                                                             bidder.cpp:118-212, evaluator.cpp:78-156
+//
+// Party i of auction a draws from PA stream (seed, (auction_id << 32) | i), the bulletin board of
+// auction a (g1, h) from (seed, (auction_id << 32) | 0xFFFFFFFF), in the reference's draw order.
+// Layout of a party's secret block (scalars): bidder x[c] r[c] s[c] t[c]; evaluator x[c] r[c]
+// beta[c][n-1] — exactly the array the setup hash runs over (bidder.cpp:74-77, evaluator.cpp:43-50).
+#pragma once
+
+// ---- runner kernels -----------------------------------------------------------------------
+// one thread per party: R, then the per-bit draws, written in hash order
+__global__ void k_ccs22_setup_rng(u64 seed, const u64 *streams, u64 *ctrs, const u32 *soff, const u32 *cs, const u32 *ns,
+                                  const unsigned char *is_eval, unsigned char *sec, unsigned char *R, int m) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m) return;
+  u64 ctr = ctrs[p];
+  sc v;
+  pa_stream_rand_range(v, seed, streams[p], ctr);  // constructor: R                 CCS22/bidder.cpp:21-27
+  st_sc(R + 32 * (size_t)p, v);
+  unsigned char *blk = sec + 32 * (size_t)soff[p];
+  u32 c = cs[p], nb = ns[p] - 1;
+  for (u32 i = 0; i < c; ++i) {
+    if (is_eval[p]) {  // x_i, r_i, beta_{i,0..n-2}                                   evaluator.cpp:38-50
+      pa_stream_rand_range(v, seed, streams[p], ctr);
+      st_sc(blk + 32 * (size_t)i, v);
+      pa_stream_rand_range(v, seed, streams[p], ctr);
+      st_sc(blk + 32 * (size_t)(c + i), v);
+      for (u32 j = 0; j < nb; ++j) {
+        pa_stream_rand_range(v, seed, streams[p], ctr);
+        st_sc(blk + 32 * ((size_t)2 * c + (size_t)i * nb + j), v);
+      }
+    } else {  // x_i, r_i, s_i, t_i                                                    bidder.cpp:63-66
+      for (u32 k = 0; k < 4; ++k) {
+        pa_stream_rand_range(v, seed, streams[p], ctr);
+        st_sc(blk + 32 * ((size_t)k * c + i), v);
+      }
+    }
+  }
+  ctrs[p] = ctr;
+}
+
+// SHA256inSetup over a party's block (variable length per party)
+__global__ void k_ccs22_party_hash(const unsigned char *sec, const u32 *soff, const u32 *scnt, unsigned char *out, int m) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m) return;
+  sha256_state s;
+  sha256_init(s);
+  bool failed = false;
+  const unsigned char *blk = sec + 32 * (size_t)soff[p];
+  for (u32 j = 0; j < scnt[p] && !failed; ++j) {
+    const unsigned char *q = blk + 32 * (size_t)j;
+    int lead = 0;
+    while (lead < 32 && q[lead] == 0) ++lead;
+    if (lead == 32) failed = true;
+    for (int b = lead; b < 32; ++b) sha256_put(s, q[b]);
+  }
+  sc h;
+  sc_set_zero(h);
+  if (!failed) {
+    u32 d[8];
+    sha256_final(s, d);
+    sc_from_digest(h, d);
+  }
+  st_sc(out + 32 * (size_t)p, h);
+}
+
+// dst[i] = src[idx[i]] for items of 32 or 64 bytes
+__global__ void k_gather(unsigned char *dst, const unsigned char *src, const u32 *idx, int item, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 *s = reinterpret_cast<const uint4 *>(src + (size_t)item * idx[i]);
+  uint4 *d = reinterpret_cast<uint4 *>(dst + (size_t)item * i);
+  for (int k = 0; k < item / 16; ++k) d[k] = s[k];
+}
+// dst[dst_idx[i]] = src[src_idx[i]] (src_idx == NULL: i) for 64-byte items
+__global__ void k_scatter64(unsigned char *dst, const u32 *dst_idx, const unsigned char *src, const u32 *src_idx, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 *s = reinterpret_cast<const uint4 *>(src + 64 * (size_t)(src_idx ? src_idx[i] : i));
+  uint4 *d = reinterpret_cast<uint4 *>(dst + 64 * (size_t)dst_idx[i]);
+  d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+// big-endian scalar from a small integer array (bids, 0/1 flags)
+__global__ void k_scalar_from_u64(unsigned char *dst, const u64 *v, const u32 *idx, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 x = v[idx ? idx[i] : i];
+  unsigned char *o = dst + 32 * (size_t)i;
+  for (int k = 0; k < 24; ++k) o[k] = 0;
+  for (int k = 0; k < 8; ++k) o[31 - k] = (unsigned char)(x >> (8 * k));
+}
+
+// BESEncode: d = inRace && bit; B = Y^x (d = 0) or g^r (d = 1)                CCS22/bidder.cpp:118-147
+__global__ void __launch_bounds__(PA_BLOCK)
+k_ccs22_bes(const u32 *act, const unsigned char *bits, const u32 *boff, int step, const unsigned char *inrace,
+            const unsigned char *Y, const unsigned char *sec, const u32 *soff, const u32 *cs, const u32 *__restrict__ comb,
+            u64 *dflag, u32 *jout, int n) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  u32 p = act[q];
+  int d = inrace[p] && bits[boff[p] + step];
+  dflag[p] = (u64)d;
+  const unsigned char *blk = sec + 32 * (size_t)soff[p];
+  jac r;
+  sc k;
+  if (d) {
+    ld_sc(k, blk + 32 * ((size_t)cs[p] + step));  // r_step
+    fixed_base_mul(r, k, comb);
+  } else {
+    jac P;
+    ld_point_jac(P, Y + 64 * (size_t)q);
+    ld_sc(k, blk + 32 * (size_t)step);  // x_step
+    var_base_mul(r, P, k);
+  }
+  st_jac(jout + 24 * (size_t)q, r);
+}
+
+// after OTReceive2: the published d of every active auction                 bidder.cpp:200-212, evaluator.cpp:117-156
+//   newd[a] = d_e ? 1 : !isinf[a];  on newd: every party with d == 0 leaves the race
+__global__ void k_ccs22_update(const u32 *act, const u32 *pseg, const u32 *aeval, const u64 *dflag, const int *isinf,
+                               unsigned char *inrace, int *newd, int n) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  u32 p = act[q], seg = pseg[q];
+  int de = (int)dflag[aeval[seg]];
+  int nd = de ? 1 : (isinf[seg] ? 0 : 1);
+  if (p == aeval[seg]) newd[seg] = nd;
+  if (nd && dflag[p] == 0) inrace[p] = 0;
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+namespace {
+int dev_point_add(pa_ctx *ctx, const unsigned char *p, const unsigned char *q, unsigned char *out, size_t n, int sub) {
+  if (n == 0) return PA_OK;
+  int rc = work_reserve(ctx, n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_POINT_ADD, k_point_add<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(p, q, work_jac(ctx), (int)n, sub));
+  return normalize_to(ctx, out, n);
+}
+int dev_gather(pa_ctx *ctx, unsigned char *dst, const unsigned char *src, const u32 *idx, int item, size_t n) {
+  if (n == 0) return PA_OK;
+  PA_LAUNCH(ctx, PA_K_ENCODE, k_gather<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(dst, src, idx, item, (int)n));
+  return PA_OK;
+}
+}  // namespace
+
+extern "C" int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job) {
+  PA_ARGCHECK(ctx, ctx && job && job->n_auctions >= 1 && job->n && job->c && job->bids && job->evaluator);
+  const size_t A = job->n_auctions;
+  int rc;
+  // ---- host-side index ---------------------------------------------------------------------------
+  std::vector<u32> pauc, boff(1, 0), soff(1, 0), aoff(A + 1, 0), cs, ns, scnt, aeval(A), slot_party, slot_auc, slot_j, sl_off(A + 1, 0);
+  std::vector<u64> streams, bbstreams(A), bids64;
+  std::vector<unsigned char> bits, is_eval;
+  size_t cmax = 0;
+  for (size_t a = 0; a < A; ++a) {
+    u32 n = job->n[a], c = job->c[a], e = job->evaluator[a];
+    PA_ARGCHECK(ctx, n >= 1 && c >= 1 && c <= 64 && e < n);
+    cmax = c > cmax ? c : cmax;
+    u64 aid = job->auction_ids ? job->auction_ids[a] : a;
+    bbstreams[a] = (aid << 32) | 0xFFFFFFFFull;
+    for (u32 i = 0; i < n; ++i) {
+      u32 p = (u32)pauc.size();
+      u64 bid = job->bids[p];
+      pauc.push_back((u32)a);
+      streams.push_back((aid << 32) | i);
+      bids64.push_back(bid);
+      cs.push_back(c), ns.push_back(n);
+      is_eval.push_back(i == e);
+      if (i == e) aeval[a] = p;
+      u32 cnt = i == e ? (n + 1) * c : 4 * c;
+      scnt.push_back(cnt);
+      soff.push_back(soff.back() + cnt);
+      for (u32 k = 0; k < c; ++k) bits.push_back((unsigned char)((bid >> (c - 1 - k)) & 1));
+      boff.push_back((u32)bits.size());
+      if (i != e) slot_party.push_back(p), slot_auc.push_back((u32)a), slot_j.push_back((u32)(slot_party.size() - 1 - sl_off[a]));
+    }
+    aoff[a + 1] = (u32)pauc.size();
+    sl_off[a + 1] = (u32)slot_party.size();
+  }
+  const size_t m = pauc.size(), Mb = bits.size(), NS = soff.back(), ms = slot_party.size();
+
+  // ---- device state ----------------------------------------------------------------------------------
+  unsigned char *d_bits, *d_iseval, *d_sec, *d_R, *d_H, *d_params, *d_pub, *d_com, *d_inrace, *d_tmp32a, *d_tmp32b, *d_tmp32c,
+      *d_p1, *d_p2, *d_p3, *d_p4, *d_p5, *d_p6, *d_Xs, *d_Y, *d_B, *d_T2, *d_G, *d_Hh, *d_z, *d_C0, *d_C1, *d_sum;
+  u32 *d_soff, *d_scnt, *d_cs, *d_ns, *d_boff, *d_idx[10], *d_act, *d_pseg, *d_aeval, *d_segoff;
+  u64 *d_streams, *d_ctr, *d_bbstreams, *d_bbctr, *d_bids, *d_dflag;
+  int *d_isinf, *d_newd;
+  const size_t mx = m > ms ? m : ms, SUM = ms + A;
+  auto carve = [&](DevPool &pool) {
+    d_bits = pool.alloc<unsigned char>(Mb); d_iseval = pool.alloc<unsigned char>(m);
+    d_sec = pool.alloc<unsigned char>(NS * 32); d_R = pool.alloc<unsigned char>(m * 32); d_H = pool.alloc<unsigned char>(m * 32);
+    d_params = pool.alloc<unsigned char>(A * 128); d_pub = pool.alloc<unsigned char>(Mb * 64); d_com = pool.alloc<unsigned char>(m * 64);
+    d_inrace = pool.alloc<unsigned char>(m);
+    d_tmp32a = pool.alloc<unsigned char>((Mb > mx ? Mb : mx) * 32); d_tmp32b = pool.alloc<unsigned char>(mx * 32); d_tmp32c = pool.alloc<unsigned char>(mx * 32);
+    d_p1 = pool.alloc<unsigned char>(mx * 64); d_p2 = pool.alloc<unsigned char>(mx * 64); d_p3 = pool.alloc<unsigned char>(mx * 64);
+    d_p4 = pool.alloc<unsigned char>(mx * 64); d_p5 = pool.alloc<unsigned char>(mx * 64); d_p6 = pool.alloc<unsigned char>(mx * 64);
+    d_Xs = pool.alloc<unsigned char>(m * 64); d_Y = pool.alloc<unsigned char>(m * 64); d_B = pool.alloc<unsigned char>(m * 64);
+    d_T2 = pool.alloc<unsigned char>(ms * 64); d_G = pool.alloc<unsigned char>(ms * 64); d_Hh = pool.alloc<unsigned char>(ms * 64);
+    d_z = pool.alloc<unsigned char>(ms * 64); d_C0 = pool.alloc<unsigned char>(ms * 64); d_C1 = pool.alloc<unsigned char>(ms * 64);
+    d_sum = pool.alloc<unsigned char>(SUM * 64);
+    d_soff = pool.alloc<u32>(m + 1); d_scnt = pool.alloc<u32>(m); d_cs = pool.alloc<u32>(m); d_ns = pool.alloc<u32>(m); d_boff = pool.alloc<u32>(m + 1);
+    for (int k = 0; k < 10; ++k) d_idx[k] = pool.alloc<u32>(SUM > Mb ? SUM : Mb);
+    d_act = pool.alloc<u32>(m); d_pseg = pool.alloc<u32>(m); d_aeval = pool.alloc<u32>(A); d_segoff = pool.alloc<u32>(A + 1);
+    d_streams = pool.alloc<u64>(m); d_ctr = pool.alloc<u64>(m, true); d_bbstreams = pool.alloc<u64>(A); d_bbctr = pool.alloc<u64>(A, true);
+    d_bids = pool.alloc<u64>(m); d_dflag = pool.alloc<u64>(m, true);
+    d_isinf = pool.alloc<int>(A); d_newd = pool.alloc<int>(A);
+  };
+  {
+    DevPool sizing(ctx, true);
+    carve(sizing);
+    if ((rc = ensure(ctx, &ctx->d_pool, &ctx->pool_bytes, sizing.off + 4096))) return rc;
+    DevPool real(ctx, false);
+    carve(real);
+  }
+  if ((rc = up(ctx, d_bits, bits)) || (rc = up(ctx, d_iseval, is_eval)) || (rc = up(ctx, d_soff, soff)) || (rc = up(ctx, d_scnt, scnt)) ||
+      (rc = up(ctx, d_cs, cs)) || (rc = up(ctx, d_ns, ns)) || (rc = up(ctx, d_boff, boff)) || (rc = up(ctx, d_streams, streams)) ||
+      (rc = up(ctx, d_bbstreams, bbstreams)) || (rc = up(ctx, d_bids, bids64)))
+    return rc;
+  PA_CUDA(ctx, cudaMemsetAsync(d_inrace, 1, m, ctx->stream));
+  auto upidx = [&](int k, const std::vector<u32> &v) { return up(ctx, d_idx[k], v); };
+  auto d2h = [&](void *h, const void *d, size_t bytes) -> int {
+    if (h && bytes) PA_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return PA_OK;
+  };
+
+  // ================= setup =====================================================================
+  // public parameters g1 = g^rand256, h = g^rand256                          CCS22/bulletinBoard.cpp:28-51
+  PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(A), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_bbstreams, d_bbctr, nullptr, 2, d_tmp32a, (int)A, 1)));
+  if ((rc = pa_fixed_base_mul_dev(ctx, d_tmp32a, d_params, 2 * A))) return rc;
+  // every party: R, per-bit secrets, X_i = g^x_i, H, Com = g^bid g1^H + h^R      bidder.cpp:48-89, evaluator.cpp:22-63
+  PA_LAUNCH(ctx, PA_K_RNG, (k_ccs22_setup_rng<<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, d_soff, d_cs, d_ns, d_iseval, d_sec, d_R, (int)m)));
+  {
+    std::vector<u32> ix(Mb), ig1(m), ih(m);
+    for (size_t p = 0; p < m; ++p) {
+      for (u32 k = boff[p]; k < boff[p + 1]; ++k) ix[k] = soff[p] + (k - boff[p]);  // x_i of the party's block
+      ig1[p] = 2 * pauc[p], ih[p] = 2 * pauc[p] + 1;
+    }
+    if ((rc = upidx(0, ix)) || (rc = upidx(1, ig1)) || (rc = upidx(2, ih))) return rc;
+    if ((rc = dev_gather(ctx, d_tmp32a, d_sec, d_idx[0], 32, Mb))) return rc;
+    if ((rc = pa_fixed_base_mul_dev(ctx, d_tmp32a, d_pub, Mb))) return rc;
+    PA_LAUNCH(ctx, PA_K_CHALLENGE, (k_ccs22_party_hash<<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(d_sec, d_soff, d_scnt, d_H, (int)m)));
+    PA_LAUNCH(ctx, PA_K_ENCODE, (k_scalar_from_u64<<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(d_tmp32b, d_bids, nullptr, (int)m)));
+    if ((rc = dev_gather(ctx, d_p1, d_params, d_idx[1], 64, m)) || (rc = dev_gather(ctx, d_p2, d_params, d_idx[2], 64, m))) return rc;
+    if ((rc = pa_double_mul_dev(ctx, d_tmp32b, d_p1, d_H, d_p3, m))) return rc;   // g^bid * g1^H
+    if ((rc = pa_var_base_mul_dev(ctx, d_p2, d_R, d_p4, m))) return rc;           // h^R
+    if ((rc = dev_point_add(ctx, d_p3, d_p4, d_com, m, 0))) return rc;
+  }
+  if ((rc = d2h(job->out_params, d_params, A * 128)) || (rc = d2h(job->out_com, d_com, m * 64)) || (rc = d2h(job->out_pub, d_pub, Mb * 64))) return rc;
+  std::vector<u64> hctr(m);  // stream counters after setup (they include any rejected range draws)
+  PA_CUDA(ctx, cudaMemcpyAsync(hctr.data(), d_ctr, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+  std::vector<u64> maxbid(m, 0);
+  // ================= computation phase ============================================================
+  for (size_t step = 0; step < cmax; ++step) {
+    std::vector<u32> act, pseg, segoff(1, 0), aev, actauc, sact, sseg, sumoff(1, 0);
+    for (size_t a = 0; a < A; ++a) {
+      if (job->c[a] <= step) continue;
+      for (u32 p = aoff[a]; p < aoff[a + 1]; ++p) act.push_back(p), pseg.push_back((u32)actauc.size());
+      for (u32 q = sl_off[a]; q < sl_off[a + 1]; ++q) sact.push_back(q), sseg.push_back((u32)actauc.size());
+      aev.push_back(aeval[a]);
+      actauc.push_back((u32)a);
+      segoff.push_back((u32)act.size());
+      sumoff.push_back((u32)(sact.size() + actauc.size()));
+    }
+    const size_t ma = act.size(), na = actauc.size(), sa = sact.size();
+    if (ma == 0) break;
+    // position of every active party inside the active list (for B of a slot / of an evaluator)
+    std::vector<u32> pos_of(m, 0);
+    for (size_t q = 0; q < ma; ++q) pos_of[act[q]] = (u32)q;
+    if ((rc = up(ctx, d_act, act)) || (rc = up(ctx, d_pseg, pseg)) || (rc = up(ctx, d_segoff, segoff)) || (rc = up(ctx, d_aeval, aev))) return rc;
+
+    // ---- BESEncode for every party ------------------------------------------------------------
+    {
+      std::vector<u32> ix(ma);
+      for (size_t q = 0; q < ma; ++q) ix[q] = boff[act[q]] + (u32)step;  // public key of this step
+      if ((rc = upidx(0, ix))) return rc;
+      if ((rc = dev_gather(ctx, d_Xs, d_pub, d_idx[0], 64, ma))) return rc;
+      if ((rc = work_reserve(ctx, ma))) return rc;
+      PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)na, PA_SCAN_T, 0, ctx->stream>>>(d_Xs, 64, d_segoff, (int)ma, work_jac(ctx))));
+      if ((rc = normalize_to(ctx, d_Y, ma))) return rc;
+      PA_LAUNCH(ctx, PA_K_VAR, (k_ccs22_bes<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(d_act, d_bits, d_boff, (int)step, d_inrace, d_Y, d_sec, d_soff, d_cs, ctx->d_comb, d_dflag, work_jac(ctx), (int)ma)));
+      if ((rc = normalize_to(ctx, d_B, ma))) return rc;
+    }
+    if (sa) {
+      // per slot (= one non-evaluator bidder of an active auction): index arrays
+      std::vector<u32> i_beta(sa), i_s(sa), i_t(sa), i_g1(sa), i_h(sa), i_alpha(sa), i_B(sa), i_bidder(sa), i_eval(sa);
+      for (size_t k = 0; k < sa; ++k) {
+        u32 q = sact[k], p = slot_party[q], a = slot_auc[q], e = aeval[a], c = job->c[a], nb = job->n[a] - 1;
+        i_beta[k] = soff[e] + 2 * c + (u32)step * nb + slot_j[q];
+        i_s[k] = soff[p] + 2 * c + (u32)step;
+        i_t[k] = soff[p] + 3 * c + (u32)step;
+        i_g1[k] = 2 * a, i_h[k] = 2 * a + 1;
+        i_alpha[k] = e;  // d flag of the evaluator
+        i_B[k] = pos_of[p];
+        i_bidder[k] = p, i_eval[k] = e;
+      }
+      if ((rc = upidx(0, i_beta)) || (rc = upidx(1, i_s)) || (rc = upidx(2, i_t)) || (rc = upidx(3, i_g1)) || (rc = upidx(4, i_h)) ||
+          (rc = upidx(5, i_alpha)) || (rc = upidx(6, i_B)) || (rc = upidx(7, i_bidder)) || (rc = upidx(8, i_eval)))
+        return rc;
+      // ---- OTReceive1: k <- rand256 (evaluator's stream, one per slot, in slot order), T2 = g^k,
+      //      G = g^beta * g1^alpha, H = T2^alpha + h^beta                               evaluator.cpp:91-111
+      // rand256 draws are never rejected, so the stream counters are tracked on the host: slot j of
+      // evaluator e draws at counter ctr[e] + j; then every bidder draws once (M1 of OTSend)
+      {
+        std::vector<u64> sstream(sa), sctr(sa), bstream(sa), bctr(sa);
+        for (size_t k = 0; k < sa; ++k) {
+          u32 q = sact[k], e = aeval[slot_auc[q]];
+          sstream[k] = streams[e], sctr[k] = hctr[e] + slot_j[q];
+        }
+        for (size_t k = 0; k < na; ++k) hctr[aev[k]] += job->n[actauc[k]] - 1;
+        for (size_t k = 0; k < sa; ++k) {
+          u32 p = slot_party[sact[k]];
+          bstream[k] = streams[p], bctr[k] = hctr[p]++;
+        }
+        u64 *d_s64 = (u64 *)d_p6, *d_c64 = d_s64 + sa;  // scratch
+        PA_CUDA(ctx, cudaMemcpyAsync(d_s64, sstream.data(), sa * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PA_CUDA(ctx, cudaMemcpyAsync(d_c64, sctr.data(), sa * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(sa), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_s64, d_c64, nullptr, 1, d_tmp32a, (int)sa, 1)));
+        PA_CUDA(ctx, cudaMemcpyAsync(d_s64, bstream.data(), sa * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PA_CUDA(ctx, cudaMemcpyAsync(d_c64, bctr.data(), sa * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(sa), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_s64, d_c64, nullptr, 1, d_tmp32c, (int)sa, 1)));
+      }
+      if ((rc = pa_fixed_base_mul_dev(ctx, d_tmp32a, d_T2, sa))) return rc;                       // T2 = g^k
+      if ((rc = dev_gather(ctx, d_tmp32a, d_sec, d_idx[0], 32, sa))) return rc;                   // beta
+      PA_LAUNCH(ctx, PA_K_ENCODE, (k_scalar_from_u64<<<grid_for(sa), PA_BLOCK, 0, ctx->stream>>>(d_tmp32b, d_dflag, d_idx[5], (int)sa)));  // alpha = d_e
+      if ((rc = dev_gather(ctx, d_p1, d_params, d_idx[3], 64, sa)) || (rc = dev_gather(ctx, d_p2, d_params, d_idx[4], 64, sa))) return rc;  // g1, h
+      if ((rc = pa_double_mul_dev(ctx, d_tmp32a, d_p1, d_tmp32b, d_G, sa))) return rc;            // G = g^beta g1^alpha
+      if ((rc = pa_lincomb2_dev(ctx, d_T2, d_tmp32b, d_p2, d_tmp32a, d_Hh, sa))) return rc;       // H = T2^alpha + h^beta
+      // ---- OTSend: M1 = g^rand256, z = g^s h^t, C0 = G^s + H^t + B, C1 = (G - g1)^s + (H - T2)^t + M1   bidder.cpp:155-198
+      if ((rc = pa_fixed_base_mul_dev(ctx, d_tmp32c, d_p3, sa))) return rc;                       // M1
+      if ((rc = dev_gather(ctx, d_tmp32b, d_sec, d_idx[1], 32, sa)) || (rc = dev_gather(ctx, d_tmp32c, d_sec, d_idx[2], 32, sa))) return rc;  // s, t
+      if ((rc = pa_double_mul_dev(ctx, d_tmp32b, d_p2, d_tmp32c, d_z, sa))) return rc;            // z
+      if ((rc = pa_lincomb2_dev(ctx, d_G, d_tmp32b, d_Hh, d_tmp32c, d_p4, sa))) return rc;
+      if ((rc = dev_gather(ctx, d_p5, d_B, d_idx[6], 64, sa))) return rc;                         // B of the bidder
+      if ((rc = dev_point_add(ctx, d_p4, d_p5, d_C0, sa, 0))) return rc;
+      if ((rc = dev_point_add(ctx, d_G, d_p1, d_p4, sa, 1)) || (rc = dev_point_add(ctx, d_Hh, d_T2, d_p5, sa, 1))) return rc;
+      if ((rc = pa_lincomb2_dev(ctx, d_p4, d_tmp32b, d_p5, d_tmp32c, d_p6, sa))) return rc;
+      if ((rc = dev_point_add(ctx, d_p6, d_p3, d_C1, sa, 0))) return rc;
+      // ---- OTReceive2: sum_j (C0_j - beta_j z_j) + B_e                                evaluator.cpp:131-143
+      if ((rc = pa_var_base_mul_dev(ctx, d_z, d_tmp32a, d_p4, sa))) return rc;                    // beta z
+      if ((rc = dev_point_add(ctx, d_C0, d_p4, d_p5, sa, 1))) return rc;                          // M0
+    }
+    {
+      // per active auction: its M0's (slot order) followed by the evaluator's own B, then one segmented sum
+      std::vector<u32> where_m0(sa), where_b(na), src_b(na);
+      size_t k = 0, w = 0;
+      for (size_t sgi = 0; sgi < na; ++sgi) {
+        while (k < sa && sseg[k] == sgi) where_m0[k++] = (u32)w++;
+        src_b[sgi] = pos_of[aev[sgi]];
+        where_b[sgi] = (u32)w++;
+      }
+      if ((rc = upidx(0, where_m0)) || (rc = upidx(1, where_b)) || (rc = upidx(2, src_b)) || (rc = up(ctx, d_segoff, sumoff))) return rc;
+      if (sa) PA_LAUNCH(ctx, PA_K_ENCODE, (k_scatter64<<<grid_for(sa), PA_BLOCK, 0, ctx->stream>>>(d_sum, d_idx[0], d_p5, nullptr, (int)sa)));
+      PA_LAUNCH(ctx, PA_K_ENCODE, (k_scatter64<<<grid_for(na), PA_BLOCK, 0, ctx->stream>>>(d_sum, d_idx[1], d_B, d_idx[2], (int)na)));
+      PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<(unsigned)na, PA_SCAN_T, 0, ctx->stream>>>(d_sum, 64, d_segoff, (int)(sa + na), d_isinf)));
+      PA_LAUNCH(ctx, PA_K_VERDICT, (k_ccs22_update<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(d_act, d_pseg, d_aeval, d_dflag, d_isinf, d_inrace, d_newd, (int)ma)));
+    }
+    // ---- results of the step -----------------------------------------------------------------------
+    std::vector<int> newd(na);
+    PA_CUDA(ctx, cudaMemcpyAsync(newd.data(), d_newd, na * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned char> h_r1, h_ots;
+    if (job->out_r1 && sa) {
+      h_r1.resize(sa * 192);
+      PA_CUDA(ctx, cudaMemcpy2DAsync(h_r1.data(), 192, d_T2, 64, 64, sa, cudaMemcpyDeviceToHost, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpy2DAsync(h_r1.data() + 64, 192, d_G, 64, 64, sa, cudaMemcpyDeviceToHost, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpy2DAsync(h_r1.data() + 128, 192, d_Hh, 64, 64, sa, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (job->out_ots && sa) {
+      h_ots.resize(sa * 192);
+      PA_CUDA(ctx, cudaMemcpy2DAsync(h_ots.data(), 192, d_z, 64, 64, sa, cudaMemcpyDeviceToHost, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpy2DAsync(h_ots.data() + 64, 192, d_C0, 64, 64, sa, cudaMemcpyDeviceToHost, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpy2DAsync(h_ots.data() + 128, 192, d_C1, 64, 64, sa, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < sa; ++k) {
+      if (job->out_r1) memcpy(job->out_r1 + (step * ms + sact[k]) * 192, h_r1.data() + 192 * k, 192);
+      if (job->out_ots) memcpy(job->out_ots + (step * ms + sact[k]) * 192, h_ots.data() + 192 * k, 192);
+    }
+    for (size_t s = 0; s < na; ++s) {
+      u32 a = actauc[s];
+      if (job->out_d) job->out_d[step * A + a] = (uint8_t)newd[s];
+      if (newd[s])
+        for (u32 p = aoff[a]; p < aoff[a + 1]; ++p) maxbid[p] |= (u64)1 << (job->c[a] - step - 1);  // bidder.cpp:210, evaluator.cpp:122, 147
+    }
+  }
+  for (size_t p = 0; p < m; ++p)
+    if (job->max_bid) job->max_bid[p] = maxbid[p];
+  return PA_OK;
+}

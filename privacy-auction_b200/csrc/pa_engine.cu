@@ -769,3 +769,4 @@ int pa_rng_fill(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *c
 }  // extern "C"
 
 #include "pa_seal.cuh"
+#include "pa_ccs22.cuh"

@@ -73,6 +73,7 @@ SIGNATURES = {
     "pa_rng_fill": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_rng_fill_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_seal_run": (ctypes.c_int, [_ctx, _vp]),
+    "pa_ccs22_run": (ctypes.c_int, [_ctx, _vp]),
     "pa_rng_fill256": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_rng_fill256_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_ccs22_setup_hash": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _sz]),
@@ -100,6 +101,16 @@ class SealJob(ctypes.Structure):
         ("out_commit", ctypes.c_void_p), ("out_commit_ok", ctypes.c_void_p), ("out_r1", ctypes.c_void_p),
         ("out_r1_ok", ctypes.c_void_p), ("out_r2_tag", ctypes.c_void_p), ("out_r2_b", ctypes.c_void_p),
         ("out_r2_proof", ctypes.c_void_p), ("out_r2_ok", ctypes.c_void_p), ("out_r3", ctypes.c_void_p),
+    ]
+
+
+class Ccs22Job(ctypes.Structure):
+    """pa_ccs22_job of include/pa_engine.h"""
+    _fields_ = [
+        ("seed", ctypes.c_uint64), ("n_auctions", ctypes.c_size_t), ("n", ctypes.c_void_p), ("c", ctypes.c_void_p),
+        ("evaluator", ctypes.c_void_p), ("auction_ids", ctypes.c_void_p), ("bids", ctypes.c_void_p), ("max_bid", ctypes.c_void_p),
+        ("out_params", ctypes.c_void_p), ("out_com", ctypes.c_void_p), ("out_pub", ctypes.c_void_p), ("out_r1", ctypes.c_void_p),
+        ("out_ots", ctypes.c_void_p), ("out_d", ctypes.c_void_p),
     ]
 
 
@@ -396,6 +407,38 @@ class Engine:
                 out[name] = buf
         self._check(self.lib.pa_seal_run(self.ctx, ctypes.byref(job)))
         res = {"max_bid": list(max_bid), "ok": [bool(v) for v in ok]}
+        for name, buf in out.items():
+            res[name[4:]] = bytes(buf)
+        return res
+
+    def ccs22_run(self, seed, n, c, evaluator, bids, sections=False, auction_ids=None):
+        """pa_ccs22_run: whole CCS22 auctions, device resident.  Returns dict(max_bid[, sections...])."""
+        A, m = len(n), len(bids)
+        arr = lambda T, v: (T * max(len(v), 1))(*v)
+        n_a, c_a, e_a, b_a = arr(ctypes.c_uint32, n), arr(ctypes.c_uint32, c), arr(ctypes.c_uint32, evaluator), arr(ctypes.c_uint64, bids)
+        mb = (ctypes.c_uint64 * max(m, 1))()
+        job = Ccs22Job()
+        job.seed, job.n_auctions = seed, A
+        job.n, job.c, job.evaluator, job.bids = map(ctypes.addressof, (n_a, c_a, e_a, b_a))
+        job.max_bid = ctypes.addressof(mb)
+        keep = [n_a, c_a, e_a, b_a, mb]
+        if auction_ids is not None:
+            aid = arr(ctypes.c_uint64, auction_ids)
+            job.auction_ids = ctypes.addressof(aid)
+            keep.append(aid)
+        out = {}
+        if sections:
+            cmax = max(c)
+            Mb = sum(n[a] * c[a] for a in range(A))
+            ms = sum(n[a] - 1 for a in range(A))
+            sizes = {"out_params": A * 128, "out_com": m * 64, "out_pub": Mb * 64, "out_r1": cmax * ms * 192,
+                     "out_ots": cmax * ms * 192, "out_d": cmax * A}
+            for name, sz in sizes.items():
+                buf = (ctypes.c_uint8 * max(sz, 1))()
+                setattr(job, name, ctypes.addressof(buf))
+                out[name] = buf
+        self._check(self.lib.pa_ccs22_run(self.ctx, ctypes.byref(job)))
+        res = {"max_bid": list(mb)[:m]}
         for name, buf in out.items():
             res[name[4:]] = bytes(buf)
         return res

@@ -18,10 +18,10 @@ def b32(x):
 
 
 class Ccs22Flow:
-    def __init__(self, backend, n, c, seed, evaluator_id, bids):
+    def __init__(self, backend, n, c, seed, evaluator_id, bids, auction=0):
         self.be, self.n, self.c, self.seed, self.e, self.bids = backend, n, c, seed, evaluator_id, list(bids)
-        self.st = [E.PaStream(seed, i) for i in range(n)]
-        self.bb = E.PaStream(seed, 0xFFFFFFFF)
+        self.st = [E.PaStream(seed, (auction << 32) | i) for i in range(n)]
+        self.bb = E.PaStream(seed, (auction << 32) | 0xFFFFFFFF)
         self.bits = [[(bid >> (c - 1 - i)) & 1 for i in range(c)] for bid in bids]
         self.in_race = [True] * n
         self.max_bid = [0] * n
@@ -124,3 +124,31 @@ class Ccs22Flow:
         for i in range(n):
             out += struct.pack("<Q", self.max_bid[i])
         return bytes(out)
+
+
+def sections_to_transcripts(seed, n, c, evaluator, bids, res):
+    """PACCS22T transcript of every auction from the section arrays pa_ccs22_run returns."""
+    A = len(n)
+    ms = sum(x - 1 for x in n)
+    outs, p0, b0, s0 = [], 0, 0, 0
+    for a in range(A):
+        na, ca = n[a], c[a]
+        out = bytearray(b"PACCS22T" + struct.pack("<QQQQ", na, ca, seed, evaluator[a]))
+        for i in range(na):
+            out += struct.pack("<Q", bids[p0 + i])
+        out += res["params"][128 * a:128 * (a + 1)]
+        for i in range(na):
+            out += res["com"][64 * (p0 + i):64 * (p0 + i + 1)]
+            out += res["pub"][64 * (b0 + i * ca):64 * (b0 + (i + 1) * ca)]
+        for step in range(ca):
+            base = step * ms + s0
+            out += res["r1"][192 * base:192 * (base + na - 1)]
+            out += res["ots"][192 * base:192 * (base + na - 1)]
+            out.append(res["d"][step * A + a])
+        for i in range(na):
+            out += struct.pack("<Q", res["max_bid"][p0 + i])
+        outs.append(bytes(out))
+        p0 += na
+        b0 += na * ca
+        s0 += na - 1
+    return outs

@@ -62,3 +62,41 @@ def test_engine_setup_hash_parity(engine, oracle):
         sc = bytearray(b"".join(rnd.getrandbits(rnd.choice([256, 250, 200, 64, 8])).to_bytes(32, "big") for _ in range(9 * k)))
         sc[32 * (3 * k + 1):32 * (3 * k + 2)] = bytes(32)     # item 3 has a zero scalar
         assert engine.ccs22_setup_hash(bytes(sc), k) == oracle.ccs22_setup_hash(bytes(sc), k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_ccs22_runner_reproduces_reference(engine, path):
+    gold = open(path, "rb").read()
+    n, c, seed, ev, bids = _hdr(gold)
+    res = engine.ccs22_run(seed, [n], [c], [ev], bids, sections=True)
+    assert ccs22_flow.sections_to_transcripts(seed, [n], [c], [ev], bids, res)[0] == gold
+    assert res["max_bid"] == [max(bids)] * n
+
+
+@pytest.mark.gpu
+def test_ccs22_runner_ragged_batch_matches_oracle(engine, oracle):
+    rnd = random.Random(909)
+    A = 8
+    n = [rnd.randint(1, 7) for _ in range(A)]
+    c = [rnd.randint(1, 9) for _ in range(A)]
+    n[0], c[0] = 1, 2
+    ev = [rnd.randrange(x) for x in n]
+    per = [[rnd.randrange(1 << c[a]) for _ in range(n[a])] for a in range(A)]
+    per[1] = [0] * n[1]
+    bids = [b for row in per for b in row]
+    ids = [500 + a for a in range(A)]
+    res = engine.ccs22_run(31, n, c, ev, bids, sections=True, auction_ids=ids)
+    got = ccs22_flow.sections_to_transcripts(31, n, c, ev, bids, res)
+    for a in range(A):
+        fl = ccs22_flow.Ccs22Flow(oracle, n[a], c[a], 31, ev[a], per[a], auction=ids[a])
+        assert got[a] == fl.run(), f"auction {a} (n={n[a]}, c={c[a]}, evaluator={ev[a]})"
+
+
+@pytest.mark.gpu
+def test_ccs22_runner_config2_digest(engine):
+    import hashlib, json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_config_digests.json")))["ccs22_20_32"]
+    res = engine.ccs22_run(g["seed"], [g["n"]], [g["c"]], [g["evaluator"]], g["bids"], sections=True)
+    out = ccs22_flow.sections_to_transcripts(g["seed"], [g["n"]], [g["c"]], [g["evaluator"]], g["bids"], res)[0]
+    assert hashlib.sha256(out).hexdigest() == g["sha256"]
