@@ -100,6 +100,12 @@ int pa_lincomb2_dev(pa_ctx *ctx, const uint8_t *d_p, const uint8_t *d_a, const u
  * SEAL/bidder.cpp:130, 178-180 */
 int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, int sub);
 
+/* ok[i] = 1 if points[i] is the point at infinity or a valid curve point (both coordinates < p and
+ * y^2 = x^3 + 7): what EC_POINT_set_affine_coordinates checks when a point enters libcrypto.  The
+ * other entry points do NOT validate their inputs (the reference only ever feeds them points it
+ * computed itself); call this on anything received from outside. */
+int pa_point_on_curve(pa_ctx *ctx, const uint8_t *points, size_t n, uint8_t *ok);
+
 /* EC_POINT_point2oct, SEAL/hash.cpp:27-29, SEAL/bulletinBoard.cpp:277.
  * compressed == 0: 04 || X || Y (65 bytes); compressed != 0: 02/03 || X (33 bytes);
  * infinity: the single byte 00.  Each output slot is `stride` bytes (>= 65 or 33),

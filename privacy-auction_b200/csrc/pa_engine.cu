@@ -98,12 +98,6 @@ static std::string g_create_err;
     }                                                                                           \
   } while (0)
 
-#define PA_LAUNCH_CHECK(ctx)       \
-  do {                             \
-    (ctx)->launches++;             \
-    PA_CUDA(ctx, cudaGetLastError()); \
-  } while (0)
-
 static int pa_fail(pa_ctx *ctx, int code, const char *msg) {
   if (ctx) ctx->err = msg;
   return code;
@@ -418,6 +412,20 @@ int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, 
   PA_LAUNCH(ctx, PA_K_POINT_ADD, k_point_add<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_p, d_q, work_jac(ctx), (int)n, sub));
   if ((rc = normalize_to(ctx, d_o, n))) return rc;
   PA_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+int pa_point_on_curve(pa_ctx *ctx, const uint8_t *points, size_t n, uint8_t *ok) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (points && ok)) && n < (1u << 30));
+  if (n == 0) return PA_OK;
+  int rc = stage_reserve(ctx, n * 65 + 1024);
+  if (rc) return rc;
+  Stage s(ctx);
+  unsigned char *d_p = s.take(n * 64), *d_o = s.take(n);
+  PA_CUDA(ctx, cudaMemcpyAsync(d_p, points, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  PA_LAUNCH(ctx, PA_K_ENCODE, k_on_curve<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_p, (int)n, d_o));
+  PA_CUDA(ctx, cudaMemcpyAsync(ok, d_o, n, cudaMemcpyDeviceToHost, ctx->stream));
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PA_OK;
 }

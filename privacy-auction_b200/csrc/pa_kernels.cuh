@@ -225,6 +225,21 @@ k_normalize(const u32 *jin, u32 *prefix, unsigned char *out, int n, int T, int n
   }
 }
 
+// ---- is the wire point on the curve (coordinates < p, y^2 = x^3 + 7; infinity counts)? ---------
+// What EC_POINT_set_affine_coordinates enforces when a point enters libcrypto.
+__global__ void k_on_curve(const unsigned char *points, int n, unsigned char *ok) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  aff a, c;
+  ld_aff(a, points + 64 * (size_t)i);
+  fe_canon(c.x, a.x);
+  fe_canon(c.y, a.y);
+  bool canonical = true;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) canonical &= c.x.v[k] == a.x.v[k] && c.y.v[k] == a.y.v[k];
+  ok[i] = (canonical && aff_on_curve(a)) ? 1 : 0;
+}
+
 // ---- EC_POINT_point2oct ------------------------------------------------------------
 __global__ void k_encode(const unsigned char *points, int n, int compressed, unsigned char *out, size_t stride,
                          u32 *lens) {

@@ -42,6 +42,7 @@ SIGNATURES = {
     "pa_lincomb2": (ctypes.c_int, [_ctx] + [ctypes.c_void_p] * 5 + [_sz]),
     "pa_lincomb2_dev": (ctypes.c_int, [_ctx] + [ctypes.c_void_p] * 5 + [_sz]),
     "pa_point_add": (ctypes.c_int, [_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _sz, ctypes.c_int]),
+    "pa_point_on_curve": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.c_void_p]),
     "pa_point_encode": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.c_int, ctypes.c_void_p, _sz, ctypes.c_void_p]),
     "pa_measure_int_peak": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_double)]),
     "pa_challenge": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _vp, _sz]),
@@ -243,6 +244,14 @@ class Engine:
         out = bytearray(64 * n)
         bufs = [_buf(x) for x in (p, q, out)]
         self._check(self.lib.pa_point_add(self.ctx, *[x[0] for x in bufs], n, 1 if sub else 0))
+        return bytes(out)
+
+    def point_on_curve(self, points):
+        n = len(points) // 64
+        out = bytearray(n)
+        pp, k0 = _buf(points)
+        po, k1 = _buf(out)
+        self._check(self.lib.pa_point_on_curve(self.ctx, pp, n, po))
         return bytes(out)
 
     def point_encode(self, points, compressed=False, stride=None):

@@ -113,3 +113,17 @@ def test_full_size_properties(engine, oracle):
     assert b"".join(g1[64 * i:64 * i + 64] for i in idx) == oracle.fixed_base_mul(sub_k)
     sub_p = b"".join(g1[64 * i:64 * i + 64] for i in idx)
     assert b"".join(v[64 * i:64 * i + 64] for i in idx) == oracle.var_base_mul(sub_p, _b([k2[i] for i in idx]))
+
+
+def test_point_on_curve(engine, oracle):
+    p = bytearray(oracle.fixed_base_mul(_b(_scalars(61, 64))))
+    want = [1] * 64
+    p[64 * 3 + 63] ^= 1; want[3] = 0                                   # y off by one
+    p[64 * 5:64 * 5 + 32] = (E.P + 1).to_bytes(32, "big"); want[5] = 0   # x >= p
+    p[64 * 7:64 * 8] = bytes(64); want[7] = 1                            # infinity
+    x0 = int.from_bytes(p[64 * 9:64 * 9 + 32], "big")
+    p[64 * 9 + 32:64 * 10] = ((E.P - int.from_bytes(p[64 * 9 + 32:64 * 10], "big")) % E.P).to_bytes(32, "big")  # -P is on the curve
+    got = engine.point_on_curve(bytes(p))
+    assert list(got) == want
+    for i in range(64):
+        assert bool(got[i]) == E.on_curve(E.dec64(bytes(p[64 * i:64 * i + 64]))) or i == 5
