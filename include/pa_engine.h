@@ -203,6 +203,17 @@ int pa_point_sum_is_inf_dev(pa_ctx *ctx, const uint8_t *d_B, const uint32_t *d_o
 int pa_ccs22_setup_hash(pa_ctx *ctx, const uint8_t *scalars, size_t k, uint8_t *out, size_t n);
 int pa_ccs22_setup_hash_dev(pa_ctx *ctx, const uint8_t *d_scalars, size_t k, uint8_t *d_out, size_t n);
 
+/* Fused oblivious-transfer messages: the 3-6 scalar multiplications of one message run
+ * concurrently (one warp each) instead of one after the other.  params[i] = (g1, h) of item i.
+ *   pa_ccs22_ot_recv1: (k, beta, alpha) -> (T2, G, H) = (g^k, g^beta g1^alpha, T2^alpha h^beta)
+ *                      Evaluator::OTReceive1, CCS22/evaluator.cpp:91-111
+ *   pa_ccs22_ot_send:  r1 = (T2, G, H), B, st = (s, t), m -> (z, C0, C1) = (g^s h^t, G^s H^t B,
+ *                      (G/g1)^s (H/T2)^t g^m)        Bidder::OTSend, CCS22/bidder.cpp:155-198 */
+int pa_ccs22_ot_recv1(pa_ctx *ctx, const uint8_t *k, const uint8_t *beta, const uint8_t *alpha, const uint8_t *params, uint8_t *out, size_t n);
+int pa_ccs22_ot_recv1_dev(pa_ctx *ctx, const uint8_t *k, const uint8_t *beta, const uint8_t *alpha, const uint8_t *params, uint8_t *out, size_t n);
+int pa_ccs22_ot_send(pa_ctx *ctx, const uint8_t *r1, const uint8_t *params, const uint8_t *B, const uint8_t *st, const uint8_t *m, uint8_t *out, size_t n);
+int pa_ccs22_ot_send_dev(pa_ctx *ctx, const uint8_t *r1, const uint8_t *params, const uint8_t *B, const uint8_t *st, const uint8_t *m, uint8_t *out, size_t n);
+
 /* ---- seeded randomness ------------------------------------------------------------------
  * The reference draws from OpenSSL's DRBG and is not reproducible.
  * The PA stream replaces BN_rand_range(., order) (SEAL/bidder.cpp:97 and 44 more sites):

@@ -133,6 +133,103 @@ __global__ void k_ccs22_update(const u32 *act, const u32 *pseg, const u32 *aeval
   if (nd && dflag[p] == 0) inrace[p] = 0;
 }
 
+// ---- fused oblivious-transfer messages for the per-party class API --------------------------------------
+// A party's OT message is 3-6 scalar multiplications that the reference runs one after the other.
+// Here each of them gets its own WARP (role = warp index, 32 items per block), so a single
+// message costs the latency of its slowest multiplication, not the sum; the warps meet in shared
+// memory for the final additions.  (Roles must be warps, not lanes: lanes of one warp that take
+// different code paths are serialised.)
+//
+// OTSend (CCS22/bidder.cpp:155-198): M1 = g^m, z = g^s h^t, C0 = G^s H^t B,
+//   C1 = (G/g1)^s (H/T2)^t M1 = C0 / B / (g1^s T2^t) * M1
+__global__ void __launch_bounds__(128)
+k_ccs22_ot_send(const unsigned char *r1, const unsigned char *params, const unsigned char *B, const unsigned char *st,
+                const unsigned char *mm, const u32 *__restrict__ comb, u32 *jout, int n) {
+  __shared__ __align__(16) u32 res[4][32][24];
+  int lane = threadIdx.x & 31, role = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
+  bool live = i < n;
+  if (live) {
+    const unsigned char *rec = r1 + 192 * (size_t)i, *pp = params + 128 * (size_t)i;
+    sc s, t;
+    ld_sc(s, st + 64 * (size_t)i);
+    ld_sc(t, st + 64 * (size_t)i + 32);
+    jac r, P, Q;
+    if (role == 0) {  // M1 = g^m
+      sc m;
+      ld_sc(m, mm + 32 * (size_t)i);
+      fixed_base_mul(r, m, comb);
+    } else if (role == 1) {  // z = g^s h^t
+      jac v;
+      ld_point_jac(P, pp + 64);
+      fixed_base_mul(r, s, comb);
+      var_base_mul(v, P, t);
+      jac_add(r, r, v);
+    } else if (role == 2) {  // G^s H^t
+      ld_point_jac(P, rec + 64);
+      ld_point_jac(Q, rec + 128);
+      strauss<2>(r, P, s, Q, t);
+    } else {  // g1^s T2^t
+      ld_point_jac(P, pp);
+      ld_point_jac(Q, rec);
+      strauss<2>(r, P, s, Q, t);
+    }
+    st_jac(res[role][lane], r);
+  }
+  __syncthreads();
+  if (!live) return;
+  if (role == 0) {  // C0 = G^s H^t * B
+    jac a;
+    aff b;
+    ld_jac(a, res[2][lane]);
+    ld_aff(b, B + 64 * (size_t)i);
+    jac_madd(a, a, b);
+    st_jac(jout + 24 * ((size_t)i * 3 + 1), a);
+  } else if (role == 1) {  // C1 = G^s H^t / (g1^s T2^t) * M1
+    jac a, u, m1;
+    ld_jac(a, res[2][lane]);
+    ld_jac(u, res[3][lane]);
+    ld_jac(m1, res[0][lane]);
+    jac_neg(u, u);
+    jac_add(a, a, u);
+    jac_add(a, a, m1);
+    st_jac(jout + 24 * ((size_t)i * 3 + 2), a);
+  } else if (role == 2) {  // z
+    jac z;
+    ld_jac(z, res[1][lane]);
+    st_jac(jout + 24 * ((size_t)i * 3), z);
+  }
+}
+
+// OTReceive1 (CCS22/evaluator.cpp:91-111): T2 = g^k, G = g^beta g1^alpha, H = T2^alpha h^beta = g^(alpha k) h^beta
+__global__ void __launch_bounds__(96)
+k_ccs22_ot_recv1(const unsigned char *k, const unsigned char *beta, const unsigned char *alpha, const unsigned char *params,
+                 const u32 *__restrict__ comb, u32 *jout, int n) {
+  int lane = threadIdx.x & 31, role = threadIdx.x >> 5, i = blockIdx.x * 32 + lane;
+  if (i >= n) return;
+  const unsigned char *pp = params + 128 * (size_t)i;
+  sc sk, sb, sa;
+  ld_sc(sk, k + 32 * (size_t)i);
+  ld_sc(sb, beta + 32 * (size_t)i);
+  ld_sc(sa, alpha + 32 * (size_t)i);
+  jac r, v, P;
+  if (role == 0) {
+    fixed_base_mul(r, sk, comb);
+  } else if (role == 1) {
+    ld_point_jac(P, pp);
+    fixed_base_mul(r, sb, comb);
+    var_base_mul(v, P, sa);
+    jac_add(r, r, v);
+  } else {
+    sc ak;
+    sc_mul(ak, sa, sk);
+    ld_point_jac(P, pp + 64);
+    fixed_base_mul(r, ak, comb);
+    var_base_mul(v, P, sb);
+    jac_add(r, r, v);
+  }
+  st_jac(jout + 24 * ((size_t)i * 3 + role), r);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
 int dev_point_add(pa_ctx *ctx, const unsigned char *p, const unsigned char *q, unsigned char *out, size_t n, int sub) {
@@ -148,6 +245,37 @@ int dev_gather(pa_ctx *ctx, unsigned char *dst, const unsigned char *src, const 
   return PA_OK;
 }
 }  // namespace
+
+extern "C" int pa_ccs22_ot_send_dev(pa_ctx *ctx, const uint8_t *r1, const uint8_t *params, const uint8_t *B, const uint8_t *st,
+                                    const uint8_t *m, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (r1 && params && B && st && m && out)) && n < (1u << 26));
+  if (n == 0) return PA_OK;
+  int rc = work_reserve(ctx, 3 * n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_LINCOMB2, (k_ccs22_ot_send<<<(unsigned)((n + 31) / 32), 128, 0, ctx->stream>>>(r1, params, B, st, m, ctx->d_comb, work_jac(ctx), (int)n)));
+  return normalize_to(ctx, out, 3 * n);
+}
+extern "C" int pa_ccs22_ot_send(pa_ctx *ctx, const uint8_t *r1, const uint8_t *params, const uint8_t *B, const uint8_t *st,
+                                const uint8_t *m, uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (r1 && params && B && st && m && out)));
+  HArg a[] = {{r1, 0, n * 192}, {params, 0, n * 128}, {B, 0, n * 64}, {st, 0, n * 64}, {m, 0, n * 32}, {0, out, n * 192}};
+  return staged(ctx, a, 6, [&](unsigned char **d) { return pa_ccs22_ot_send_dev(ctx, d[0], d[1], d[2], d[3], d[4], d[5], n); });
+}
+extern "C" int pa_ccs22_ot_recv1_dev(pa_ctx *ctx, const uint8_t *k, const uint8_t *beta, const uint8_t *alpha, const uint8_t *params,
+                                     uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (k && beta && alpha && params && out)) && n < (1u << 26));
+  if (n == 0) return PA_OK;
+  int rc = work_reserve(ctx, 3 * n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_DOUBLE, (k_ccs22_ot_recv1<<<(unsigned)((n + 31) / 32), 96, 0, ctx->stream>>>(k, beta, alpha, params, ctx->d_comb, work_jac(ctx), (int)n)));
+  return normalize_to(ctx, out, 3 * n);
+}
+extern "C" int pa_ccs22_ot_recv1(pa_ctx *ctx, const uint8_t *k, const uint8_t *beta, const uint8_t *alpha, const uint8_t *params,
+                                 uint8_t *out, size_t n) {
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (k && beta && alpha && params && out)));
+  HArg a[] = {{k, 0, n * 32}, {beta, 0, n * 32}, {alpha, 0, n * 32}, {params, 0, n * 128}, {0, out, n * 192}};
+  return staged(ctx, a, 5, [&](unsigned char **d) { return pa_ccs22_ot_recv1_dev(ctx, d[0], d[1], d[2], d[3], d[4], n); });
+}
 
 extern "C" int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job) {
   PA_ARGCHECK(ctx, ctx && job && job->n_auctions >= 1 && job->n && job->c && job->bids && job->evaluator);

@@ -75,6 +75,10 @@ SIGNATURES = {
     "pa_rng_fill_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_seal_run": (ctypes.c_int, [_ctx, _vp]),
     "pa_ccs22_run": (ctypes.c_int, [_ctx, _vp]),
+    "pa_ccs22_ot_recv1": (ctypes.c_int, [_ctx] + [_vp] * 5 + [_sz]),
+    "pa_ccs22_ot_recv1_dev": (ctypes.c_int, [_ctx] + [_vp] * 5 + [_sz]),
+    "pa_ccs22_ot_send": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_ccs22_ot_send_dev": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
     "pa_rng_fill256": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_rng_fill256_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_ccs22_setup_hash": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _sz]),
@@ -451,6 +455,14 @@ class Engine:
         for name, buf in out.items():
             res[name[4:]] = bytes(buf)
         return res
+
+    def ccs22_ot_recv1(self, k, beta, alpha, params):
+        n = len(k) // 32
+        return self._run("pa_ccs22_ot_recv1", (k, beta, alpha, params), 192 * n, n)
+
+    def ccs22_ot_send(self, r1, params, B, st, m):
+        n = len(m) // 32
+        return self._run("pa_ccs22_ot_send", (r1, params, B, st, m), 192 * n, n)
 
     def ccs22_setup_hash(self, scalars, k):
         n = len(scalars) // (32 * k)

@@ -212,21 +212,15 @@ void Bidder::BESEncode(const std::vector<Point> &pk, size_t step) {
   TimeTracker::getInstance().stop(BIDDER_CATEGORY);
 }
 
-// Reference: CCS22/bidder.cpp:155-198
+// Reference: CCS22/bidder.cpp:155-198 — six scalar multiplications one after the other there; here one
+// engine call in which every multiplication of the message runs in its own warp.
 OT_S Bidder::OTSend(size_t step, const OT_R1 &r1) {
   TimeTracker::getInstance().start(BIDDER_CATEGORY);
-  pa_ctx *e = engine();
   OT_S out;
-  Point M1, t, Gm, Hm;
-  Scalar m = draw256(1)[0];
-  check(pa_fixed_base_mul(e, m.b, M1.b, 1), "pa_fixed_base_mul");                                     // M1 = g^rand
-  check(pa_double_mul(e, randomS[step].b, pp.h.b, randomT[step].b, out.z.b, 1), "pa_double_mul");      // z = g^s h^t
-  check(pa_lincomb2(e, r1.G.b, randomS[step].b, r1.H.b, randomT[step].b, t.b, 1), "pa_lincomb2");
-  check(pa_point_add(e, t.b, B.b, out.C0.b, 1, 0), "pa_point_add");                                    // C0 = G^s H^t B
-  check(pa_point_add(e, r1.G.b, pp.g1.b, Gm.b, 1, 1), "pa_point_add");                                 // G / T1, T1 = g1
-  check(pa_point_add(e, r1.H.b, r1.T2.b, Hm.b, 1, 1), "pa_point_add");                                 // H / T2
-  check(pa_lincomb2(e, Gm.b, randomS[step].b, Hm.b, randomT[step].b, t.b, 1), "pa_lincomb2");
-  check(pa_point_add(e, t.b, M1.b, out.C1.b, 1, 0), "pa_point_add");                                   // C1 = (G/T1)^s (H/T2)^t M1
+  Scalar m = draw256(1)[0];  // M1 = g^rand
+  Point params[2] = {pp.g1, pp.h};
+  Scalar st[2] = {randomS[step], randomT[step]};
+  check(pa_ccs22_ot_send(engine(), r1.T2.b, params[0].b, B.b, st[0].b, m.b, out.z.b, 1), "pa_ccs22_ot_send");
   TimeTracker::getInstance().stop(BIDDER_CATEGORY);
   return out;
 }
@@ -273,19 +267,17 @@ void Evaluator::BESEncode(const std::vector<Point> &pk, size_t step) {
   TimeTracker::getInstance().stop(EVALUATOR_CATEGORY);
 }
 
-// Reference: CCS22/evaluator.cpp:78-115 — 4 scalar mults per other bidder, batched here
+// Reference: CCS22/evaluator.cpp:78-115 — 4 scalar mults per other bidder; one batched, fused call here
 OT_R1_VEC Evaluator::OTReceive1(size_t step) {
   TimeTracker::getInstance().start(EVALUATOR_CATEGORY);
   size_t nb = n_ - 1;
   OT_R1_VEC out(nb);
   if (nb) {
-    pa_ctx *e = engine();
     std::vector<Scalar> k = draw256(nb), alpha(nb, scalarOf(d));
-    std::vector<Point> T2(nb), G(nb), H(nb), g1s(nb, pp.g1), hs(nb, pp.h);
-    check(pa_fixed_base_mul(e, bytes(k), bytes(T2), nb), "pa_fixed_base_mul");                                        // T2 = g^k
-    check(pa_double_mul(e, bytes(randomBeta[step]), bytes(g1s), bytes(alpha), bytes(G), nb), "pa_double_mul");        // G = g^beta T1^alpha
-    check(pa_lincomb2(e, bytes(T2), bytes(alpha), bytes(hs), bytes(randomBeta[step]), bytes(H), nb), "pa_lincomb2");  // H = T2^alpha h^beta
-    for (size_t j = 0; j < nb; ++j) out[j] = OT_R1{T2[j], G[j], H[j]};
+    std::vector<Point> params(2 * nb);
+    for (size_t j = 0; j < nb; ++j) params[2 * j] = pp.g1, params[2 * j + 1] = pp.h;
+    check(pa_ccs22_ot_recv1(engine(), bytes(k), bytes(randomBeta[step]), bytes(alpha), bytes(params), (uint8_t *)out.data(), nb),
+          "pa_ccs22_ot_recv1");
   }
   TimeTracker::getInstance().stop(EVALUATOR_CATEGORY);
   return out;

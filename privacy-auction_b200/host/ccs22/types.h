@@ -16,4 +16,5 @@ struct OT_S {
   Point z, C0, C1;
 };
 typedef std::vector<OT_S> OT_S_VEC;
+static_assert(sizeof(OT_R1) == 192 && sizeof(OT_S) == 192, "OT messages must equal their wire records");
 #endif

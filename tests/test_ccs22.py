@@ -100,3 +100,34 @@ def test_ccs22_runner_config2_digest(engine):
     res = engine.ccs22_run(g["seed"], [g["n"]], [g["c"]], [g["evaluator"]], g["bids"], sections=True)
     out = ccs22_flow.sections_to_transcripts(g["seed"], [g["n"]], [g["c"]], [g["evaluator"]], g["bids"], res)[0]
     assert hashlib.sha256(out).hexdigest() == g["sha256"]
+
+
+@pytest.mark.gpu
+def test_fused_ot_messages_match_oracle_composition(engine, oracle):
+    """pa_ccs22_ot_recv1 / pa_ccs22_ot_send (one warp per scalar multiplication) against the same
+    messages composed from the oracle's EC_POINT_mul call shapes (CCS22/evaluator.cpp:91-111, bidder.cpp:155-198)"""
+    import secp256k1_py as E
+    rnd = random.Random(515)
+    n = 70
+    sc = lambda: b"".join(rnd.getrandbits(256).to_bytes(32, "big") for _ in range(n))
+    k, beta, s, t, m = sc(), sc(), sc(), sc(), sc()
+    alpha = b"".join((rnd.randrange(2)).to_bytes(32, "big") for _ in range(n))
+    gh = oracle.fixed_base_mul(sc() + sc())
+    params = b"".join(gh[64 * i:64 * i + 64] + gh[64 * (n + i):64 * (n + i) + 64] for i in range(n))
+    g1 = b"".join(params[128 * i:128 * i + 64] for i in range(n))
+    h = b"".join(params[128 * i + 64:128 * i + 128] for i in range(n))
+    B = bytearray(oracle.fixed_base_mul(sc()))
+    B[64 * 5:64 * 6] = bytes(64)                                  # B = infinity (n = 1 auctions)
+    B = bytes(B)
+    T2 = oracle.fixed_base_mul(k)
+    G = oracle.double_mul(beta, g1, alpha)
+    H = oracle.lincomb2(T2, alpha, h, beta)
+    want_r1 = b"".join(T2[64 * i:64 * i + 64] + G[64 * i:64 * i + 64] + H[64 * i:64 * i + 64] for i in range(n))
+    assert engine.ccs22_ot_recv1(k, beta, alpha, params) == want_r1
+    M1 = oracle.fixed_base_mul(m)
+    z = oracle.double_mul(s, h, t)
+    C0 = oracle.point_add(oracle.lincomb2(G, s, H, t), B)
+    C1 = oracle.point_add(oracle.lincomb2(oracle.point_add(G, g1, sub=True), s, oracle.point_add(H, T2, sub=True), t), M1)
+    want_s = b"".join(z[64 * i:64 * i + 64] + C0[64 * i:64 * i + 64] + C1[64 * i:64 * i + 64] for i in range(n))
+    st = b"".join(s[32 * i:32 * i + 32] + t[32 * i:32 * i + 32] for i in range(n))
+    assert engine.ccs22_ot_send(want_r1, params, B, st, m) == want_s
