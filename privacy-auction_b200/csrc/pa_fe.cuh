@@ -321,7 +321,7 @@ PA_HD void fe_sqr(fe &r, const fe &a) { fe_sqr_inl(r, a); }
 struct fe2 {
   fe a, b;
 };
-#if defined(__CUDA_ARCH__) && !defined(PA_FE_PAIRS)  // default: the two products as two calls
+#if defined(__CUDA_ARCH__) && !defined(PA_FE_PAIRS) && !defined(PA_FE_INLINE)  // default: the two products as two calls
 PA_D void fe_mul2(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1) {
   fe x = fe_mul_call(a0, b0), y = fe_mul_call(a1, b1);
   r0 = x;

@@ -255,15 +255,6 @@ PA_HD void glv_scale_table(glv_table &T, const fe &f) {
   }
 }
 
-PA_HD void glv_add_digit(jac &r, const glv_table &T, int d, bool neg, bool lam) {
-  if (d == 0) return;
-  int idx = (d > 0 ? d : -d) - 1;
-  aff q;
-  q.x = lam ? T.bx[idx] : T.x[idx];
-  if ((d < 0) != neg) fe_neg(q.y, T.y[idx]); else q.y = T.y[idx];
-  jac_madd(r, r, q);
-}
-
 // r = a*P (+ b*Q when NB == 2), scalars < n, bases Jacobian (may be infinity)
 template <int NB>
 PA_HD void strauss(jac &r, const jac &P, const sc &a, const jac &Q, const sc &b) {
@@ -295,21 +286,29 @@ PA_HD void strauss(jac &r, const jac &P, const sc &a, const jac &Q, const sc &b)
   }
   jac_set_inf(r);
   if (!useP && !useQ) return;
+  // One doubling body and one mixed-addition body in the loop (point formulas inlined here, field
+  // products still shared calls): the 2*NB digit sources go through the same addition code, which
+  // keeps the hot loop small and saves the register shuffling of a call per point operation.
 #pragma unroll 1
   for (int i = PA_GLV_WINDOWS; i >= 0; --i) {
     if (i != PA_GLV_WINDOWS) {
-      jac_dbl(r, r);
-      jac_dbl(r, r);
-      jac_dbl(r, r);
-      jac_dbl(r, r);
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) jac_dbl_inl(r, r);
     }
-    if (useP) {
-      glv_add_digit(r, TP, glv_digit(a1, i), sa.neg1, false);
-      glv_add_digit(r, TP, glv_digit(a2, i), sa.neg2, true);
-    }
-    if (useQ) {
-      glv_add_digit(r, TQ, glv_digit(b1, i), sb.neg1, false);
-      glv_add_digit(r, TQ, glv_digit(b2, i), sb.neg2, true);
+#pragma unroll 1
+    for (int t = 0; t < 2 * NB; ++t) {
+      bool second = t >= 2, lam = t & 1;
+      if (second ? !useQ : !useP) continue;
+      const glv_table &T = second ? TQ : TP;
+      const u32 *kk = second ? (lam ? b2 : b1) : (lam ? a2 : a1);
+      bool neg = second ? (lam ? sb.neg2 : sb.neg1) : (lam ? sa.neg2 : sa.neg1);
+      int d = glv_digit(kk, i);
+      if (d == 0) continue;
+      int idx = (d > 0 ? d : -d) - 1;
+      aff q;
+      q.x = lam ? T.bx[idx] : T.x[idx];
+      if ((d < 0) != neg) fe_neg(q.y, T.y[idx]); else q.y = T.y[idx];
+      jac_madd_inl(r, r, q);
     }
   }
   if (!jac_is_inf(r)) fe_mul(r.Z, r.Z, zeta);  // back from the isomorphic curve
