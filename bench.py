@@ -36,8 +36,11 @@ N_PER_KIND = 1 << 20
 METRIC = "ec_scalar_mults_per_s"
 UNIT = "scalar-mults/s"
 WORKLOAD = "configs[2]: batched EC microbench, 2^20 fixed-base + 2^20 variable-base scalar mults on secp256k1 per GPU per step"
-# SURVEY.md §8(d) algorithmic work figures
+# SURVEY.md §8(d) algorithmic work figures (nominal double-and-add / comb on 32-bit IMAD)
 FM_VAR, FM_FIXED, IMAD_PER_FM = 2900, 712, 272
+# Executed 32x32->64 multiply-adds (SASS IMAD.WIDE) per scalar multiplication, counted by ncu on the
+# shipped kernels (profiles/r01c_k_var_base_opcode_mix.txt; the fixed-base figure from the same capture)
+WIDE_VAR, WIDE_FIXED = 98793, 14807
 ECMUL_REF = os.path.join(ROOT, "oracle", "_ref", "ecmul_ref")
 
 
@@ -466,7 +469,9 @@ def main():
         sm_max = clocks.get("sm_max_mhz") or 1965.0
         nominal_peak = 64.0 * 148 * sm_max * 1e6
         peak_imad = peak["imad_per_s"]
-        achieved = n * FM_VAR * IMAD_PER_FM / (var_ms * 1e-3)
+        peak_wide = peak["imad_wide_per_s"]
+        achieved = n * WIDE_VAR / (var_ms * 1e-3)
+        nominal = n * FM_VAR * IMAD_PER_FM / (var_ms * 1e-3)
         total_k_ms = sum(v["total_ms"] for v in kstats.values()) or 1.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -478,18 +483,25 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n, "d2h_bytes_per_step": 128 * n,
                     "steps": e2e_steps, "bytes_match_device_run": same},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "imad", "kernel": "k_var_base", "achieved": achieved / 1e12, "peak": peak_imad / 1e12,
-                         "unit": "TIMAD/s", "frac": achieved / peak_imad,
-                         "traffic": 1.80e9,  # dram read + write per launch, ncu --set full (profiles/r01b_ncu_full_k_var_base_glv_summary.csv)
-                         "peak_source": "measured on this GPU by pa_measure_int_peak (register-only 32-bit IMAD loop); not in MEASURED_PEAKS.json",
-                         "nominal_peak": nominal_peak / 1e12, "frac_of_nominal": achieved / nominal_peak,
-                         "algorithmic": f"{FM_VAR} field mults x {IMAD_PER_FM} IMAD per variable-base mult (SURVEY.md 8d) x {n} per launch",
+            # The path is 256-bit integer arithmetic: neither HBM nor the tensor cores bound it, the
+            # integer multiply pipe does ("fmaheavy" in ncu).  achieved = executed 32x32->64 multiply-adds
+            # per second, peak = the same instruction in a register-only loop on this GPU.
+            "roofline": {"bound": "int-multiply pipe (IMAD.WIDE on fmaheavy); not hbm, not tensor", "kernel": "k_var_base",
+                         "achieved": achieved / 1e12, "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE/s", "frac": achieved / peak_wide,
+                         "traffic": 2.25e9,  # dram read + write per launch, ncu --set full (profiles/r01c_ncu_full_k_var_base_summary.csv)
+                         "traffic_note": "algorithmic bytes are 0.2 GB per launch (64 B point + 32 B scalar in, 96 B Jacobian out); the rest is "
+                                         "write-back and refill of per-thread stack lines (window tables and register spills at 96 registers), "
+                                         "113 GB/s = 1.5 % of HBM bandwidth, not on the critical path",
+                         "peak_source": "measured on this GPU by pa_measure_int_peak (register-only IMAD.WIDE loop); MEASURED_PEAKS.json has no integer figure",
+                         "units_per_launch": n, "per_unit": f"{WIDE_VAR} IMAD.WIDE per variable-base mult (ncu count on this kernel)",
                          "avg_launch_ms": var_ms, "share_of_kernel_time": var["total_ms"] / total_k_ms,
-                         "executed": "GLV split + co-Z tables: ~1,800 field mults (~97 k IMAD.WIDE) actually executed per variable-base mult; "
-                                     "frac > 1 is fewer multiplications than the nominal algorithm, not a faster pipe - ncu pipe utilisation is in profiles/"},
-            "roofline_fixed_base": {"bound": "imad", "kernel": "k_fixed_base", "achieved": n * FM_FIXED * IMAD_PER_FM / (fix_ms * 1e-3) / 1e12,
-                                    "peak": peak_imad / 1e12, "unit": "TIMAD/s", "frac": n * FM_FIXED * IMAD_PER_FM / (fix_ms * 1e-3) / peak_imad,
-                                    "avg_launch_ms": fix_ms},
+                         "ncu": "fmaheavy pipe 80.5 % active, top stall math_pipe_throttle; 22.6 % of the pipe's cycles are IMAD.MOV register moves",
+                         "nominal_algorithm": {"per_unit": f"{FM_VAR} field mults x {IMAD_PER_FM} 32-bit IMAD (SURVEY.md 8d, plain double-and-add)",
+                                               "achieved_timad_s": nominal / 1e12, "peak_timad_s": peak_imad / 1e12, "frac": nominal / peak_imad,
+                                               "note": "above 1 because GLV + co-Z tables execute ~1,800 field mults instead of 2,900"}},
+            "roofline_fixed_base": {"bound": "int-multiply pipe", "kernel": "k_fixed_base", "achieved": n * WIDE_FIXED / (fix_ms * 1e-3) / 1e12,
+                                    "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE/s", "frac": n * WIDE_FIXED / (fix_ms * 1e-3) / peak_wide,
+                                    "avg_launch_ms": fix_ms, "per_unit": f"{WIDE_FIXED} IMAD.WIDE per fixed-base mult (ncu count)"},
             "roofline_point_stream": point_stream_roofline(kstats, n),
             "kernels": {k: {"launches": v["launches"], "avg_ms": v["total_ms"] / max(v["launches"], 1)} for k, v in kstats.items()},
             "int_peak_measured": peak,

@@ -93,20 +93,16 @@ __global__ void k_comb_base(u32 *bases) {  // one thread per window: B_w = 2^(PA
   st_fe(bases + 16 * w + 8, B.y);
 }
 __global__ void k_comb_entries(const u32 *bases, u32 *tab) {  // one thread per table entry
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= PA_COMB_WINDOWS * PA_COMB_ENTRIES) return;
-  int w = t / PA_COMB_ENTRIES;
-  u32 d = t % PA_COMB_ENTRIES;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)PA_COMB_WINDOWS * PA_COMB_ENTRIES) return;
+  int w = (int)(t / PA_COMB_ENTRIES);
+  u32 d = (u32)(t % PA_COMB_ENTRIES) + 1;
   aff B, e;
   ld_fe(B.x, bases + 16 * w);
   ld_fe(B.y, bases + 16 * w + 8);
-  if (d == 0) {
-    aff_set_inf(e);
-  } else {
-    comb_entry(e, d, B);
-  }
-  st_fe(tab + (size_t)t * 16, e.x);
-  st_fe(tab + (size_t)t * 16 + 8, e.y);
+  comb_entry(e, d, B);
+  st_fe(tab + t * 16, e.x);
+  st_fe(tab + t * 16 + 8, e.y);
 }
 
 // ---- scalar multiplication -----------------------------------------------------

@@ -41,21 +41,53 @@ void hc_mp_mul8(const unsigned char *a, const unsigned char *b, unsigned char *o
 
 #include "pa_smul.cuh"
 #include <vector>
+#include <cstdio>
+#include <cstdlib>
 
 static std::vector<u32> g_tab;
+// The whole signed-window table on the host: per window a running sum e_d = e_(d-1) + B_w in Jacobian
+// form and one batched inversion (building every entry with comb_entry, as the GPU does, would
+// take minutes here); comb_entry itself is checked against a sample of the entries.
 static void ensure_tab() {
   if (!g_tab.empty()) return;
   g_tab.assign(PA_COMB_WORDS, 0);
   aff G;
   aff_set_generator(G);
+  std::vector<jac> J(PA_COMB_ENTRIES);
+  std::vector<fe> pre(PA_COMB_ENTRIES);
   for (int w = 0; w < PA_COMB_WINDOWS; ++w) {
     aff Bw;
     comb_base(Bw, w, G);
-    for (u32 d = 1; d < PA_COMB_ENTRIES; ++d) {
+    jac acc;
+    jac_from_aff(acc, Bw);
+    J[0] = acc;
+    for (u32 d = 2; d <= PA_COMB_ENTRIES; ++d) {
+      if (d == 2) jac_dbl(acc, acc); else jac_madd(acc, acc, Bw);
+      J[d - 1] = acc;
+    }
+    fe run;
+    fe_set_one(run);
+    for (u32 i = 0; i < PA_COMB_ENTRIES; ++i) {
+      pre[i] = run;
+      fe_mul(run, run, J[i].Z);
+    }
+    fe inv;
+    fe_inv(inv, run);
+    for (int i = PA_COMB_ENTRIES - 1; i >= 0; --i) {
+      fe zi;
+      fe_mul(zi, inv, pre[i]);
+      fe_mul(inv, inv, J[i].Z);
+      aff e;
+      jac_to_aff_with_zinv(e, J[i], zi);
+      u32 *o = g_tab.data() + ((size_t)w * PA_COMB_ENTRIES + i) * 16;
+      for (int k = 0; k < 8; ++k) { o[k] = e.x.v[k]; o[8 + k] = e.y.v[k]; }
+    }
+    for (u32 d : {1u, 2u, 3u, (u32)PA_COMB_ENTRIES / 3, (u32)PA_COMB_ENTRIES - 1, (u32)PA_COMB_ENTRIES}) {
       aff e;
       comb_entry(e, d, Bw);
-      u32 *o = g_tab.data() + ((size_t)w * PA_COMB_ENTRIES + d) * 16;
-      for (int i = 0; i < 8; ++i) { o[i] = e.x.v[i]; o[8 + i] = e.y.v[i]; }
+      const u32 *o = g_tab.data() + ((size_t)w * PA_COMB_ENTRIES + (d - 1)) * 16;
+      for (int k = 0; k < 8; ++k)
+        if (o[k] != e.x.v[k] || o[8 + k] != e.y.v[k]) { fprintf(stderr, "hostcheck: comb_entry(%d, %u) disagrees with the running sum\n", w, d); abort(); }
     }
   }
 }
