@@ -16,6 +16,9 @@ def _b(ks):
 
 EDGE_K = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 255, 256, N - 1, N - 2, N, N + 5, M - 1, (N - 1) // 2,
           int("8" * 64, 16) % N, int("7" * 64, 16), 2**255, 2**128, 1 << 8, 1 << 248, 0xFF << 248]
+# boundaries of the signed 16-bit fixed-base windows: digits -2^15, 2^15 - 1, carries rippling through every window
+EDGE_K += [int(w * (64 // len(w)), 16) for w in ("8000", "7FFF", "8001", "0001", "FFFF", "7FFF8000", "80007FFF", "0000FFFF")] + \
+          [(1 << 15) - 1, 1 << 15, (1 << 15) + 1, (1 << 16) - 1, 1 << 16, 0x7FFF << 240, 0x8000 << 240, (1 << 256) - (1 << 16)]
 
 
 def _scalars(seed, n):

@@ -108,6 +108,11 @@ def test_group_and_scalar_mult(hc):
 
     ks = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 255, 256, N - 1, N - 2, N, N + 5, M - 1, (N - 1) // 2,
           int("8" * 64, 16) % N, int("7" * 64, 16)] + [rnd.getrandbits(256) for _ in range(12)]
+    # boundaries of the signed 16-bit fixed-base windows (digits -2^15 and 2^15 - 1, carries through every window)
+    wk = [int(w * (64 // len(w)), 16) for w in ("8000", "7FFF", "8001", "0001", "FFFF", "7FFF8000", "80007FFF", "0000FFFF")] + \
+         [(1 << 15) - 1, 1 << 15, (1 << 15) + 1, (1 << 16) - 1, 1 << 16, 0x7FFF << 240, 0x8000 << 240, (1 << 256) - (1 << 16)]
+    for k in wk:
+        assert fixed(k) == E.mul(k, E.G)
     for k in ks:
         assert fixed(k) == E.mul(k, E.G)
     pts = [E.G, E.mul(2, E.G), E.mul(12345, E.G), E.neg(E.G), E.INF, E.mul(N - 1, E.G)] + \
