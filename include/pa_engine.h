@@ -214,6 +214,20 @@ int pa_ccs22_ot_recv1_dev(pa_ctx *ctx, const uint8_t *k, const uint8_t *beta, co
 int pa_ccs22_ot_send(pa_ctx *ctx, const uint8_t *r1, const uint8_t *params, const uint8_t *B, const uint8_t *st, const uint8_t *m, uint8_t *out, size_t n);
 int pa_ccs22_ot_send_dev(pa_ctx *ctx, const uint8_t *r1, const uint8_t *params, const uint8_t *B, const uint8_t *st, const uint8_t *m, uint8_t *out, size_t n);
 
+/* The other three per-party steps of CCS22 as one call each (SURVEY.md 8b lower seam).
+ *   pa_ccs22_commit:     H = SHA256inSetup(k scalars) and Com = g^bid * g1^H + h^R, params[i] = (g1, h)
+ *                        Bidder::setupInner, CCS22/bidder.cpp:80-88; Evaluator::setupInner, evaluator.cpp:54-62
+ *   pa_ccs22_bes_encode: X = the n public keys of this step; for each of m parties ids[i] of that auction
+ *                        B = Y_ids[i]^x (d = 0) or g^r (d = 1)        Bidder::BESEncodeInner, CCS22/bidder.cpp:118-147
+ *   pa_ccs22_ot_recv2:   is_inf = (sum_j (C0_j - beta_j z_j) + B == infinity) over the n OT_S records (z, C0, C1)
+ *                        Evaluator::OTReceive2, CCS22/evaluator.cpp:117-156 */
+int pa_ccs22_commit(pa_ctx *ctx, const uint8_t *scalars, size_t k, const uint8_t *bid, const uint8_t *R, const uint8_t *params, uint8_t *out_H, uint8_t *out_com, size_t n);
+int pa_ccs22_commit_dev(pa_ctx *ctx, const uint8_t *scalars, size_t k, const uint8_t *bid, const uint8_t *R, const uint8_t *params, uint8_t *out_H, uint8_t *out_com, size_t n);
+int pa_ccs22_bes_encode(pa_ctx *ctx, const uint8_t *X, size_t n, const uint64_t *ids, const uint8_t *d, const uint8_t *x, const uint8_t *r, uint8_t *out, size_t m);
+int pa_ccs22_bes_encode_dev(pa_ctx *ctx, const uint8_t *X, size_t n, const uint64_t *ids, const uint8_t *d, const uint8_t *x, const uint8_t *r, uint8_t *out, size_t m);
+int pa_ccs22_ot_recv2(pa_ctx *ctx, const uint8_t *ots, const uint8_t *beta, const uint8_t *B, size_t n, int *is_inf);
+int pa_ccs22_ot_recv2_dev(pa_ctx *ctx, const uint8_t *ots, const uint8_t *beta, const uint8_t *B, size_t n, int32_t *d_is_inf);
+
 /* ---- seeded randomness ------------------------------------------------------------------
  * The reference draws from OpenSSL's DRBG and is not reproducible.
  * The PA stream replaces BN_rand_range(., order) (SEAL/bidder.cpp:97 and 44 more sites):

@@ -230,6 +230,62 @@ k_ccs22_ot_recv1(const unsigned char *k, const unsigned char *beta, const unsign
   st_jac(jout + 24 * ((size_t)i * 3 + role), r);
 }
 
+// BESEncode (CCS22/bidder.cpp:118-147): B = Y_id^x when the party does not veto (d = 0), g^r when it does
+__global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
+k_ccs22_bes_encode(const unsigned char *Y, const u64 *ids, const unsigned char *d, const unsigned char *x, const unsigned char *r,
+                   const u32 *__restrict__ comb, u32 *jout, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  jac res;
+  sc k;
+  if (d[i]) {
+    ld_sc(k, r + 32 * (size_t)i);
+    fixed_base_mul(res, k, comb);
+  } else {
+    jac P;
+    ld_point_jac(P, Y + 64 * (size_t)ids[i]);
+    ld_sc(k, x + 32 * (size_t)i);
+    var_base_mul(res, P, k);
+  }
+  st_jac(jout + 24 * (size_t)i, res);
+}
+
+// Com = g^bid * g1^H + h^R (CCS22/bidder.cpp:80-88)
+__global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
+k_ccs22_commit(const unsigned char *bid, const unsigned char *H, const unsigned char *R, const unsigned char *params,
+               const u32 *__restrict__ comb, u32 *jout, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  jac g1, h, res, f;
+  sc a, b;
+  ld_point_jac(g1, params + 128 * (size_t)i);
+  ld_point_jac(h, params + 128 * (size_t)i + 64);
+  ld_sc(a, H + 32 * (size_t)i);
+  ld_sc(b, R + 32 * (size_t)i);
+  strauss<2>(res, g1, a, h, b);
+  ld_sc(a, bid + 32 * (size_t)i);
+  fixed_base_mul(f, a, comb);
+  jac_add(res, res, f);
+  st_jac(jout + 24 * (size_t)i, res);
+}
+
+// OTReceive2 (CCS22/evaluator.cpp:130-140): M0_j = C0_j - beta_j * z_j
+__global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
+k_ccs22_recv2_terms(const unsigned char *ots, const unsigned char *beta, u32 *jout, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  jac z, res;
+  aff c0;
+  sc k;
+  ld_point_jac(z, ots + 192 * (size_t)i);
+  ld_sc(k, beta + 32 * (size_t)i);
+  var_base_mul(res, z, k);
+  jac_neg(res, res);
+  ld_aff(c0, ots + 192 * (size_t)i + 64);
+  jac_madd(res, res, c0);
+  st_jac(jout + 24 * (size_t)i, res);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
 int dev_point_add(pa_ctx *ctx, const unsigned char *p, const unsigned char *q, unsigned char *out, size_t n, int sub) {
@@ -275,6 +331,61 @@ extern "C" int pa_ccs22_ot_recv1(pa_ctx *ctx, const uint8_t *k, const uint8_t *b
   PA_ARGCHECK(ctx, ctx && (n == 0 || (k && beta && alpha && params && out)));
   HArg a[] = {{k, 0, n * 32}, {beta, 0, n * 32}, {alpha, 0, n * 32}, {params, 0, n * 128}, {0, out, n * 192}};
   return staged(ctx, a, 5, [&](unsigned char **d) { return pa_ccs22_ot_recv1_dev(ctx, d[0], d[1], d[2], d[3], d[4], n); });
+}
+
+extern "C" int pa_ccs22_bes_encode_dev(pa_ctx *ctx, const uint8_t *X, size_t n, const uint64_t *ids, const uint8_t *d, const uint8_t *x,
+                                       const uint8_t *r, uint8_t *out, size_t m) {
+  PA_ARGCHECK(ctx, ctx && n >= 1 && n < (1u << 26) && m < (1u << 26) && X && (m == 0 || (ids && d && x && r && out)));
+  if (m == 0) return PA_OK;
+  int rc = ensure(ctx, &ctx->d_aux, &ctx->aux_bytes, n * 64);
+  if (rc) return rc;
+  if ((rc = pa_y_scan_dev(ctx, X, ctx->d_aux, nullptr, 1, n))) return rc;
+  if ((rc = work_reserve(ctx, m))) return rc;
+  PA_LAUNCH(ctx, PA_K_VAR, (k_ccs22_bes_encode<<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(ctx->d_aux, ids, d, x, r, ctx->d_comb, work_jac(ctx), (int)m)));
+  return normalize_to(ctx, out, m);
+}
+extern "C" int pa_ccs22_bes_encode(pa_ctx *ctx, const uint8_t *X, size_t n, const uint64_t *ids, const uint8_t *d, const uint8_t *x,
+                                   const uint8_t *r, uint8_t *out, size_t m) {
+  PA_ARGCHECK(ctx, ctx && n >= 1 && X && (m == 0 || (ids && d && x && r && out)));
+  for (size_t i = 0; i < m; ++i) PA_ARGCHECK(ctx, ids[i] < n);
+  HArg a[] = {{X, 0, n * 64}, {ids, 0, m * 8}, {d, 0, m}, {x, 0, m * 32}, {r, 0, m * 32}, {0, out, m * 64}};
+  return staged(ctx, a, 6, [&](unsigned char **p) { return pa_ccs22_bes_encode_dev(ctx, p[0], n, (const uint64_t *)p[1], p[2], p[3], p[4], p[5], m); });
+}
+extern "C" int pa_ccs22_commit_dev(pa_ctx *ctx, const uint8_t *scalars, size_t k, const uint8_t *bid, const uint8_t *R, const uint8_t *params,
+                                   uint8_t *out_H, uint8_t *out_com, size_t n) {
+  PA_ARGCHECK(ctx, ctx && k >= 1 && n < (1u << 26) && (n == 0 || (scalars && bid && R && params && out_H && out_com)));
+  if (n == 0) return PA_OK;
+  int rc = pa_ccs22_setup_hash_dev(ctx, scalars, k, out_H, n);
+  if (rc) return rc;
+  if ((rc = work_reserve(ctx, n))) return rc;
+  PA_LAUNCH(ctx, PA_K_LINCOMB2, (k_ccs22_commit<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(bid, out_H, R, params, ctx->d_comb, work_jac(ctx), (int)n)));
+  return normalize_to(ctx, out_com, n);
+}
+extern "C" int pa_ccs22_commit(pa_ctx *ctx, const uint8_t *scalars, size_t k, const uint8_t *bid, const uint8_t *R, const uint8_t *params,
+                               uint8_t *out_H, uint8_t *out_com, size_t n) {
+  PA_ARGCHECK(ctx, ctx && k >= 1 && (n == 0 || (scalars && bid && R && params && out_H && out_com)));
+  HArg a[] = {{scalars, 0, n * k * 32}, {bid, 0, n * 32}, {R, 0, n * 32}, {params, 0, n * 128}, {0, out_H, n * 32}, {0, out_com, n * 64}};
+  return staged(ctx, a, 6, [&](unsigned char **p) { return pa_ccs22_commit_dev(ctx, p[0], k, p[1], p[2], p[3], p[4], p[5], n); });
+}
+extern "C" int pa_ccs22_ot_recv2_dev(pa_ctx *ctx, const uint8_t *ots, const uint8_t *beta, const uint8_t *B, size_t n, int32_t *d_is_inf) {
+  PA_ARGCHECK(ctx, ctx && B && d_is_inf && n < (1u << 26) && (n == 0 || (ots && beta)));
+  int rc = ensure(ctx, &ctx->d_aux, &ctx->aux_bytes, (n + 1) * 64);
+  if (rc) return rc;
+  if (n) {
+    if ((rc = work_reserve(ctx, n))) return rc;
+    PA_LAUNCH(ctx, PA_K_VAR, (k_ccs22_recv2_terms<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(ots, beta, work_jac(ctx), (int)n)));
+    if ((rc = normalize_to(ctx, ctx->d_aux, n))) return rc;
+  }
+  PA_CUDA(ctx, cudaMemcpyAsync(ctx->d_aux + 64 * n, B, 64, cudaMemcpyDeviceToDevice, ctx->stream));
+  return pa_point_sum_is_inf_dev(ctx, ctx->d_aux, nullptr, 1, n + 1, d_is_inf);
+}
+extern "C" int pa_ccs22_ot_recv2(pa_ctx *ctx, const uint8_t *ots, const uint8_t *beta, const uint8_t *B, size_t n, int *is_inf) {
+  PA_ARGCHECK(ctx, ctx && B && is_inf && (n == 0 || (ots && beta)));
+  int32_t flag = 0;
+  HArg a[] = {{ots, 0, n * 192}, {beta, 0, n * 32}, {B, 0, 64}, {0, &flag, 4}};
+  int rc = staged(ctx, a, 4, [&](unsigned char **p) { return pa_ccs22_ot_recv2_dev(ctx, p[0], p[1], p[2], n, (int32_t *)p[3]); });
+  *is_inf = flag;
+  return rc;
 }
 
 extern "C" int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job) {

@@ -21,6 +21,8 @@ struct pa_ctx {
   size_t stage_bytes = 0;
   unsigned char *d_pool = nullptr;  // state of the whole-auction runner (pa_seal_run)
   size_t pool_bytes = 0;
+  unsigned char *d_aux = nullptr;  // intermediate points of the composite CCS22 entry points
+  size_t aux_bytes = 0;
   // side lanes of the whole-auction runner: a stream with its own work arena each (created on first use)
   struct Lane {
     cudaStream_t stream = nullptr;
@@ -172,6 +174,7 @@ int pa_ctx_destroy(pa_ctx *ctx) {
   cudaFree(ctx->d_work);
   cudaFree(ctx->d_stage);
   cudaFree(ctx->d_pool);
+  cudaFree(ctx->d_aux);
   for (auto &l : ctx->lanes) {
     if (l.stream) cudaStreamDestroy(l.stream);
     cudaFree(l.work);

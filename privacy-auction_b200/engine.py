@@ -75,6 +75,12 @@ SIGNATURES = {
     "pa_rng_fill_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_seal_run": (ctypes.c_int, [_ctx, _vp]),
     "pa_ccs22_run": (ctypes.c_int, [_ctx, _vp]),
+    "pa_ccs22_commit": (ctypes.c_int, [_ctx, _vp, _sz] + [_vp] * 5 + [_sz]),
+    "pa_ccs22_commit_dev": (ctypes.c_int, [_ctx, _vp, _sz] + [_vp] * 5 + [_sz]),
+    "pa_ccs22_bes_encode": (ctypes.c_int, [_ctx, _vp, _sz] + [_vp] * 5 + [_sz]),
+    "pa_ccs22_bes_encode_dev": (ctypes.c_int, [_ctx, _vp, _sz] + [_vp] * 5 + [_sz]),
+    "pa_ccs22_ot_recv2": (ctypes.c_int, [_ctx, _vp, _vp, _vp, _sz, ctypes.POINTER(ctypes.c_int)]),
+    "pa_ccs22_ot_recv2_dev": (ctypes.c_int, [_ctx, _vp, _vp, _vp, _sz, _vp]),
     "pa_ccs22_ot_recv1": (ctypes.c_int, [_ctx] + [_vp] * 5 + [_sz]),
     "pa_ccs22_ot_recv1_dev": (ctypes.c_int, [_ctx] + [_vp] * 5 + [_sz]),
     "pa_ccs22_ot_send": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
@@ -455,6 +461,28 @@ class Engine:
         for name, buf in out.items():
             res[name[4:]] = bytes(buf)
         return res
+
+    def ccs22_commit(self, scalars, k, bid, R, params):
+        n = len(bid) // 32
+        H, com = bytearray(32 * n), bytearray(64 * n)
+        b = [_buf(x) for x in (scalars, bid, R, params, H, com)]
+        self._check(self.lib.pa_ccs22_commit(self.ctx, b[0][0], k, b[1][0], b[2][0], b[3][0], b[4][0], b[5][0], n))
+        return bytes(H), bytes(com)
+
+    def ccs22_bes_encode(self, X, ids, d, x, r):
+        n, m = len(X) // 64, len(ids)
+        ida = (ctypes.c_uint64 * max(m, 1))(*ids)
+        out = bytearray(64 * m)
+        b = [_buf(v) for v in (X, bytes(d), x, r, out)]
+        self._check(self.lib.pa_ccs22_bes_encode(self.ctx, b[0][0], n, ida, b[1][0], b[2][0], b[3][0], b[4][0], m))
+        return bytes(out)
+
+    def ccs22_ot_recv2(self, ots, beta, B):
+        n = len(beta) // 32
+        flag = ctypes.c_int(0)
+        b = [_buf(v) for v in (ots, beta, B)]
+        self._check(self.lib.pa_ccs22_ot_recv2(self.ctx, b[0][0], b[1][0], b[2][0], n, ctypes.byref(flag)))
+        return bool(flag.value)
 
     def ccs22_ot_recv1(self, k, beta, alpha, params):
         n = len(k) // 32

@@ -166,13 +166,9 @@ std::vector<Scalar> Bidder::draw256(size_t k) {
 
 // H = SHA256inSetup(hashed...) and Com = g^bid * g1^H + h^R          CCS22/bidder.cpp:80-88
 void Bidder::commit(const std::vector<Scalar> &hashed) {
-  pa_ctx *e = engine();
-  check(pa_ccs22_setup_hash(e, bytes(hashed), hashed.size(), H.b, 1), "pa_ccs22_setup_hash");
   Scalar bid = scalarOf(bid_);
-  Point t1, t2;
-  check(pa_double_mul(e, bid.b, pp.g1.b, H.b, t1.b, 1), "pa_double_mul");
-  check(pa_var_base_mul(e, pp.h.b, R.b, t2.b, 1), "pa_var_base_mul");
-  check(pa_point_add(e, t1.b, t2.b, Com.b, 1, 0), "pa_point_add");
+  Point params[2] = {pp.g1, pp.h};
+  check(pa_ccs22_commit(engine(), bytes(hashed), hashed.size(), bid.b, R.b, params[0].b, H.b, Com.b, 1), "pa_ccs22_commit");
 }
 
 // Reference: CCS22/bidder.cpp:48-89 — per bit x, r, s, t and X = g^x
@@ -196,15 +192,11 @@ void Bidder::setup() {
 
 // Reference: CCS22/bidder.cpp:118-147 — own Y (n-2 additions), B = Y^x or g^r
 void Bidder::BESEncodeInner(const std::vector<Point> &pk, size_t step) {
-  pa_ctx *e = engine();
   int bit = binaryBidStr[step] - '0';
   d = (inRaceFlag && bit == 1) ? 1 : 0;
-  std::vector<Point> Ys(n_);
-  check(pa_y_scan(e, bytes(pk), bytes(Ys), n_), "pa_y_scan");
-  if (d == 0)
-    check(pa_var_base_mul(e, Ys[id_].b, privKeys[step].x.b, B.b, 1), "pa_var_base_mul");
-  else
-    check(pa_fixed_base_mul(e, privKeys[step].r.b, B.b, 1), "pa_fixed_base_mul");
+  uint64_t id = id_;
+  uint8_t veto = (uint8_t)d;
+  check(pa_ccs22_bes_encode(engine(), bytes(pk), n_, &id, &veto, privKeys[step].x.b, privKeys[step].r.b, B.b, 1), "pa_ccs22_bes_encode");
 }
 void Bidder::BESEncode(const std::vector<Point> &pk, size_t step) {
   TimeTracker::getInstance().start(BIDDER_CATEGORY);
@@ -293,16 +285,8 @@ size_t Evaluator::OTReceive2(size_t step, const OT_S_VEC &ots) {
   } else {
     size_t nb = n_ - 1;
     assert(ots.size() == nb);
-    pa_ctx *e = engine();
-    std::vector<Point> z(nb), C0(nb), zb(nb), M0(nb + 1);
-    for (size_t j = 0; j < nb; ++j) z[j] = ots[j].z, C0[j] = ots[j].C0;
-    if (nb) {
-      check(pa_var_base_mul(e, bytes(z), bytes(randomBeta[step]), bytes(zb), nb), "pa_var_base_mul");
-      check(pa_point_add(e, bytes(C0), bytes(zb), bytes(M0), nb, 1), "pa_point_add");  // M0 = C0 * z^-beta
-    }
-    M0[nb] = B;
     int isInf = 1;
-    check(pa_point_sum_is_inf(e, bytes(M0), nb + 1, &isInf), "pa_point_sum_is_inf");
+    check(pa_ccs22_ot_recv2(engine(), (const uint8_t *)ots.data(), bytes(randomBeta[step]), B.b, nb, &isInf), "pa_ccs22_ot_recv2");
     if (!isInf) {
       inRaceFlag = false;
       maxBid |= ((size_t)1 << (c_ - step - 1));

@@ -131,3 +131,49 @@ def test_fused_ot_messages_match_oracle_composition(engine, oracle):
     want_s = b"".join(z[64 * i:64 * i + 64] + C0[64 * i:64 * i + 64] + C1[64 * i:64 * i + 64] for i in range(n))
     st = b"".join(s[32 * i:32 * i + 32] + t[32 * i:32 * i + 32] for i in range(n))
     assert engine.ccs22_ot_send(want_r1, params, B, st, m) == want_s
+
+
+@pytest.mark.gpu
+def test_commit_bes_encode_recv2_match_oracle_composition(engine, oracle):
+    """pa_ccs22_commit / pa_ccs22_bes_encode / pa_ccs22_ot_recv2 against the same steps composed from the
+    oracle's call shapes (CCS22/bidder.cpp:80-88, 118-147; evaluator.cpp:117-156)"""
+    import secp256k1_py as E
+    rnd = random.Random(616)
+    sc = lambda n: b"".join(rnd.getrandbits(256).to_bytes(32, "big") for _ in range(n))
+    cut = lambda b, i, w=64: b[w * i:w * i + w]
+    # commit: 5 parties, 12 hashed scalars each, one of them a bid of 0
+    n, k = 5, 12
+    hashed, R = sc(n * k), sc(n)
+    bids = [0, 1, 77, 2**31 - 1, 2**32 - 1]
+    bid = b"".join(v.to_bytes(32, "big") for v in bids)
+    gh = oracle.fixed_base_mul(sc(2 * n))
+    params = b"".join(cut(gh, i) + cut(gh, n + i) for i in range(n))
+    g1 = b"".join(cut(params, 2 * i) for i in range(n))
+    h = b"".join(cut(params, 2 * i + 1) for i in range(n))
+    H = oracle.ccs22_setup_hash(hashed, k)
+    com = oracle.point_add(oracle.double_mul(bid, g1, H), oracle.var_base_mul(h, R))
+    assert engine.ccs22_commit(hashed, k, bid, R, params) == (H, com)
+    # BESEncode: 9 public keys, every party once vetoing and once not, plus n = 1 (Y = infinity)
+    npk = 9
+    X = oracle.fixed_base_mul(sc(npk))
+    Y = oracle.y_scan(X)
+    ids = list(range(npk)) * 2
+    d = [0] * npk + [1] * npk
+    x, r = sc(2 * npk), sc(2 * npk)
+    want = b"".join(cut(oracle.fixed_base_mul(cut(r, i, 32)), 0) if d[i] else cut(oracle.var_base_mul(cut(Y, ids[i]), cut(x, i, 32)), 0)
+                    for i in range(2 * npk))
+    assert engine.ccs22_bes_encode(X, ids, d, x, r) == want
+    assert engine.ccs22_bes_encode(cut(X, 0), [0], [0], cut(x, 0, 32), cut(r, 0, 32)) == bytes(64)
+    # OTReceive2: sum of C0_j - beta_j z_j plus B; made to cancel exactly, then perturbed
+    m = 7
+    beta, zk, ck = sc(m), sc(m), sc(m)
+    z, C0 = oracle.fixed_base_mul(zk), oracle.fixed_base_mul(ck)
+    terms = oracle.point_add(C0, oracle.var_base_mul(z, beta), sub=True)
+    total = E.INF
+    for j in range(m):
+        total = E.add(total, E.dec64(cut(terms, j)))
+    ots = b"".join(cut(z, j) + cut(C0, j) + cut(C0, j) for j in range(m))
+    assert engine.ccs22_ot_recv2(ots, beta, E.enc64(E.neg(total))) is True
+    assert engine.ccs22_ot_recv2(ots, beta, E.enc64(total)) is False
+    assert engine.ccs22_ot_recv2(b"", b"", bytes(64)) is True          # n = 1 auction: no other party, B = infinity
+    assert engine.ccs22_ot_recv2(b"", b"", cut(z, 0)) is False
