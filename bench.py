@@ -219,7 +219,7 @@ def proof_throughput(eng, torch, n=1 << 15, seed=77):
     return out
 
 
-def seal_figures(eng, pa, rank, world, dist, torch):
+def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096):
     """Secondary figures (not the headline `value`): SEAL auctions through pa_seal_run.
       config4: ONE auction, n = 1000 bidders x 32-bit bids, sharded by bidder slice over the ranks
                (NCCL all-gather of X and b per step), every proof verified once;
@@ -274,7 +274,7 @@ def seal_figures(eng, pa, rank, world, dist, torch):
     out["config4_kernels_ms"] = {k: round(v["total_ms"], 3) for k, v in ks.items()}
 
     # config 5 sample: independent auctions, each rank its own batch
-    A = 4096
+    A = config5_auctions
     r5 = random.Random(5000 + rank)
     n5 = [r5.randint(1, 20) for _ in range(A)]
     c5 = [r5.randint(1, 32) for _ in range(A)]
@@ -355,6 +355,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_PER_KIND, help="scalar mults per kind per GPU per step (default 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-seal", action="store_true", help="skip the SEAL auction / proof-verify figures")
+    ap.add_argument("--config5-auctions", type=int, default=4096,
+                    help="genTests-style auctions per GPU in the config-5 figure (12500 per GPU on 8 GPUs = BASELINE's 10^5)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -459,7 +461,7 @@ def main():
     # ---- secondary figures of BASELINE.json's metric: proof-verifies/s and auctions/s --------------
     seal = None
     if not args.no_seal:
-        seal = seal_figures(eng, pa, rank, world, dist if world > 1 else None, torch)
+        seal = seal_figures(eng, pa, rank, world, dist if world > 1 else None, torch, args.config5_auctions)
 
     if rank == 0:
         var = kstats.get("k_var_base", {"launches": 1, "total_ms": float("nan")})
