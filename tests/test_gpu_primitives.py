@@ -130,3 +130,43 @@ def test_point_on_curve(engine, oracle):
     assert list(got) == want
     for i in range(64):
         assert bool(got[i]) == E.on_curve(E.dec64(bytes(p[64 * i:64 * i + 64]))) or i == 5
+
+
+def test_pipeline_chunk_boundaries(engine, oracle):
+    """Host-buffer calls above one pipeline chunk (148 x 128 x 20 items) are cut into a short head, whole
+    waves and a short tail; sizes around every boundary must give the same bytes as the oracle on a
+    sample and as the one-chunk path everywhere."""
+    unit = 148 * 128
+    rnd = random.Random(7)
+    base = [rnd.getrandbits(256) for _ in range(4096)]
+    for n in (20 * unit, 20 * unit + 1, 25 * unit - 1, 25 * unit + 3, 45 * unit + 77):
+        ks = (base * (n // len(base) + 1))[:n]
+        got = engine.fixed_base_mul(_b(ks))
+        one = engine.fixed_base_mul(_b(base))                     # single-chunk path
+        assert len(got) == 64 * n
+        for off in range(0, n, len(base)):
+            m = min(len(base), n - off)
+            assert got[64 * off:64 * (off + m)] == one[:64 * m], (n, off)
+    assert one[:64 * 64] == oracle.fixed_base_mul(_b(base[:64]))
+
+
+def test_two_contexts_and_argument_errors(pa, oracle):
+    """Contexts are independent (one per thread is the rule): two alive at once, calls interleaved.
+    Bad arguments come back as an error code with a message, not a crash."""
+    a, b = pa.Engine(0), pa.Engine(0)
+    try:
+        ks = _scalars(77, 300)
+        want = oracle.fixed_base_mul(_b(ks))
+        ra = a.fixed_base_mul(_b(ks))
+        pts = b.fixed_base_mul(_b(ks[::-1]))
+        assert ra == want and a.var_base_mul(pts, _b(ks)) == b.var_base_mul(pts, _b(ks)) == oracle.var_base_mul(pts, _b(ks))
+        import ctypes
+        rc = a.lib.pa_fixed_base_mul(a.ctx, None, None, 5)
+        assert rc < 0 and a.lib.pa_last_error(a.ctx)
+        out = ctypes.create_string_buffer(64)
+        off_curve = (5).to_bytes(32, "big") + (7).to_bytes(32, "big")
+        assert a.point_on_curve(off_curve + pts[:64]) == bytes([0, 1])
+        assert a.fixed_base_mul(_b(ks)) == want                     # still usable after an error
+    finally:
+        a.close()
+        b.close()
