@@ -287,7 +287,16 @@ typedef struct {
   uint64_t *max_bid;            /* [n_auctions] */
   uint8_t *ok;                  /* [n_auctions] 1 = every local verification held */
   uint8_t *out_commit, *out_commit_ok, *out_r1, *out_r1_ok, *out_r2_tag, *out_r2_b, *out_r2_proof, *out_r2_ok, *out_r3;
+  /* How the steps are scheduled; the results are the same bytes either way.
+   *   step-major:  one batched kernel sequence per protocol step (any batch, any sharding);
+   *   phase-major: ONE unsharded auction - keys, Y and both cryptogram candidates of every step in
+   *                three large launches, the step-by-step decisions by one thread block on the
+   *                device, then all proofs of all steps in one batch per kind (a single auction is
+   *                otherwise a chain of lone-warp latencies, ~2 ms per step whatever n is).
+   * 0 picks phase-major where it applies. */
+  int schedule;
 } pa_seal_job;
+enum { PA_SEAL_AUTO = 0, PA_SEAL_STEP_MAJOR = 1, PA_SEAL_PHASE_MAJOR = 2 };
 int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job);
 
 /* pa_ccs22_run: the same for the CCS22 protocol (CCS22/main.cpp:16-130): every party of a batch of

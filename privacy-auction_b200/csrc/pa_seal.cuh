@@ -147,6 +147,128 @@ __global__ void k_seal_scatter_u8(const u32 *g, const unsigned char *src, unsign
   if (i < n) dst[g[i]] = src[i];
 }
 
+// ---- single-auction schedule ("phase-major") ------------------------------------------------------
+// One auction advanced step by step is a chain of lone-warp latencies: keys -> Y scan -> cryptogram ->
+// round three cost ~2 ms per step whatever n is.  But the keys of ALL steps depend only on the draw
+// counters, the Y of all steps only on the keys, and the cryptogram of a bidder is one of two values,
+// Y^x or R^x, whichever the auction state selects.  So for one auction the runner computes keys, Y and
+// BOTH candidates for every step in three large launches, lets one thread block walk through the
+// steps (select, sum, is-infinity, update the state) without the host, and then proves and verifies
+// the proofs of all steps in one batch per kind.  Item i = step * m + bidder.
+
+// both candidates of every item: cand[2i] = Y^x (no veto), cand[2i+1] = R^x (veto)    SEAL/bidder.cpp:1301-1309
+__global__ void __launch_bounds__(PA_BLOCK, PA_VAR_MINBLOCKS)
+k_seal_candidates(const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1, u32 *jout, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n) return;
+  int which = t / n, i = t % n;
+  jac P, r;
+  sc x;
+  ld_point_jac(P, which ? r1 + 320 * (size_t)i + 64 : Y + 64 * (size_t)i);
+  ld_sc(x, rnd1 + 128 * (size_t)i);
+  var_base_mul(r, P, x);
+  st_jac(jout + 24 * ((size_t)i * 2 + which), r);
+}
+
+// state[0] = junction flag, state[1] = previous deciding step (-1: none), state[2] = next step to run.
+// Walks steps [state[2], limit).  While `speculative` the keys were drawn on the assumption that no
+// junction has happened; they stay valid up to and including the step after the first deciding step
+// (its draws come after stage-1 proofs only), so the walk stops there.        SEAL/bidder.cpp:1301-1309, 1386-1421
+__global__ void __launch_bounds__(PA_SCAN_T)
+k_seal_decide(int m, int limit, int speculative, const unsigned char *bits, const u32 *boff, const unsigned char *cand,
+              unsigned char *prevbit, int *state, unsigned char *ebit, unsigned char *bj, unsigned char *b, int *stage,
+              int *prevstep, int *r3) {
+  __shared__ __align__(16) u32 part[PA_SCAN_T][24];
+  __shared__ int s_junc, s_last, s_deciding;
+  int t = threadIdx.x;
+  if (t == 0) s_junc = state[0], s_last = state[1];
+  __syncthreads();
+  int s = state[2];
+  for (; s < limit; ++s) {
+    int junc = s_junc;
+    jac acc;
+    jac_set_inf(acc);
+    for (int p = t; p < m; p += PA_SCAN_T) {
+      size_t i = (size_t)s * m + p;
+      int bit = bits[boff[p] + s];
+      int pb = prevbit[p];
+      int veto = bit && (!junc || pb);
+      ebit[i] = (unsigned char)veto;
+      bj[i] = (unsigned char)pb;
+      const unsigned char *src = cand + 64 * (2 * i + veto);
+      cp64(b + 64 * i, src);
+      aff x;
+      ld_aff(x, src);
+      jac_madd(acc, acc, x);
+    }
+    st_jac(part[t], acc);
+    __syncthreads();
+    for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
+      if (t < d) {
+        jac a, c;
+        ld_jac(a, part[t]);
+        ld_jac(c, part[t + d]);
+        jac_add(a, a, c);
+        st_jac(part[t], a);
+      }
+      __syncthreads();
+    }
+    if (t == 0) {
+      jac a;
+      ld_jac(a, part[0]);
+      s_deciding = jac_is_inf(a) ? 0 : 1;
+      stage[s] = junc ? 2 : 1;
+      prevstep[s] = s_last;
+      r3[s] = s_deciding;
+    }
+    __syncthreads();
+    bool stop = false;
+    if (s_deciding) {
+      for (int p = t; p < m; p += PA_SCAN_T) prevbit[p] &= bits[boff[p] + s];
+      if (speculative && !junc) stop = true;  // first deciding step: one more step is still valid
+      __syncthreads();
+      if (t == 0) s_junc = 1, s_last = s;
+    }
+    __syncthreads();
+    if (stop && limit > s + 2) limit = s + 2;
+  }
+  if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
+}
+
+// statements and witnesses of the round-two proofs of every item; stage-1 items are the first n1
+__global__ void k_seal_stmt_items(int m, int n1, const int *stage, const int *prevstep, const u32 *boff, const unsigned char *b,
+                                  const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1,
+                                  const unsigned char *crec, const unsigned char *rndc, const unsigned char *ebit,
+                                  const unsigned char *bjv, unsigned char *stmt1, unsigned char *sec1, unsigned char *bi1,
+                                  unsigned char *stmt2, unsigned char *sec2, unsigned char *bi2, unsigned char *bj2, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int s = i / m, p = i % m;
+  size_t cs = (size_t)boff[p] + s;
+  const unsigned char *X = r1 + 320 * (size_t)i, *R = X + 64, *c = crec + 736 * cs;
+  if (stage[s] == 1) {
+    size_t q = i;
+    unsigned char *o = stmt1 + 448 * q;
+    cp64(o, b + 64 * (size_t)i); cp64(o + 64, X); cp64(o + 128, Y + 64 * (size_t)i); cp64(o + 192, R);
+    cp64(o + 256, c); cp64(o + 320, c + 64); cp64(o + 384, c + 128);
+    cp32(sec1 + 64 * q, rnd1 + 128 * (size_t)i);
+    cp32(sec1 + 64 * q + 32, rndc + 224 * cs);
+    bi1[q] = ebit[i];
+  } else {
+    size_t q = (size_t)i - n1, j = (size_t)prevstep[s] * m + p;  // the same bidder at the previous deciding step
+    unsigned char *o = stmt2 + 704 * q;
+    cp64(o, b + 64 * (size_t)i); cp64(o + 64, X); cp64(o + 128, R);
+    cp64(o + 192, b + 64 * j); cp64(o + 256, r1 + 320 * j); cp64(o + 320, r1 + 320 * j + 64);
+    cp64(o + 384, c); cp64(o + 448, c + 64); cp64(o + 512, c + 128);
+    cp64(o + 576, Y + 64 * (size_t)i); cp64(o + 640, Y + 64 * j);
+    cp32(sec2 + 96 * q, rnd1 + 128 * (size_t)i);
+    cp32(sec2 + 96 * q + 32, rnd1 + 128 * j);
+    cp32(sec2 + 96 * q + 64, rndc + 224 * cs);
+    bi2[q] = ebit[i];
+    bj2[q] = bjv[i];
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
 
@@ -218,6 +340,9 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   const bool sharded = job->allgather != nullptr;
   PA_ARGCHECK(ctx, !sharded || (A == 1 && job->hi > job->lo && job->hi <= job->n[0] && job->d_send && job->d_recv && job->slice >= job->hi - job->lo));
   const bool verify = job->verify != 0;
+  // one unsharded auction: phase-major schedule unless the caller asks for the step-major one
+  bool phased = A == 1 && !sharded && job->schedule != PA_SEAL_STEP_MAJOR;
+  PA_ARGCHECK(ctx, job->schedule != PA_SEAL_PHASE_MAJOR || phased);
   const bool want_r1 = job->out_r1 != nullptr, want_b = job->out_r2_b != nullptr, want_proof = job->out_r2_proof != nullptr;
   int rc;
   if ((rc = lanes_init(ctx))) return rc;
@@ -256,8 +381,28 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   u32 *d_boff;
   u64 *d_ids, *d_streams, *d_ctr, *d_cid, *d_sstream, *d_sctr;
   StepBufs SB[2];
+  struct Phased {  // arrays over all items i = step * m + bidder of the single-auction schedule
+    u64 *istream, *ictr, *pid;
+    u32 *soff;
+    int *stage, *prevstep, *r3, *state;
+    unsigned char *rnd1, *r1, *pokv, *r1ok, *Y, *cand, *b, *ebit, *bj, *stmt, *sec, *bi, *bjp, *rnd2, *proof, *r2ok;
+  } PH{};
+  const size_t T = phased ? cmax * m : 0;
   const size_t nY = sharded ? (size_t)job->n[0] : m;
   auto carve = [&](DevPool &pool) {
+    if (phased) {
+      PH.istream = pool.alloc<u64>(T); PH.ictr = pool.alloc<u64>(T); PH.pid = pool.alloc<u64>(T);
+      PH.soff = pool.alloc<u32>(cmax + 1);
+      PH.stage = pool.alloc<int>(cmax); PH.prevstep = pool.alloc<int>(cmax); PH.r3 = pool.alloc<int>(cmax); PH.state = pool.alloc<int>(4);
+      PH.rnd1 = pool.alloc<unsigned char>(T * 128); PH.r1 = pool.alloc<unsigned char>(T * 320);
+      PH.pokv = pool.alloc<unsigned char>(T * 2); PH.r1ok = pool.alloc<unsigned char>(T);
+      PH.Y = pool.alloc<unsigned char>(T * 64); PH.cand = pool.alloc<unsigned char>(T * 128); PH.b = pool.alloc<unsigned char>(T * 64);
+      PH.ebit = pool.alloc<unsigned char>(T); PH.bj = pool.alloc<unsigned char>(T);
+      PH.stmt = pool.alloc<unsigned char>(T * 704 + 256); PH.sec = pool.alloc<unsigned char>(T * 96 + 256);
+      PH.bi = pool.alloc<unsigned char>(T + 256); PH.bjp = pool.alloc<unsigned char>(T + 256);
+      PH.rnd2 = pool.alloc<unsigned char>(T * 352 + 256); PH.proof = pool.alloc<unsigned char>(T * 1344 + 256);
+      PH.r2ok = pool.alloc<unsigned char>(T + 256);
+    }
     d_bits = pool.alloc<unsigned char>(Mb);
     d_boff = pool.alloc<u32>(m + 1);
     d_ids = pool.alloc<u64>(m);
@@ -345,6 +490,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       bool clean = true;
       for (u32 k = boff[s]; k < boff[s + 1]; ++k) clean &= after[k] == sctr[k] + 7;
       u64 cnt = 7ull * (boff[s + 1] - boff[s]);
+      if (!clean) phased = false;  // a rejected draw (probability 2^-128): counters are no longer arithmetic
       if (!clean) {
         u64 zero = 0;
         PA_CUDA(ctx, cudaMemcpyAsync(d_ctr + s, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -373,6 +519,124 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     if (job->out_commit_ok) memcpy(job->out_commit_ok, cv.data(), Mb);
     for (size_t s = 0; s < m; ++s)
       for (u32 k = boff[s]; k < boff[s + 1]; ++k) okv[auc[s]] &= cv[k];
+  }
+
+  // ================= single auction, phase-major schedule ==============================================
+  if (phased) {
+    const size_t c = cmax;
+    // Draw counters are arithmetic: 7 per committed bit, then per step 4 (x, r, v_X, v_R) and 5 (stage 1)
+    // or 11 (stage 2).  Stage 2 starts the step after the first deciding step J.
+    const u64 base = 7ull * c;
+    auto key_ctr = [&](size_t s, long J) -> u64 {  // J < 0: no deciding step before s
+      if (J < 0 || s <= (size_t)J + 1) return base + 9ull * s;
+      return base + 9ull * ((size_t)J + 1) + 15ull * (s - (size_t)J - 1);
+    };
+    {
+      std::vector<u32> soff(c + 1);
+      for (size_t k = 0; k <= c; ++k) soff[k] = (u32)(k * m);
+      std::vector<u64> pid(T);
+      for (size_t i = 0; i < T; ++i) pid[i] = ids[i % m];
+      int st0[4] = {0, -1, 0, 0};
+      if ((rc = up(ctx, PH.soff, soff)) || (rc = up(ctx, PH.pid, pid))) return rc;
+      PA_CUDA(ctx, cudaMemcpyAsync(PH.state, st0, sizeof st0, cudaMemcpyHostToDevice, ctx->stream));
+      PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // st0 / vectors go out of scope
+    }
+    std::vector<u64> istream(T), ictr(T), after(T);
+    // keys, Y and both cryptogram candidates of steps [s0, c), then the walk through those steps
+    auto run_steps = [&](size_t s0, long J, int speculative) -> int {
+      const size_t i0 = s0 * m, cnt = (c - s0) * m;
+      for (size_t i = i0; i < T; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, J);
+      PA_CUDA(ctx, cudaMemcpyAsync(PH.istream + i0, istream.data() + i0, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpyAsync(PH.ictr + i0, ictr.data() + i0, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
+      PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream + i0, PH.ictr + i0, nullptr, 4, PH.rnd1 + 128 * i0, (int)cnt)));
+      PA_CUDA(ctx, cudaMemcpyAsync(after.data() + i0, PH.ictr + i0, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      int rc2;
+      if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
+      PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
+      if ((rc2 = normalize_to(ctx, PH.r1 + 320 * i0, 2 * cnt, 2, 320))) return rc2;
+      PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(c - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
+      if ((rc2 = normalize_to(ctx, PH.Y + 64 * i0, cnt))) return rc2;
+      PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1 + 320 * i0, PH.Y + 64 * i0, PH.rnd1 + 128 * i0, work_jac(ctx), (int)cnt)));
+      if ((rc2 = normalize_to(ctx, PH.cand + 128 * i0, 2 * cnt))) return rc2;
+      PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)c, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
+      return PA_OK;
+    };
+    int st[4];
+    if ((rc = run_steps(0, -1, 1))) return rc;
+    PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool clean = true;
+    for (size_t i = 0; i < T; ++i) clean &= after[i] == ictr[i] + 4;
+    long J = -1;
+    if ((size_t)st[2] < c) {  // stopped one step after the first deciding step: redo the rest on the stage-2 counters
+      J = (long)st[2] - 2;
+      const size_t s0 = (size_t)st[2];
+      if ((rc = run_steps(s0, J, 0))) return rc;
+      PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+      PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (size_t i = s0 * m; i < T; ++i) clean &= after[i] == ictr[i] + 4;
+    }
+    std::vector<int> stage(c), r3(c);
+    PA_CUDA(ctx, cudaMemcpyAsync(stage.data(), PH.stage, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PA_CUDA(ctx, cudaMemcpyAsync(r3.data(), PH.r3, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (J < 0)
+      for (size_t s2 = 0; s2 < c; ++s2)
+        if (r3[s2]) { J = (long)s2; break; }  // a junction in the last two steps never triggers the second pass
+    size_t c1 = c;  // stage-1 steps: 0 .. J
+    for (size_t s2 = 0; s2 < c; ++s2)
+      if (stage[s2] == 2) { c1 = s2; break; }
+    const size_t n1 = c1 * m, n2 = T - n1;
+    const size_t o_stmt = align_up(n1 * 448, 256), o_sec = align_up(n1 * 64, 256), o_b = align_up(n1, 256),
+                 o_rnd = align_up(n1 * 160, 256), o_proof = align_up(n1 * 672, 256);
+    // ---- Schnorr proofs of X and R for every item, one batch ------------------------------------------
+    if ((rc = prove_dev<PA_POK>(ctx, PH.r1, PH.rnd1, nullptr, nullptr, PH.pid, PH.rnd1 + 64, PH.r1 + 128, 2 * T, LR2))) return rc;
+    if (verify) {
+      if ((rc = verify_dev<PA_POK, 1>(ctx, PH.r1 + 128, PH.r1, PH.pid, PH.pokv, 2 * T, LR2))) return rc;
+      PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(PH.pokv, nullptr, PH.r1ok, (int)T)));
+    } else {
+      PA_CUDA(ctx, cudaMemsetAsync(PH.r1ok, 1, T, ctx->stream));
+    }
+    // ---- round-two proofs: statements, draws (right after the four key draws), prove, verify -----------------
+    PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt_items<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>((int)m, (int)n1, PH.stage, PH.prevstep, d_boff, PH.b, PH.r1, PH.Y, PH.rnd1, d_crec, d_rndc, PH.ebit, PH.bj, PH.stmt, PH.sec, PH.bi, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, (int)T)));
+    for (size_t i = 0; i < T; ++i) ictr[i] = key_ctr(i / m, J) + 4, istream[i] = streams[i % m];
+    PA_CUDA(ctx, cudaMemcpyAsync(PH.istream, istream.data(), T * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PA_CUDA(ctx, cudaMemcpyAsync(PH.ictr, ictr.data(), T * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n1) PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream, PH.ictr, nullptr, 5, PH.rnd2, (int)n1)));
+    if (n2) PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream + n1, PH.ictr + n1, nullptr, 11, PH.rnd2 + o_rnd, (int)n2)));
+    PA_CUDA(ctx, cudaMemcpyAsync(after.data(), PH.ictr, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n1 && (rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
+    if (n2 && (rc = prove_dev<PA_S2>(ctx, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.pid + n1, PH.rnd2 + o_rnd, PH.proof + o_proof, n2))) return rc;
+    if (verify) {
+      if (n1 && (rc = verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1))) return rc;
+      if (n2 && (rc = verify_dev<PA_S2, 16>(ctx, PH.proof + o_proof, PH.stmt + o_stmt, PH.pid + n1, PH.r2ok + n1, n2))) return rc;
+    } else {
+      PA_CUDA(ctx, cudaMemsetAsync(PH.r2ok, 1, T, ctx->stream));
+    }
+    // ---- results ---------------------------------------------------------------------------------------------
+    std::vector<unsigned char> r1ok(T), r2ok(T);
+    PA_CUDA(ctx, cudaMemcpyAsync(r1ok.data(), PH.r1ok, T, cudaMemcpyDeviceToHost, ctx->stream));
+    PA_CUDA(ctx, cudaMemcpyAsync(r2ok.data(), PH.r2ok, T, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_r1) PA_CUDA(ctx, cudaMemcpyAsync(job->out_r1, PH.r1, T * 320, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_b) PA_CUDA(ctx, cudaMemcpyAsync(job->out_r2_b, PH.b, T * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_proof) {
+      if (n1) PA_CUDA(ctx, cudaMemcpy2DAsync(job->out_r2_proof, 1344, PH.proof, 672, 672, n1, cudaMemcpyDeviceToHost, ctx->stream));
+      if (n2) PA_CUDA(ctx, cudaMemcpyAsync(job->out_r2_proof + n1 * 1344, PH.proof + o_proof, n2 * 1344, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < T; ++i) clean &= after[i] == ictr[i] + (i < n1 ? 5 : 11);
+    if (!clean) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: a draw was rejected (probability 2^-128); rerun with schedule = PA_SEAL_STEP_MAJOR");
+    for (size_t i = 0; i < T; ++i) okv[0] &= r1ok[i] & r2ok[i];
+    if (job->out_r1_ok) memcpy(job->out_r1_ok, r1ok.data(), T);
+    if (job->out_r2_ok) memcpy(job->out_r2_ok, r2ok.data(), T);
+    for (size_t s2 = 0; s2 < c; ++s2) {
+      if (job->out_r2_tag) memset(job->out_r2_tag + s2 * m, stage[s2], m);
+      if (job->out_r3) job->out_r3[s2] = r3[s2] ? 1 : 0;
+      if (r3[s2]) maxbid[0] |= (u64)1 << (c - s2 - 1);  // SEAL/bidder.cpp:1403, 64-bit shift
+    }
+    if (job->max_bid) job->max_bid[0] = maxbid[0];
+    if (job->ok) job->ok[0] = okv[0];
+    return PA_OK;
   }
 
   // ================= auction steps =====================================================

@@ -112,6 +112,7 @@ class SealJob(ctypes.Structure):
         ("out_commit", ctypes.c_void_p), ("out_commit_ok", ctypes.c_void_p), ("out_r1", ctypes.c_void_p),
         ("out_r1_ok", ctypes.c_void_p), ("out_r2_tag", ctypes.c_void_p), ("out_r2_b", ctypes.c_void_p),
         ("out_r2_proof", ctypes.c_void_p), ("out_r2_ok", ctypes.c_void_p), ("out_r3", ctypes.c_void_p),
+        ("schedule", ctypes.c_int),
     ]
 
 
@@ -380,7 +381,7 @@ class Engine:
         self._check(self.lib.pa_rng_fill(self.ctx, seed, b[0][0], b[1][0], per_item, b[2][0], n))
         return bytes(out), list(struct.unpack(f"<{n}Q", bytes(ctr)))
 
-    def seal_run(self, seed, n, c, bids, verify=True, sections=False, auction_ids=None, shard=None):
+    def seal_run(self, seed, n, c, bids, verify=True, sections=False, auction_ids=None, shard=None, schedule=0):
         """pa_seal_run: whole SEAL auctions, device resident.
         n, c: per-auction lists; bids: flat list of the LOCAL bidders' bids (auction-major).
         shard = dict(lo, hi, slice, d_send, d_recv, allgather=callable(which) -> 0) for one
@@ -401,6 +402,7 @@ class Engine:
             job.auction_ids = ctypes.addressof(aid)
             keep.append(aid)
         job.verify = 1 if verify else 0
+        job.schedule = schedule   # 0 auto, 1 step-major, 2 phase-major (one unsharded auction)
         job.max_bid, job.ok = ctypes.addressof(max_bid), ctypes.addressof(ok)
         cb = None
         if shard is not None:

@@ -209,11 +209,12 @@ def test_prove_verify_parity_and_tampering(engine, oracle, kind):
 
 
 # ---- the device-resident whole-auction runner (pa_seal_run) ---------------------------------
+@pytest.mark.parametrize("schedule", [1, 2], ids=["step-major", "phase-major"])
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
-def test_runner_reproduces_reference_transcript(engine, path):
+def test_runner_reproduces_reference_transcript(engine, path, schedule):
     gold = open(path, "rb").read()
     t = seal_flow.parse_transcript(gold)
-    res = engine.seal_run(t["seed"], [t["n"]], [t["c"]], t["bids"], verify=True, sections=True)
+    res = engine.seal_run(t["seed"], [t["n"]], [t["c"]], t["bids"], verify=True, sections=True, schedule=schedule)
     assert res["max_bid"] == [max(t["bids"])] and res["ok"] == [True]
     assert seal_flow.sections_to_transcripts(t["seed"], [t["n"]], [t["c"]], t["bids"], res)[0] == gold
 
@@ -242,18 +243,38 @@ def test_runner_batch_of_ragged_auctions_matches_oracle(engine, oracle):
         assert got[a] == want, f"auction {a} (n={n[a]}, c={c[a]})"
 
 
-def test_runner_32_bit_bids(engine):
+@pytest.mark.parametrize("schedule", [1, 2], ids=["step-major", "phase-major"])
+def test_runner_32_bit_bids(engine, schedule):
     """c = 32 with the top bit set: the reference cannot run this"""
     bids = [0x80000001, 0xFFFFFFFF, 0x7FFFFFFF, 5]
-    res = engine.seal_run(3, [4], [32], bids, verify=True)
+    res = engine.seal_run(3, [4], [32], bids, verify=True, schedule=schedule)
     assert res["ok"] == [True] and res["max_bid"] == [0xFFFFFFFF]
+
+
+def test_runner_schedules_agree(engine):
+    """The phase-major schedule of a single auction publishes the same bytes as the step-major one: junction at
+    the first, a middle, the second-to-last and the last step, never (all bids 0), and one bidder alone."""
+    rnd = random.Random(88)
+    cases = [(7, 9, None), (5, 8, 0x80), (6, 8, 0x02), (6, 8, 0x01), (4, 6, 0), (1, 5, 0x15), (40, 16, None), (3, 1, 1), (3, 2, 2)]
+    for n, c, top in cases:
+        bids = [rnd.randrange(1 << c) for _ in range(n)] if top is None else [rnd.randrange(top + 1) if top else 0 for _ in range(n)]
+        if top:
+            bids[rnd.randrange(n)] = top
+        a = engine.seal_run(500 + n, [n], [c], bids, verify=True, sections=True, schedule=1)
+        b = engine.seal_run(500 + n, [n], [c], bids, verify=True, sections=True, schedule=2)
+        assert a["ok"] == b["ok"] == [True] and a["max_bid"] == b["max_bid"] == [max(bids)], (n, c, bids)
+        ta = seal_flow.sections_to_transcripts(500 + n, [n], [c], bids, a)[0]
+        tb = seal_flow.sections_to_transcripts(500 + n, [n], [c], bids, b)[0]
+        assert ta == tb, (n, c, bids)
 
 
 def test_runner_matches_oracle_n64_c12(engine, oracle):
     """a mid-size auction (64 bidders x 12 bits, ~67 k scalar mults on the oracle's single core)"""
     rnd = random.Random(6412)
     bids = [rnd.randrange(1 << 12) for _ in range(64)]
-    res = engine.seal_run(64012, [64], [12], bids, verify=True, sections=True)
-    got = seal_flow.sections_to_transcripts(64012, [64], [12], bids, res)[0]
     fl = seal_flow.SealFlow(oracle, 64, 12, 64012, bids)
-    assert got == fl.run() and fl.ok and res["ok"] == [True] and res["max_bid"] == [max(bids)]
+    want = fl.run()
+    for schedule in (1, 2):
+        res = engine.seal_run(64012, [64], [12], bids, verify=True, sections=True, schedule=schedule)
+        got = seal_flow.sections_to_transcripts(64012, [64], [12], bids, res)[0]
+        assert got == want and fl.ok and res["ok"] == [True] and res["max_bid"] == [max(bids)], schedule
