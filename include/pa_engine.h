@@ -269,7 +269,7 @@ int pa_rng_fill256_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *d_streams, ui
  *   out_r2_b      [cmax x m x 64]   out_r2_proof [cmax x m x 1344] (stage 1 uses 672)
  *   out_r3        [cmax x n_auctions]  1 = deciding step
  * tests/seal_flow.py turns sections into the PASEALT1 transcript. */
-typedef int (*pa_allgather_fn)(void *user, int which /* 0: X of round one, 1: b of round two */);
+typedef int (*pa_allgather_fn)(void *user, int which /* 0: X of round one, 1: b of round two (slice * 64 bytes each); 2, 3: see `schedule` */);
 typedef struct {
   uint64_t seed;
   size_t n_auctions;
@@ -293,8 +293,14 @@ typedef struct {
    *                three large launches, the step-by-step decisions by one thread block on the
    *                device, then all proofs of all steps in one batch per kind (a single auction is
    *                otherwise a chain of lone-warp latencies, ~2 ms per step whatever n is).
+   *                A sharded auction can use it too when the exchange buffers are large enough
+   *                (xchg_bytes >= max(c * slice * 64, 128)): allgather(user, 2) then exchanges the
+   *                first c * slice * 64 bytes of d_send (the X of all steps) and allgather(user, 3)
+   *                the first 128 bytes (a rank's partial sum of one step's cryptograms), each into
+   *                d_recv at that stride; one `2` per pass (at most two) and one `3` per step.
    * 0 picks phase-major where it applies. */
   int schedule;
+  size_t xchg_bytes;            /* capacity of d_send; d_recv holds world times as much (0: slice * 64) */
 } pa_seal_job;
 enum { PA_SEAL_AUTO = 0, PA_SEAL_STEP_MAJOR = 1, PA_SEAL_PHASE_MAJOR = 2 };
 int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job);

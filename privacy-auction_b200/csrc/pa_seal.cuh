@@ -269,6 +269,82 @@ __global__ void k_seal_stmt_items(int m, int n1, const int *stage, const int *pr
   }
 }
 
+// ---- the same schedule with the auction sharded by bidder slice ---------------------------------------
+// dst[i] = src[idx[i]], 64-byte items
+__global__ void k_seal_gather64(unsigned char *dst, const unsigned char *src, const u32 *idx, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cp64(dst + 64 * (size_t)i, src + 64 * (size_t)idx[i]);
+}
+// send[(s * slice + p) * 64] = X of local item (s, p), steps [s0, c)
+__global__ void k_seal_pack_x(const unsigned char *r1, unsigned char *send, int m, int slice, int s0, int n) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int s = s0 + k / m, p = k % m;
+  cp64(send + 64 * ((size_t)s * slice + p), r1 + 320 * ((size_t)s * m + p));
+}
+// One step of the walk when every rank holds a slice: first fold the ranks' partial sums of step s - 1
+// (Jacobian, 128 bytes apart in `recv`) into the auction state, then select this rank's cryptograms of
+// step s and leave their sum in `send`.  s == limit only folds.
+__global__ void __launch_bounds__(PA_SCAN_T)
+k_seal_decide_shard(int s, int m, int limit, int world, const unsigned char *bits, const u32 *boff, const unsigned char *cand,
+                    unsigned char *prevbit, int *state, unsigned char *ebit, unsigned char *bj, unsigned char *b, int *stage,
+                    int *prevstep, int *r3, const u32 *recv, u32 *send) {
+  __shared__ __align__(16) u32 part[PA_SCAN_T][24];
+  __shared__ int s_junc, s_last, s_deciding;
+  int t = threadIdx.x;
+  if (t == 0) {
+    s_junc = state[0], s_last = state[1], s_deciding = 0;
+    if (s > 0) {
+      jac a;
+      jac_set_inf(a);
+      for (int r = 0; r < world; ++r) {
+        jac c;
+        ld_jac(c, recv + 32 * (size_t)r);
+        jac_add(a, a, c);
+      }
+      s_deciding = jac_is_inf(a) ? 0 : 1;
+      r3[s - 1] = s_deciding;
+      if (s_deciding) s_junc = 1, s_last = s - 1;
+    }
+  }
+  __syncthreads();
+  if (s_deciding)
+    for (int p = t; p < m; p += PA_SCAN_T) prevbit[p] &= bits[boff[p] + s - 1];
+  if (s < limit) {
+    int junc = s_junc;
+    jac acc;
+    jac_set_inf(acc);
+    for (int p = t; p < m; p += PA_SCAN_T) {
+      size_t i = (size_t)s * m + p;
+      int bit = bits[boff[p] + s];
+      int pb = prevbit[p];
+      int veto = bit && (!junc || pb);
+      ebit[i] = (unsigned char)veto;
+      bj[i] = (unsigned char)pb;
+      const unsigned char *src = cand + 64 * (2 * i + veto);
+      cp64(b + 64 * i, src);
+      aff x;
+      ld_aff(x, src);
+      jac_madd(acc, acc, x);
+    }
+    st_jac(part[t], acc);
+    __syncthreads();
+    for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
+      if (t < d) {
+        jac a, c;
+        ld_jac(a, part[t]);
+        ld_jac(c, part[t + d]);
+        jac_add(a, a, c);
+        st_jac(part[t], a);
+      }
+      __syncthreads();
+    }
+    if (t < 32) send[t] = t < 24 ? part[0][t] : 0u;
+    if (t == 0) stage[s] = junc ? 2 : 1, prevstep[s] = s_last;
+  }
+  if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
 
@@ -341,7 +417,9 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   PA_ARGCHECK(ctx, !sharded || (A == 1 && job->hi > job->lo && job->hi <= job->n[0] && job->d_send && job->d_recv && job->slice >= job->hi - job->lo));
   const bool verify = job->verify != 0;
   // one unsharded auction: phase-major schedule unless the caller asks for the step-major one
-  bool phased = A == 1 && !sharded && job->schedule != PA_SEAL_STEP_MAJOR;
+  // (sharded: the exchange buffers must hold the X of all steps, and a Jacobian partial sum)
+  bool phased = A == 1 && job->schedule != PA_SEAL_STEP_MAJOR &&
+                (!sharded || (job->xchg_bytes >= (size_t)job->c[0] * job->slice * 64 && job->xchg_bytes >= 128));
   PA_ARGCHECK(ctx, job->schedule != PA_SEAL_PHASE_MAJOR || phased);
   const bool want_r1 = job->out_r1 != nullptr, want_b = job->out_r2_b != nullptr, want_proof = job->out_r2_proof != nullptr;
   int rc;
@@ -386,9 +464,12 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     u32 *soff;
     int *stage, *prevstep, *r3, *state;
     unsigned char *rnd1, *r1, *pokv, *r1ok, *Y, *cand, *b, *ebit, *bj, *stmt, *sec, *bi, *bjp, *rnd2, *proof, *r2ok;
+    unsigned char *Xall, *Yall, *part;  // sharded: every bidder's X / Y of every step; the ranks' partial sums of a step
+    u32 *gidx, *lidx, *soffN;
   } PH{};
+  const size_t nall = job->n[0];
   const size_t T = phased ? cmax * m : 0;
-  const size_t nY = sharded ? (size_t)job->n[0] : m;
+  const size_t nY = sharded ? nall : m;
   auto carve = [&](DevPool &pool) {
     if (phased) {
       PH.istream = pool.alloc<u64>(T); PH.ictr = pool.alloc<u64>(T); PH.pid = pool.alloc<u64>(T);
@@ -402,6 +483,11 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PH.bi = pool.alloc<unsigned char>(T + 256); PH.bjp = pool.alloc<unsigned char>(T + 256);
       PH.rnd2 = pool.alloc<unsigned char>(T * 352 + 256); PH.proof = pool.alloc<unsigned char>(T * 1344 + 256);
       PH.r2ok = pool.alloc<unsigned char>(T + 256);
+      if (sharded) {
+        PH.Xall = pool.alloc<unsigned char>(cmax * nall * 64); PH.Yall = pool.alloc<unsigned char>(cmax * nall * 64);
+        PH.gidx = pool.alloc<u32>(cmax * nall); PH.lidx = pool.alloc<u32>(T); PH.soffN = pool.alloc<u32>(cmax + 1);
+        PH.part = pool.alloc<unsigned char>(((nall + job->slice - 1) / job->slice) * 128);
+      }
     }
     d_bits = pool.alloc<unsigned char>(Mb);
     d_boff = pool.alloc<u32>(m + 1);
@@ -554,27 +640,76 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
       PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.r1 + 320 * i0, 2 * cnt, 2, 320))) return rc2;
-      PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(c - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
-      if ((rc2 = normalize_to(ctx, PH.Y + 64 * i0, cnt))) return rc2;
+      if (!sharded) {
+        PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(c - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
+        if ((rc2 = normalize_to(ctx, PH.Y + 64 * i0, cnt))) return rc2;
+      } else {
+        // one exchange for the X of all remaining steps: rank r's block is [step][position in slice]
+        const size_t cn = (c - s0) * nall;
+        PA_CUDA(ctx, cudaMemsetAsync(job->d_send, 0, c * (size_t)job->slice * 64, ctx->stream));
+        PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_pack_x<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1, job->d_send, (int)m, (int)job->slice, (int)s0, (int)cnt)));
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (job->allgather(job->user, 2) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (X of all steps)");
+        PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_gather64<<<grid_for(cn), PA_BLOCK, 0, ctx->stream>>>(PH.Xall + 64 * s0 * nall, job->d_recv, PH.gidx + s0 * nall, (int)cn)));
+        if ((rc2 = work_reserve(ctx, cn))) return rc2;
+        PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(c - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.Xall + 64 * s0 * nall, 64, PH.soffN, (int)cn, work_jac(ctx))));
+        if ((rc2 = normalize_to(ctx, PH.Yall + 64 * s0 * nall, cn))) return rc2;
+        PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_gather64<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(PH.Y + 64 * i0, PH.Yall, PH.lidx + i0, (int)cnt)));
+      }
+      if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
       PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1 + 320 * i0, PH.Y + 64 * i0, PH.rnd1 + 128 * i0, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.cand + 128 * i0, 2 * cnt))) return rc2;
-      PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)c, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
+      if (!sharded)
+        PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)c, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
       return PA_OK;
     };
     int st[4];
-    if ((rc = run_steps(0, -1, 1))) return rc;
-    PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
-    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     bool clean = true;
-    for (size_t i = 0; i < T; ++i) clean &= after[i] == ictr[i] + 4;
     long J = -1;
-    if ((size_t)st[2] < c) {  // stopped one step after the first deciding step: redo the rest on the stage-2 counters
-      J = (long)st[2] - 2;
-      const size_t s0 = (size_t)st[2];
-      if ((rc = run_steps(s0, J, 0))) return rc;
+    if (!sharded) {
+      if ((rc = run_steps(0, -1, 1))) return rc;
       PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
       PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      for (size_t i = s0 * m; i < T; ++i) clean &= after[i] == ictr[i] + 4;
+      for (size_t i = 0; i < T; ++i) clean &= after[i] == ictr[i] + 4;
+      if ((size_t)st[2] < c) {  // stopped one step after the first deciding step: redo the rest on the stage-2 counters
+        J = (long)st[2] - 2;
+        const size_t s0 = (size_t)st[2];
+        if ((rc = run_steps(s0, J, 0))) return rc;
+        PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t i = s0 * m; i < T; ++i) clean &= after[i] == ictr[i] + 4;
+      }
+    } else {
+      // every rank walks the steps with its slice; per step one exchange of the ranks' partial sums
+      const int world = (int)((nall + job->slice - 1) / job->slice);
+      {
+        std::vector<u32> gidx(c * nall), lidx(T), soffN(c + 1);
+        for (size_t s2 = 0; s2 < c; ++s2) {
+          for (size_t j = 0; j < nall; ++j) gidx[s2 * nall + j] = (u32)(((j / job->slice) * c + s2) * job->slice + j % job->slice);
+          for (size_t q = 0; q < m; ++q) lidx[s2 * m + q] = (u32)(s2 * nall + job->lo + q);
+        }
+        for (size_t k = 0; k <= c; ++k) soffN[k] = (u32)(k * nall);
+        if ((rc = up(ctx, PH.gidx, gidx)) || (rc = up(ctx, PH.lidx, lidx)) || (rc = up(ctx, PH.soffN, soffN))) return rc;
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      }
+      if ((rc = run_steps(0, -1, 1))) return rc;
+      size_t redo_from = 0;
+      for (size_t s2 = 0; s2 <= c; ++s2) {
+        if (J >= 0 && s2 == (size_t)J + 2 && s2 < c) {  // the keys drawn on stage-1 counters end here
+          if ((rc = run_steps(s2, J, 0))) return rc;
+          redo_from = s2;
+        }
+        PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide_shard<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)s2, (int)m, (int)c, world, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3, (const u32 *)PH.part, (u32 *)job->d_send)));
+        PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (J < 0 && st[0]) J = st[1];
+        if (s2 < c) {
+          if (job->allgather(job->user, 3) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (partial sums)");
+          PA_CUDA(ctx, cudaMemcpyAsync(PH.part, job->d_recv, (size_t)world * 128, cudaMemcpyDeviceToDevice, ctx->stream));  // d_recv is reused by the X exchange
+        }
+      }
+      for (size_t i = 0; i < T; ++i) clean &= after[i] == ictr[i] + 4;
+      (void)redo_from;
     }
     std::vector<int> stage(c), r3(c);
     PA_CUDA(ctx, cudaMemcpyAsync(stage.data(), PH.stage, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -3,10 +3,11 @@
 The hot path partitions two ways:
   * independent auctions / independent batches of scalar mults: every rank works on
     its own share, there is NO data-path collective;
-  * ONE auction sharded by bidder slice: per step the X_i of round one and the b_i of
-    round two (64 B per bidder) are all-gathered, and one word of verdict is
-    MIN-reduced at the end.  The engine (pa_seal_run) calls back into `allgather`
-    below when a slice is ready in the send buffer.
+  * ONE auction sharded by bidder slice: the X_i of round one (64 B per bidder and step) are
+    all-gathered once for all steps, per step every rank contributes the sum of its
+    cryptograms (128 B), and one word of verdict is MIN-reduced at the end.  (The step-major
+    schedule, used when some rank would own no bidder, gathers X_i and b_i once per step.)
+    The engine (pa_seal_run) calls back into `allgather` below when the send buffer is ready.
 """
 import torch
 import torch.distributed as dist
@@ -20,11 +21,16 @@ def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False):
     slice_ = (n + world - 1) // world
     lo, hi = min(n, rank * slice_), min(n, (rank + 1) * slice_)
     dev = torch.device("cuda", torch.cuda.current_device())
-    send = torch.zeros(slice_ * 64, dtype=torch.uint8, device=dev)
-    recv = torch.empty(world * slice_ * 64, dtype=torch.uint8, device=dev)
+    cap = max(c * slice_ * 64, 128)
+    send = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    recv = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+    # the phase-major schedule needs every rank to own bidders (all ranks take the same decisions)
+    phase_major = (world - 1) * slice_ < n
+    sizes = {0: slice_ * 64, 1: slice_ * 64, 2: c * slice_ * 64, 3: 128}
 
     def allgather(which):
-        dist.all_gather_into_tensor(recv, send)   # NCCL over NVLink; 64 B per bidder
+        k = sizes[which]
+        dist.all_gather_into_tensor(recv[:world * k], send[:k])   # NCCL over NVLink
         # wait for the collective only: a device-wide synchronize would also wait for the engine's side
         # lanes (proofs / verification of earlier steps) and serialise them with the exchange
         torch.cuda.current_stream().synchronize()
@@ -32,7 +38,8 @@ def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False):
 
     if hi > lo:
         res = engine.seal_run(seed, [n], [c], list(bids_all[lo:hi]), verify=verify, sections=sections,
-                              shard=dict(lo=lo, hi=hi, slice=slice_, d_send=send.data_ptr(), d_recv=recv.data_ptr(), allgather=allgather))
+                              shard=dict(lo=lo, hi=hi, slice=slice_, d_send=send.data_ptr(), d_recv=recv.data_ptr(), allgather=allgather,
+                                         xchg_bytes=cap if phase_major else 0))
     else:  # more ranks than bidders: still take part in the exchanges
         for _ in range(2 * c):
             allgather(0)

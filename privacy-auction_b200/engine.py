@@ -112,7 +112,7 @@ class SealJob(ctypes.Structure):
         ("out_commit", ctypes.c_void_p), ("out_commit_ok", ctypes.c_void_p), ("out_r1", ctypes.c_void_p),
         ("out_r1_ok", ctypes.c_void_p), ("out_r2_tag", ctypes.c_void_p), ("out_r2_b", ctypes.c_void_p),
         ("out_r2_proof", ctypes.c_void_p), ("out_r2_ok", ctypes.c_void_p), ("out_r3", ctypes.c_void_p),
-        ("schedule", ctypes.c_int),
+        ("schedule", ctypes.c_int), ("xchg_bytes", ctypes.c_size_t),
     ]
 
 
@@ -411,6 +411,7 @@ class Engine:
             job.lo, job.hi, job.slice = shard["lo"], shard["hi"], shard["slice"]
             job.allgather = cb
             job.d_send, job.d_recv = shard["d_send"], shard["d_recv"]
+            job.xchg_bytes = shard.get("xchg_bytes", 0)
         out = {}
         if sections:
             cmax = max(c)

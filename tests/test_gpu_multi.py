@@ -40,7 +40,10 @@ def test_sharded_auction_two_gpus(tmp_path):
         pytest.skip("needs 2 GPUs")
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import seal_flow
-    golds = [os.path.join(ROOT, "tests", "golden", f) for f in ("seal_n5_c5_s11.bin", "seal_n4_c6_s7.bin", "seal_n3_c8_s5.bin")]
+    import glob
+    # every golden auction: n >= 2 runs the phase-major sharded schedule, n = 1 (rank 1 owns nobody) the step-major one
+    golds = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "seal_n*.bin")))
+    assert len(golds) >= 7
     w = tmp_path / "worker.py"
     w.write_text(WORKER)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
@@ -56,6 +59,8 @@ def test_sharded_auction_two_gpus(tmp_path):
             lo, hi = res["slice"]
             m = hi - lo
             assert res["ok_all"] and res["max_bid_all"] == max(t["bids"])
+            if m == 0:
+                continue                      # more ranks than bidders: this rank only took part in the exchanges
             sec = {"commit": {}, "commit_ok": {}, "r1": [], "r1_ok": [], "r2": [], "r2_ok": [], "r3": []}
             for q in range(m):
                 sec["commit"][lo + q] = res["commit"][736 * c * q:736 * c * (q + 1)]
