@@ -222,7 +222,7 @@ def proof_throughput(eng, torch, n=1 << 15, seed=77):
 def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096):
     """Secondary figures (not the headline `value`): SEAL auctions through pa_seal_run.
       config4: ONE auction, n = 1000 bidders x 32-bit bids, sharded by bidder slice over the ranks
-               (NCCL all-gather of X and b per step), every proof verified once;
+               (one NCCL all-gather of the X of all steps, then 128 B of partial sums per rank and step), every proof verified once;
       config5: a lock-step batch of independent genTests-style auctions (n ~ U{1..20}, c ~ U{1..32},
                reference tests/genTests.py:15-16) per rank, no exchange;
       verifies/s per proof kind from the CUDA-event time of the verify kernels inside the config4 run."""
@@ -255,7 +255,7 @@ def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096):
         dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
     dt = float(t_dt.item())
     out["config4_seal_n1000_c32"] = {"auctions_per_s": 1.0 / dt, "seconds": dt, "bidders": n4, "bits": c4,
-                                     "partition": "single GPU" if world == 1 else f"bidder slices over {world} GPUs, NCCL all-gather of X and b per step",
+                                     "partition": "single GPU" if world == 1 else f"bidder slices over {world} GPUs, one NCCL all-gather of the X of all steps, then 128 B of partial sums per rank and step",
                                      "verification": "every proof once (the reference repeats each check n-1 times)"}
     # proofs verified on this rank during the run, per kind
     m = n4 if world == 1 else (min(n4, (rank + 1) * ((n4 + world - 1) // world)) - min(n4, rank * ((n4 + world - 1) // world)))

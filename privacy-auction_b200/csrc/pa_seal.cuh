@@ -559,6 +559,18 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   const pa_lay LC{736, 736, 224, 224, 1, 0, 0, 0, 0}, LC2{736, 736, 224, 224, 2, 96, 64, 32, 32};
   const pa_lay LR2{320, 320, 128, 128, 2, 96, 64, 32, 32};
 
+  // verdicts and records of the commit phase to the host (after their verification has been queued)
+  auto collect_commitments = [&]() -> int {
+    std::vector<unsigned char> cv(Mb);
+    PA_CUDA(ctx, cudaMemcpyAsync(cv.data(), d_cv + 3 * Mb, Mb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (job->out_commit) PA_CUDA(ctx, cudaMemcpyAsync(job->out_commit, d_crec, Mb * 736, cudaMemcpyDeviceToHost, ctx->stream));
+    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (job->out_commit_ok) memcpy(job->out_commit_ok, cv.data(), Mb);
+    for (size_t s = 0; s < m; ++s)
+      for (u32 k = boff[s]; k < boff[s + 1]; ++k) okv[auc[s]] &= cv[k];
+    return PA_OK;
+  };
+
   // ================= commit phase ===================================================
   {
     // 7 draws per (bidder, bit): slot k of bidder s starts at counter 7 * (k - boff[s]) of the bidder's
@@ -591,20 +603,27 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     // Schnorr proofs of A (alpha, v_A) and B (beta, v_B): 2 per record, one batch
     if ((rc = prove_dev<PA_POK>(ctx, d_crec + 64, d_rndc, nullptr, nullptr, d_cid, d_rndc + 64, d_crec + 192, 2 * Mb, LC2))) return rc;
     if ((rc = prove_dev<PA_COM>(ctx, d_crec, d_rndc, d_bits, nullptr, d_cid, d_rndc + 128, d_crec + 384, Mb, LC))) return rc;
-    if (verify) {
-      if ((rc = verify_dev<PA_POK, 1>(ctx, d_crec + 192, d_crec + 64, d_cid, d_cv, 2 * Mb, LC2))) return rc;  // verdicts interleaved A, B
-      if ((rc = verify_dev<PA_COM, 4>(ctx, d_crec + 384, d_crec, d_cid, d_cv + 2 * Mb, Mb, LC))) return rc;
+    auto verify_commitments = [&]() -> int {
+      int rc2;
+      if ((rc2 = verify_dev<PA_POK, 1>(ctx, d_crec + 192, d_crec + 64, d_cid, d_cv, 2 * Mb, LC2))) return rc2;  // verdicts interleaved A, B
+      if ((rc2 = verify_dev<PA_COM, 4>(ctx, d_crec + 384, d_crec, d_cid, d_cv + 2 * Mb, Mb, LC))) return rc2;
       PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(d_cv, d_cv + 2 * Mb, d_cv + 3 * Mb, (int)Mb)));
-    } else {
+      return PA_OK;
+    };
+    if (!verify) {
       PA_CUDA(ctx, cudaMemsetAsync(d_cv + 3 * Mb, 1, Mb, ctx->stream));
+    } else if (phased) {  // on a side lane: it overlaps the keys, candidates and the walk through the steps
+      PA_CUDA(ctx, cudaEventRecord(ev_r1[0], ctx->stream));
+      LaneScope ls(ctx, L_verify);
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[0], 0));
+      if ((rc = verify_commitments())) return rc;
+      PA_CUDA(ctx, cudaEventRecord(ev_verified[0], ctx->stream));
+    } else if ((rc = verify_commitments())) {
+      return rc;
     }
-    std::vector<unsigned char> cv(Mb);
-    PA_CUDA(ctx, cudaMemcpyAsync(cv.data(), d_cv + 3 * Mb, Mb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (job->out_commit) PA_CUDA(ctx, cudaMemcpyAsync(job->out_commit, d_crec, Mb * 736, cudaMemcpyDeviceToHost, ctx->stream));
-    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (job->out_commit_ok) memcpy(job->out_commit_ok, cv.data(), Mb);
-    for (size_t s = 0; s < m; ++s)
-      for (u32 k = boff[s]; k < boff[s + 1]; ++k) okv[auc[s]] &= cv[k];
+    if (!phased) {
+      if ((rc = collect_commitments())) return rc;
+    }
   }
 
   // ================= single auction, phase-major schedule ==============================================
@@ -749,6 +768,8 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PA_CUDA(ctx, cudaMemsetAsync(PH.r2ok, 1, T, ctx->stream));
     }
     // ---- results ---------------------------------------------------------------------------------------------
+    if (verify) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_verified[0], 0));
+    if ((rc = collect_commitments())) return rc;
     std::vector<unsigned char> r1ok(T), r2ok(T);
     PA_CUDA(ctx, cudaMemcpyAsync(r1ok.data(), PH.r1ok, T, cudaMemcpyDeviceToHost, ctx->stream));
     PA_CUDA(ctx, cudaMemcpyAsync(r2ok.data(), PH.r2ok, T, cudaMemcpyDeviceToHost, ctx->stream));
