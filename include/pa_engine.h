@@ -255,11 +255,12 @@ int pa_rng_fill256_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *d_streams, ui
  * Partitioning over GPUs (one process per GPU):
  *   - independent auctions: give each rank its own auctions; no exchange;
  *   - ONE auction sharded by bidder slice: every rank passes the same n / c, its own id
- *     range [lo, hi) and the bids of that range, plus an all-gather callback.  Once per
- *     step the X_i and once the b_i of a slice (slice * 64 bytes, zero padded) are placed in
- *     d_send; allgather(user, which) must leave the concatenation of all ranks' d_send, in
- *     rank order, in d_recv (ranks own ascending id ranges of `slice` bidders each) and
- *     return 0 when d_recv is ready.  Each rank proves and verifies its own slice.
+ *     range [lo, hi) and the bids of that range, plus an all-gather callback.  In the step-major
+ *     schedule, once per step the X_i and once the b_i of a slice (slice * 64 bytes, zero padded)
+ *     are placed in d_send; allgather(user, which) must leave the concatenation of the first
+ *     so-many bytes of all ranks' d_send, in rank order, in d_recv (ranks own ascending id ranges
+ *     of `slice` bidders each) and return 0 when d_recv is ready.  (See `schedule` below for the
+ *     exchanges of the phase-major schedule.)  Each rank proves and verifies its own slice.
  *
  * Optional host outputs ("sections", NULL to skip), m = local bidders, slot = position of a
  * local bidder (auction-major, id order), Mb = sum over local bidders of c:
