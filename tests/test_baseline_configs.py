@@ -44,6 +44,31 @@ def test_engine_seal_10_20_runner_and_batched_abi(engine):
 
 
 @pytest.mark.gpu
+def test_engine_seal_10_20_step_major_schedule(engine):
+    g = D["seal_10_20"]
+    res = engine.seal_run(g["seed"], [g["n"]], [g["c"]], g["bids"], verify=True, sections=True, schedule=1)
+    out = seal_flow.sections_to_transcripts(g["seed"], [g["n"]], [g["c"]], g["bids"], res)[0]
+    assert _sha(out) == g["sha256"] and res["ok"] == [True]
+
+
+@pytest.mark.gpu
+def test_engine_config4_full_size_schedules_agree(engine):
+    """BASELINE config 4 at full size (1000 bidders x 32-bit bids, ~4.5 M scalar mults; far beyond the CPU
+    oracle): both schedules of the runner must publish the same 47 MB of records, every proof must
+    verify, and the maximum must come out.  The step-major bytes are tied to the oracle at n = 64
+    (tests/test_gpu_seal.py) and to the reference at n <= 10."""
+    import random
+    rnd = random.Random(2024)
+    n, c = 1000, 32
+    bids = [rnd.randrange(1 << 31) for _ in range(n)]
+    a = engine.seal_run(4, [n], [c], bids, verify=True, sections=True, schedule=1)
+    b = engine.seal_run(4, [n], [c], bids, verify=True, sections=True, schedule=2)
+    assert a["ok"] == b["ok"] == [True] and a["max_bid"] == b["max_bid"] == [max(bids)]
+    for key in ("commit", "commit_ok", "r1", "r1_ok", "r2_tag", "r2_b", "r2_proof", "r2_ok", "r3"):
+        assert _sha(bytes(a[key])) == _sha(bytes(b[key])), key
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["ccs22_20_32", "ccs22_20_31"])
 def test_engine_ccs22_config2(engine, name):
     g = D[name]
