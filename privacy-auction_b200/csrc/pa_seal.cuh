@@ -418,7 +418,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   const bool verify = job->verify != 0;
   // one unsharded auction: phase-major schedule unless the caller asks for the step-major one
   // (sharded: the exchange buffers must hold the X of all steps, and a Jacobian partial sum)
-  bool phased = A == 1 && job->schedule != PA_SEAL_STEP_MAJOR &&
+  bool phased = A == 1 && job->c[0] >= 1 && job->schedule != PA_SEAL_STEP_MAJOR &&
                 (!sharded || (job->xchg_bytes >= (size_t)job->c[0] * job->slice * 64 && job->xchg_bytes >= 128));
   PA_ARGCHECK(ctx, job->schedule != PA_SEAL_PHASE_MAJOR || phased);
   const bool want_r1 = job->out_r1 != nullptr, want_b = job->out_r2_b != nullptr, want_proof = job->out_r2_proof != nullptr;
