@@ -273,6 +273,27 @@ def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096):
         out["proof_throughput_large_batch"] = proof_throughput(eng, torch)
     out["config4_kernels_ms"] = {k: round(v["total_ms"], 3) for k, v in ks.items()}
 
+    # configs 1 and 2 as ONE auction through the runners (latency, rank 0 only)
+    if rank == 0:
+        r1 = random.Random(1)
+        b1 = [r1.randrange(1 << 20) for _ in range(10)]
+        b2 = [r1.randrange(1 << 31) for _ in range(20)]
+        for _ in range(2):
+            eng.sync()
+            t0 = time.perf_counter()
+            ra = eng.seal_run(1, [10], [20], b1, verify=True)
+            eng.sync()
+            dt1 = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            rb = eng.ccs22_run(2, [20], [32], [7], b2)
+            eng.sync()
+            dt2c = time.perf_counter() - t0
+        assert ra["ok"] == [True] and ra["max_bid"] == [max(b1)] and all(v == max(b2) for v in rb["max_bid"])
+        out["config1_seal_n10_c20_one_auction"] = {"seconds": dt1, "path": "pa_seal_run, phase-major schedule, every proof verified once",
+                                                   "reference": "./SEAL 10 20: 51.6-60.6 s on one core (all-pairs verification); per-party CLI on the engine: 2.6 s"}
+        out["config2_ccs22_n20_c32_one_auction"] = {"seconds": dt2c, "path": "pa_ccs22_run (latency-bound: ~25 dependent launches per step)",
+                                                    "reference": "./CCS22 20 32: 4.46 s on one core; per-party CLI on the engine: 2.7 s"}
+
     # config 5 sample: independent auctions, each rank its own batch
     A = config5_auctions
     r5 = random.Random(5000 + rank)
