@@ -322,6 +322,10 @@ typedef struct {
   const uint64_t *bids;              /* all parties, auction-major, id order */
   uint64_t *max_bid;                 /* [m] the maximum each party computed */
   uint8_t *out_params, *out_com, *out_pub, *out_r1, *out_ots, *out_d;
+  /* PA_SEAL_AUTO / PA_SEAL_STEP_MAJOR / PA_SEAL_PHASE_MAJOR as in pa_seal_job: one auction can be run
+   * phase-major (every candidate of every step in a few large launches, one block walks the steps,
+   * one kernel assembles the published records); same bytes. */
+  int schedule;
 } pa_ccs22_job;
 int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job);
 

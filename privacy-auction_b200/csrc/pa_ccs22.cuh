@@ -286,6 +286,191 @@ k_ccs22_recv2_terms(const unsigned char *ots, const unsigned char *beta, u32 *jo
   st_jac(jout + 24 * (size_t)i, res);
 }
 
+// ---- one auction, phase-major ---------------------------------------------------------------------------
+// Step by step, one CCS22 auction is ~25 dependent launches of a few hundred threads per step (6.5 ms).
+// Nothing but the race flags depends on earlier steps, and they only SELECT: a party's B is Y^x or g^r, the
+// evaluator's (G, H) is (g^beta, h^beta) or (g^beta g1, T2 h^beta), and with W_alpha = G_alpha^s H_alpha^t,
+// U = g1^s T2^t:  C0 = W_alpha B,  C1 = W_alpha / U * M1,  and the evaluator's test is
+// sum_j (W_0,j / z_j^beta_j) + sum_p B_p == infinity.  All draw counters are arithmetic (n - 1 per step for the
+// evaluator, 1 per bidder).  So every candidate of every step is computed in a few large launches, one block
+// walks the steps, and one kernel assembles the published records.  Item i = step * (n - 1) + slot,
+// party item = step * n + party.
+__global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
+k_c22p_bcand(const unsigned char *Yall, const unsigned char *sec, const u32 *soff, int c, int n, const u32 *__restrict__ comb,
+             u32 *jout, int TP) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * TP) return;
+  int which = t / TP, i = t % TP, s = i / n, p = i % n;
+  const unsigned char *blk = sec + 32 * (size_t)soff[p];
+  jac r;
+  sc k;
+  if (which) {
+    ld_sc(k, blk + 32 * ((size_t)c + s));  // r_step
+    fixed_base_mul(r, k, comb);
+  } else {
+    jac P;
+    ld_point_jac(P, Yall + 64 * (size_t)i);
+    ld_sc(k, blk + 32 * (size_t)s);  // x_step
+    var_base_mul(r, P, k);
+  }
+  st_jac(jout + 24 * ((size_t)i * 2 + which), r);
+}
+// level 1, op-major: T2 = g^k, Gb = g^beta, Hb = h^beta, z = g^s h^t, M1 = g^m
+__global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
+k_c22p_level1(const unsigned char *kk, const unsigned char *beta, const unsigned char *ssc, const unsigned char *tsc,
+              const unsigned char *mm, const unsigned char *h, const u32 *__restrict__ comb, u32 *jout, int T) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 5 * T) return;
+  int op = t / T, i = t % T;
+  jac r, P, v;
+  sc k;
+  if (op == 0 || op == 1 || op == 4) {
+    ld_sc(k, (op == 0 ? kk : op == 1 ? beta : mm) + 32 * (size_t)i);
+    fixed_base_mul(r, k, comb);
+  } else if (op == 2) {
+    ld_point_jac(P, h);
+    ld_sc(k, beta + 32 * (size_t)i);
+    var_base_mul(r, P, k);
+  } else {
+    ld_point_jac(P, h);
+    ld_sc(k, tsc + 32 * (size_t)i);
+    var_base_mul(v, P, k);
+    ld_sc(k, ssc + 32 * (size_t)i);
+    fixed_base_mul(r, k, comb);
+    jac_add(r, r, v);
+  }
+  st_jac(jout + 24 * (size_t)t, r);
+}
+// level 2, op-major, from the affine level-1 arrays L1[op][i]: W0 = Gb^s Hb^t, W1 = (Gb g1)^s (T2 Hb)^t,
+// U = g1^s T2^t, bz = z^beta, G1 = Gb g1, H1 = T2 Hb
+__global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
+k_c22p_level2(const unsigned char *L1, const unsigned char *ssc, const unsigned char *tsc, const unsigned char *beta,
+              const unsigned char *g1, u32 *jout, int T) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * T) return;
+  int op = t / T, i = t % T;
+  const unsigned char *T2 = L1 + 64 * (size_t)i, *Gb = L1 + 64 * ((size_t)T + i), *Hb = L1 + 64 * (2 * (size_t)T + i),
+                      *z = L1 + 64 * (3 * (size_t)T + i);
+  jac r, P, Q;
+  sc a, b;
+  aff q;
+  if (op <= 2) {
+    ld_sc(a, ssc + 32 * (size_t)i);
+    ld_sc(b, tsc + 32 * (size_t)i);
+    if (op == 0) {
+      ld_point_jac(P, Gb);
+      ld_point_jac(Q, Hb);
+    } else if (op == 1) {
+      ld_point_jac(P, Gb);
+      ld_aff(q, g1);
+      jac_madd(P, P, q);
+      ld_point_jac(Q, T2);
+      ld_aff(q, Hb);
+      jac_madd(Q, Q, q);
+    } else {
+      ld_point_jac(P, g1);
+      ld_point_jac(Q, T2);
+    }
+    strauss<2>(r, P, a, Q, b);
+  } else if (op == 3) {
+    ld_point_jac(P, z);
+    ld_sc(a, beta + 32 * (size_t)i);
+    var_base_mul(r, P, a);
+  } else if (op == 4) {
+    ld_point_jac(r, Gb);
+    ld_aff(q, g1);
+    jac_madd(r, r, q);
+  } else {
+    ld_point_jac(r, T2);
+    ld_aff(q, Hb);
+    jac_madd(r, r, q);
+  }
+  st_jac(jout + 24 * (size_t)t, r);
+}
+// the walk through the steps: d_p = inRace_p && bit_p; alpha = d_e; newd = alpha ? 1 : (sum != infinity);
+// on newd every party with d = 0 leaves the race       CCS22/bidder.cpp:118-147, 200-212; evaluator.cpp:117-156
+__global__ void __launch_bounds__(PA_SCAN_T)
+k_c22p_walk(int n, int c, int e, const unsigned char *bits, const u32 *boff, const unsigned char *Bcand, const unsigned char *V,
+            unsigned char *inrace, unsigned char *dsel, int *alpha, int *newd) {
+  __shared__ __align__(16) u32 part[PA_SCAN_T][24];
+  __shared__ int s_de, s_nd;
+  const int t = threadIdx.x, nb = n - 1;
+  for (int s = 0; s < c; ++s) {
+    for (int p = t; p < n; p += PA_SCAN_T) {
+      int d = inrace[p] && bits[boff[p] + s];
+      dsel[(size_t)s * n + p] = (unsigned char)d;
+      if (p == e) s_de = d;
+    }
+    __syncthreads();
+    if (!s_de) {
+      jac acc;
+      jac_set_inf(acc);
+      aff x;
+      for (int p = t; p < n; p += PA_SCAN_T) {
+        size_t i = (size_t)s * n + p;
+        ld_aff(x, Bcand + 64 * (2 * i + dsel[i]));
+        jac_madd(acc, acc, x);
+      }
+      for (int j = t; j < nb; j += PA_SCAN_T) {
+        ld_aff(x, V + 64 * ((size_t)s * nb + j));
+        jac_madd(acc, acc, x);
+      }
+      st_jac(part[t], acc);
+      __syncthreads();
+      for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
+        if (t < d) {
+          jac a, b;
+          ld_jac(a, part[t]);
+          ld_jac(b, part[t + d]);
+          jac_add(a, a, b);
+          st_jac(part[t], a);
+        }
+        __syncthreads();
+      }
+      if (t == 0) {
+        jac a;
+        ld_jac(a, part[0]);
+        s_nd = jac_is_inf(a) ? 0 : 1;
+      }
+    } else if (t == 0) {
+      s_nd = 1;
+    }
+    __syncthreads();
+    if (t == 0) alpha[s] = s_de, newd[s] = s_nd;
+    if (s_nd)
+      for (int p = t; p < n; p += PA_SCAN_T)
+        if (!dsel[(size_t)s * n + p]) inrace[p] = 0;
+    __syncthreads();
+  }
+}
+// the published records of every item: r1 = (T2, G_alpha, H_alpha); ots = (z, C0 = W_alpha B_d, C1 = W_alpha / U * M1)
+__global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
+k_c22p_select(int T, int n, const u32 *slot_party, const int *alpha, const unsigned char *dsel, const unsigned char *L1,
+              const unsigned char *L2, const unsigned char *Bcand, unsigned char *r1rec, unsigned char *otsrec, u32 *jout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const int nb = n - 1, s = i / nb, j = i % nb, a = alpha[s], p = (int)slot_party[j];
+  const size_t pi = (size_t)s * n + p;
+  auto l1 = [&](int op) { return L1 + 64 * ((size_t)op * T + i); };
+  auto l2 = [&](int op) { return L2 + 64 * ((size_t)op * T + i); };
+  cp64(r1rec + 192 * (size_t)i, l1(0));
+  cp64(r1rec + 192 * (size_t)i + 64, a ? l2(4) : l1(1));
+  cp64(r1rec + 192 * (size_t)i + 128, a ? l2(5) : l1(2));
+  cp64(otsrec + 192 * (size_t)i, l1(3));
+  jac W, r;
+  aff q;
+  ld_point_jac(W, a ? l2(1) : l2(0));
+  ld_aff(q, Bcand + 64 * (2 * pi + dsel[pi]));
+  jac_madd(r, W, q);
+  st_jac(jout + 24 * ((size_t)i * 2), r);
+  ld_aff(q, l2(2));
+  aff_neg(q, q);
+  jac_madd(r, W, q);
+  ld_aff(q, l1(4));
+  jac_madd(r, r, q);
+  st_jac(jout + 24 * ((size_t)i * 2 + 1), r);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
 int dev_point_add(pa_ctx *ctx, const unsigned char *p, const unsigned char *q, unsigned char *out, size_t n, int sub) {
@@ -431,7 +616,26 @@ extern "C" int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job) {
   u64 *d_streams, *d_ctr, *d_bbstreams, *d_bbctr, *d_bids, *d_dflag;
   int *d_isinf, *d_newd;
   const size_t mx = m > ms ? m : ms, SUM = ms + A;
+  // one auction: phase-major unless the caller asks for the step-major schedule
+  const bool phased = A == 1 && job->schedule != PA_SEAL_STEP_MAJOR;
+  const size_t pn = job->n[0], pc = job->c[0], pnb = pn - 1, T = phased ? pc * pnb : 0, TP = phased ? pc * pn : 0;
+  struct {
+    u32 *ixp, *ib, *is, *it, *sp, *soffN;
+    u64 *st64;
+    int *alpha, *newd;
+    unsigned char *Xall, *Yall, *Bcand, *kk, *mm, *beta, *ssc, *tsc, *L1, *L2, *V, *dsel, *r1rec, *otsrec;
+  } PH{};
   auto carve = [&](DevPool &pool) {
+    if (phased) {
+      PH.ixp = pool.alloc<u32>(TP); PH.ib = pool.alloc<u32>(T); PH.is = pool.alloc<u32>(T); PH.it = pool.alloc<u32>(T);
+      PH.sp = pool.alloc<u32>(pnb); PH.soffN = pool.alloc<u32>(pc + 1); PH.st64 = pool.alloc<u64>(4 * T);
+      PH.alpha = pool.alloc<int>(pc); PH.newd = pool.alloc<int>(pc);
+      PH.Xall = pool.alloc<unsigned char>(TP * 64); PH.Yall = pool.alloc<unsigned char>(TP * 64); PH.Bcand = pool.alloc<unsigned char>(TP * 128);
+      PH.kk = pool.alloc<unsigned char>(T * 32); PH.mm = pool.alloc<unsigned char>(T * 32); PH.beta = pool.alloc<unsigned char>(T * 32);
+      PH.ssc = pool.alloc<unsigned char>(T * 32); PH.tsc = pool.alloc<unsigned char>(T * 32);
+      PH.L1 = pool.alloc<unsigned char>(5 * T * 64); PH.L2 = pool.alloc<unsigned char>(6 * T * 64); PH.V = pool.alloc<unsigned char>(T * 64);
+      PH.dsel = pool.alloc<unsigned char>(TP); PH.r1rec = pool.alloc<unsigned char>(T * 192); PH.otsrec = pool.alloc<unsigned char>(T * 192);
+    }
     d_bits = pool.alloc<unsigned char>(Mb); d_iseval = pool.alloc<unsigned char>(m);
     d_sec = pool.alloc<unsigned char>(NS * 32); d_R = pool.alloc<unsigned char>(m * 32); d_H = pool.alloc<unsigned char>(m * 32);
     d_params = pool.alloc<unsigned char>(A * 128); d_pub = pool.alloc<unsigned char>(Mb * 64); d_com = pool.alloc<unsigned char>(m * 64);
@@ -494,6 +698,67 @@ extern "C" int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job) {
   std::vector<u64> hctr(m);  // stream counters after setup (they include any rejected range draws)
   PA_CUDA(ctx, cudaMemcpyAsync(hctr.data(), d_ctr, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+  // ================= one auction, phase-major (see k_c22p_*) ===================================================
+  if (phased) {
+    const u32 e = aeval[0];
+    {
+      std::vector<u32> ixp(TP), ib(T), is(T), it(T), sp(slot_party), soffN(pc + 1);
+      std::vector<u64> st64(4 * T);
+      for (size_t s = 0; s < pc; ++s) {
+        for (size_t p = 0; p < pn; ++p) ixp[s * pn + p] = boff[p] + (u32)s;
+        for (size_t j = 0; j < pnb; ++j) {
+          const size_t i = s * pnb + j, p = slot_party[j];
+          ib[i] = soff[e] + 2 * (u32)pc + (u32)(s * pnb + j);
+          is[i] = soff[p] + 2 * (u32)pc + (u32)s;
+          it[i] = soff[p] + 3 * (u32)pc + (u32)s;
+          st64[i] = streams[e], st64[T + i] = hctr[e] + s * pnb + j;      // k of OTReceive1: n - 1 draws per step
+          st64[2 * T + i] = streams[p], st64[3 * T + i] = hctr[p] + s;    // m of OTSend: one draw per step
+        }
+      }
+      for (size_t k = 0; k <= pc; ++k) soffN[k] = (u32)(k * pn);
+      if ((rc = up(ctx, PH.ixp, ixp)) || (rc = up(ctx, PH.ib, ib)) || (rc = up(ctx, PH.is, is)) || (rc = up(ctx, PH.it, it)) ||
+          (rc = up(ctx, PH.sp, sp)) || (rc = up(ctx, PH.soffN, soffN)) || (rc = up(ctx, PH.st64, st64)))
+        return rc;
+      PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // every party's Y and both B candidates of every step
+    if ((rc = dev_gather(ctx, PH.Xall, d_pub, PH.ixp, 64, TP))) return rc;
+    if ((rc = work_reserve(ctx, 2 * TP + 6 * T))) return rc;
+    PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)pc, PA_SCAN_T, 0, ctx->stream>>>(PH.Xall, 64, PH.soffN, (int)TP, work_jac(ctx))));
+    if ((rc = normalize_to(ctx, PH.Yall, TP))) return rc;
+    PA_LAUNCH(ctx, PA_K_VAR, (k_c22p_bcand<<<grid_for(2 * TP), PA_BLOCK, 0, ctx->stream>>>(PH.Yall, d_sec, d_soff, (int)pc, (int)pn, ctx->d_comb, work_jac(ctx), (int)TP)));
+    if ((rc = normalize_to(ctx, PH.Bcand, 2 * TP))) return rc;
+    if (T) {
+      PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.st64, PH.st64 + T, nullptr, 1, PH.kk, (int)T, 1)));
+      PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.st64 + 2 * T, PH.st64 + 3 * T, nullptr, 1, PH.mm, (int)T, 1)));
+      if ((rc = dev_gather(ctx, PH.beta, d_sec, PH.ib, 32, T)) || (rc = dev_gather(ctx, PH.ssc, d_sec, PH.is, 32, T)) ||
+          (rc = dev_gather(ctx, PH.tsc, d_sec, PH.it, 32, T)))
+        return rc;
+      PA_LAUNCH(ctx, PA_K_DOUBLE, (k_c22p_level1<<<grid_for(5 * T), PA_BLOCK, 0, ctx->stream>>>(PH.kk, PH.beta, PH.ssc, PH.tsc, PH.mm, d_params + 64, ctx->d_comb, work_jac(ctx), (int)T)));
+      if ((rc = normalize_to(ctx, PH.L1, 5 * T))) return rc;
+      PA_LAUNCH(ctx, PA_K_LINCOMB2, (k_c22p_level2<<<grid_for(6 * T), PA_BLOCK, 0, ctx->stream>>>(PH.L1, PH.ssc, PH.tsc, PH.beta, d_params, work_jac(ctx), (int)T)));
+      if ((rc = normalize_to(ctx, PH.L2, 6 * T))) return rc;
+      if ((rc = dev_point_add(ctx, PH.L2, PH.L2 + 64 * 3 * T, PH.V, T, 1))) return rc;   // V = W0 / z^beta
+    }
+    PA_LAUNCH(ctx, PA_K_SUMINF, (k_c22p_walk<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)pn, (int)pc, (int)e, d_bits, d_boff, PH.Bcand, PH.V, d_inrace, PH.dsel, PH.alpha, PH.newd)));
+    if (T) {
+      PA_LAUNCH(ctx, PA_K_ENCODE, (k_c22p_select<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>((int)T, (int)pn, PH.sp, PH.alpha, PH.dsel, PH.L1, PH.L2, PH.Bcand, PH.r1rec, PH.otsrec, work_jac(ctx))));
+      if ((rc = normalize_to(ctx, PH.otsrec + 64, 2 * T, 2, 192))) return rc;
+    }
+    std::vector<int> newd(pc);
+    PA_CUDA(ctx, cudaMemcpyAsync(newd.data(), PH.newd, pc * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = d2h(job->out_r1, PH.r1rec, T * 192)) || (rc = d2h(job->out_ots, PH.otsrec, T * 192))) return rc;
+    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    u64 mb = 0;
+    for (size_t s = 0; s < pc; ++s) {
+      if (job->out_d) job->out_d[s] = (uint8_t)newd[s];
+      if (newd[s]) mb |= (u64)1 << (pc - s - 1);  // bidder.cpp:210, evaluator.cpp:122, 147
+    }
+    for (size_t p = 0; p < m; ++p)
+      if (job->max_bid) job->max_bid[p] = mb;
+    return PA_OK;
+  }
 
   std::vector<u64> maxbid(m, 0);
   // ================= computation phase ============================================================

@@ -122,7 +122,7 @@ class Ccs22Job(ctypes.Structure):
         ("seed", ctypes.c_uint64), ("n_auctions", ctypes.c_size_t), ("n", ctypes.c_void_p), ("c", ctypes.c_void_p),
         ("evaluator", ctypes.c_void_p), ("auction_ids", ctypes.c_void_p), ("bids", ctypes.c_void_p), ("max_bid", ctypes.c_void_p),
         ("out_params", ctypes.c_void_p), ("out_com", ctypes.c_void_p), ("out_pub", ctypes.c_void_p), ("out_r1", ctypes.c_void_p),
-        ("out_ots", ctypes.c_void_p), ("out_d", ctypes.c_void_p),
+        ("out_ots", ctypes.c_void_p), ("out_d", ctypes.c_void_p), ("schedule", ctypes.c_int),
     ]
 
 
@@ -433,7 +433,7 @@ class Engine:
             res[name[4:]] = bytes(buf)
         return res
 
-    def ccs22_run(self, seed, n, c, evaluator, bids, sections=False, auction_ids=None):
+    def ccs22_run(self, seed, n, c, evaluator, bids, sections=False, auction_ids=None, schedule=0):
         """pa_ccs22_run: whole CCS22 auctions, device resident.  Returns dict(max_bid[, sections...])."""
         A, m = len(n), len(bids)
         arr = lambda T, v: (T * max(len(v), 1))(*v)
@@ -443,6 +443,7 @@ class Engine:
         job.seed, job.n_auctions = seed, A
         job.n, job.c, job.evaluator, job.bids = map(ctypes.addressof, (n_a, c_a, e_a, b_a))
         job.max_bid = ctypes.addressof(mb)
+        job.schedule = schedule
         keep = [n_a, c_a, e_a, b_a, mb]
         if auction_ids is not None:
             aid = arr(ctypes.c_uint64, auction_ids)

@@ -65,11 +65,12 @@ def test_engine_setup_hash_parity(engine, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("schedule", [1, 2], ids=["step-major", "phase-major"])
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
-def test_ccs22_runner_reproduces_reference(engine, path):
+def test_ccs22_runner_reproduces_reference(engine, path, schedule):
     gold = open(path, "rb").read()
     n, c, seed, ev, bids = _hdr(gold)
-    res = engine.ccs22_run(seed, [n], [c], [ev], bids, sections=True)
+    res = engine.ccs22_run(seed, [n], [c], [ev], bids, sections=True, schedule=schedule)
     assert ccs22_flow.sections_to_transcripts(seed, [n], [c], [ev], bids, res)[0] == gold
     assert res["max_bid"] == [max(bids)] * n
 
@@ -94,12 +95,30 @@ def test_ccs22_runner_ragged_batch_matches_oracle(engine, oracle):
 
 
 @pytest.mark.gpu
-def test_ccs22_runner_config2_digest(engine):
+@pytest.mark.parametrize("schedule", [1, 2], ids=["step-major", "phase-major"])
+@pytest.mark.parametrize("name", ["ccs22_20_32", "ccs22_20_31"])
+def test_ccs22_runner_config2_digest(engine, name, schedule):
     import hashlib, json
-    g = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_config_digests.json")))["ccs22_20_32"]
-    res = engine.ccs22_run(g["seed"], [g["n"]], [g["c"]], [g["evaluator"]], g["bids"], sections=True)
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_config_digests.json")))[name]
+    res = engine.ccs22_run(g["seed"], [g["n"]], [g["c"]], [g["evaluator"]], g["bids"], sections=True, schedule=schedule)
     out = ccs22_flow.sections_to_transcripts(g["seed"], [g["n"]], [g["c"]], [g["evaluator"]], g["bids"], res)[0]
     assert hashlib.sha256(out).hexdigest() == g["sha256"]
+
+
+@pytest.mark.gpu
+def test_ccs22_runner_schedules_agree(engine):
+    """phase-major == step-major on shapes the goldens do not have: 40 parties, evaluator first / last, the evaluator
+    holding the maximum (alpha = 1 steps), everybody bidding 0, and one party alone"""
+    rnd = random.Random(4040)
+    for n, c, ev, kind in [(40, 12, 0, "rand"), (9, 10, 8, "evmax"), (6, 7, 2, "zero"), (1, 4, 0, "rand"), (2, 1, 1, "rand"), (12, 32, 5, "rand")]:
+        bids = [0] * n if kind == "zero" else [rnd.randrange(1 << (c - 1)) for _ in range(n)]
+        if kind == "evmax":
+            bids[ev] = (1 << c) - 1
+        a = engine.ccs22_run(77, [n], [c], [ev], bids, sections=True, schedule=1)
+        b = engine.ccs22_run(77, [n], [c], [ev], bids, sections=True, schedule=2)
+        assert a["max_bid"] == b["max_bid"] == [max(bids)] * n, (n, c, ev, kind)
+        for key in a:
+            assert a[key] == b[key], (n, c, ev, kind, key)
 
 
 @pytest.mark.gpu
