@@ -170,7 +170,8 @@ k_seal_candidates(const unsigned char *r1, const unsigned char *Y, const unsigne
   st_jac(jout + 24 * ((size_t)i * 2 + which), r);
 }
 
-// state[0] = junction flag, state[1] = previous deciding step (-1: none), state[2] = next step to run.
+// state[0] = junction flag, state[1] = previous deciding step (-1: none), state[2] = next step to run,
+// state[3] = the first deciding step.
 // Walks steps [state[2], limit).  While `speculative` the keys were drawn on the assumption that no
 // junction has happened; they stay valid up to and including the step after the first deciding step
 // (its draws come after stage-1 proofs only), so the walk stops there.        SEAL/bidder.cpp:1301-1309, 1386-1421
@@ -227,7 +228,10 @@ k_seal_decide(int m, int limit, int speculative, const unsigned char *bits, cons
       for (int p = t; p < m; p += PA_SCAN_T) prevbit[p] &= bits[boff[p] + s];
       if (speculative && !junc) stop = true;  // first deciding step: one more step is still valid
       __syncthreads();
-      if (t == 0) s_junc = 1, s_last = s;
+      if (t == 0) {
+        if (!junc) state[3] = s;  // the junction
+        s_junc = 1, s_last = s;
+      }
     }
     __syncthreads();
     if (stop && limit > s + 2) limit = s + 2;
@@ -648,9 +652,9 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     }
     std::vector<u64> istream(T), ictr(T), after(T);
     // keys, Y and both cryptogram candidates of steps [s0, c), then the walk through those steps
-    auto run_steps = [&](size_t s0, long J, int speculative) -> int {
-      const size_t i0 = s0 * m, cnt = (c - s0) * m;
-      for (size_t i = i0; i < T; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, J);
+    auto run_steps = [&](size_t s0, size_t s1, long J, int speculative) -> int {
+      const size_t i0 = s0 * m, cnt = (s1 - s0) * m;
+      for (size_t i = i0; i < i0 + cnt; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, J);
       PA_CUDA(ctx, cudaMemcpyAsync(PH.istream + i0, istream.data() + i0, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
       PA_CUDA(ctx, cudaMemcpyAsync(PH.ictr + i0, ictr.data() + i0, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream + i0, PH.ictr + i0, nullptr, 4, PH.rnd1 + 128 * i0, (int)cnt)));
@@ -660,18 +664,18 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.r1 + 320 * i0, 2 * cnt, 2, 320))) return rc2;
       if (!sharded) {
-        PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(c - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
+        PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(s1 - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
         if ((rc2 = normalize_to(ctx, PH.Y + 64 * i0, cnt))) return rc2;
       } else {
         // one exchange for the X of all remaining steps: rank r's block is [step][position in slice]
-        const size_t cn = (c - s0) * nall;
+        const size_t cn = (s1 - s0) * nall;
         PA_CUDA(ctx, cudaMemsetAsync(job->d_send, 0, c * (size_t)job->slice * 64, ctx->stream));
         PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_pack_x<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1, job->d_send, (int)m, (int)job->slice, (int)s0, (int)cnt)));
         PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (job->allgather(job->user, 2) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (X of all steps)");
         PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_gather64<<<grid_for(cn), PA_BLOCK, 0, ctx->stream>>>(PH.Xall + 64 * s0 * nall, job->d_recv, PH.gidx + s0 * nall, (int)cn)));
         if ((rc2 = work_reserve(ctx, cn))) return rc2;
-        PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(c - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.Xall + 64 * s0 * nall, 64, PH.soffN, (int)cn, work_jac(ctx))));
+        PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(s1 - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.Xall + 64 * s0 * nall, 64, PH.soffN, (int)cn, work_jac(ctx))));
         if ((rc2 = normalize_to(ctx, PH.Yall + 64 * s0 * nall, cn))) return rc2;
         PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_gather64<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(PH.Y + 64 * i0, PH.Yall, PH.lidx + i0, (int)cnt)));
       }
@@ -679,24 +683,26 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1 + 320 * i0, PH.Y + 64 * i0, PH.rnd1 + 128 * i0, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.cand + 128 * i0, 2 * cnt))) return rc2;
       if (!sharded)
-        PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)c, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
+        PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
       return PA_OK;
     };
     int st[4];
     bool clean = true;
     long J = -1;
     if (!sharded) {
-      if ((rc = run_steps(0, -1, 1))) return rc;
-      PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
-      PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      for (size_t i = 0; i < T; ++i) clean &= after[i] == ictr[i] + 4;
-      if ((size_t)st[2] < c) {  // stopped one step after the first deciding step: redo the rest on the stage-2 counters
-        J = (long)st[2] - 2;
-        const size_t s0 = (size_t)st[2];
-        if ((rc = run_steps(s0, J, 0))) return rc;
+      // Until the first deciding step the keys are speculative, so they are computed for a short window of
+      // steps that doubles while no junction shows up (with random bids it is step 0 or 1; only an auction
+      // of all-zero bids goes through every window); after it, one pass takes all remaining steps.
+      size_t done = 0, win = 2;
+      while (done < c) {
+        const size_t s1 = J < 0 ? (done + win < c ? done + win : c) : c;
+        if ((rc = run_steps(done, s1, J, J < 0 ? 1 : 0))) return rc;
         PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (size_t i = s0 * m; i < T; ++i) clean &= after[i] == ictr[i] + 4;
+        for (size_t i = done * m; i < s1 * m; ++i) clean &= after[i] == ictr[i] + 4;
+        if (J < 0 && st[0]) J = st[3];
+        done = (size_t)st[2];
+        win *= 2;
       }
     } else {
       // every rank walks the steps with its slice; per step one exchange of the ranks' partial sums
@@ -711,11 +717,11 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
         if ((rc = up(ctx, PH.gidx, gidx)) || (rc = up(ctx, PH.lidx, lidx)) || (rc = up(ctx, PH.soffN, soffN))) return rc;
         PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       }
-      if ((rc = run_steps(0, -1, 1))) return rc;
+      if ((rc = run_steps(0, c, -1, 1))) return rc;
       size_t redo_from = 0;
       for (size_t s2 = 0; s2 <= c; ++s2) {
         if (J >= 0 && s2 == (size_t)J + 2 && s2 < c) {  // the keys drawn on stage-1 counters end here
-          if ((rc = run_steps(s2, J, 0))) return rc;
+          if ((rc = run_steps(s2, c, J, 0))) return rc;
           redo_from = s2;
         }
         PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide_shard<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)s2, (int)m, (int)c, world, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3, (const u32 *)PH.part, (u32 *)job->d_send)));
