@@ -651,7 +651,20 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // st0 / vectors go out of scope
     }
     std::vector<u64> istream(T), ictr(T), after(T);
-    // keys, Y and both cryptogram candidates of steps [s0, c), then the walk through those steps
+    // the Schnorr proofs of X and R of every item, one batch (and their verification)
+    auto pok_all = [&]() -> int {
+      int rc2;
+      if ((rc2 = prove_dev<PA_POK>(ctx, PH.r1, PH.rnd1, nullptr, nullptr, PH.pid, PH.rnd1 + 64, PH.r1 + 128, 2 * T, LR2))) return rc2;
+      if (verify) {
+        if ((rc2 = verify_dev<PA_POK, 1>(ctx, PH.r1 + 128, PH.r1, PH.pid, PH.pokv, 2 * T, LR2))) return rc2;
+        PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(PH.pokv, nullptr, PH.r1ok, (int)T)));
+      } else {
+        PA_CUDA(ctx, cudaMemsetAsync(PH.r1ok, 1, T, ctx->stream));
+      }
+      return PA_OK;
+    };
+    bool pok_on_lane = false;
+    // keys, Y and both cryptogram candidates of steps [s0, s1), then the walk through those steps
     auto run_steps = [&](size_t s0, size_t s1, long J, int speculative) -> int {
       const size_t i0 = s0 * m, cnt = (s1 - s0) * m;
       for (size_t i = i0; i < i0 + cnt; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, J);
@@ -663,6 +676,16 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
       PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.r1 + 320 * i0, 2 * cnt, 2, 320))) return rc2;
+      if (!speculative && s1 == c && !pok_on_lane) {
+        // these are the last keys: every X and R is final, so their proofs can run beside the rest of this pass
+        // (they write the proof fields of the round-one records, the pass reads the point fields)
+        PA_CUDA(ctx, cudaEventRecord(ev_r1[1], ctx->stream));
+        LaneScope ls(ctx, L_pok);
+        PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[1], 0));
+        if ((rc2 = pok_all())) return rc2;
+        PA_CUDA(ctx, cudaEventRecord(ev_pok[0], ctx->stream));
+        pok_on_lane = true;
+      }
       if (!sharded) {
         PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(s1 - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
         if ((rc2 = normalize_to(ctx, PH.Y + 64 * i0, cnt))) return rc2;
@@ -749,14 +772,8 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     const size_t n1 = c1 * m, n2 = T - n1;
     const size_t o_stmt = align_up(n1 * 448, 256), o_sec = align_up(n1 * 64, 256), o_b = align_up(n1, 256),
                  o_rnd = align_up(n1 * 160, 256), o_proof = align_up(n1 * 672, 256);
-    // ---- Schnorr proofs of X and R for every item, one batch ------------------------------------------
-    if ((rc = prove_dev<PA_POK>(ctx, PH.r1, PH.rnd1, nullptr, nullptr, PH.pid, PH.rnd1 + 64, PH.r1 + 128, 2 * T, LR2))) return rc;
-    if (verify) {
-      if ((rc = verify_dev<PA_POK, 1>(ctx, PH.r1 + 128, PH.r1, PH.pid, PH.pokv, 2 * T, LR2))) return rc;
-      PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(PH.pokv, nullptr, PH.r1ok, (int)T)));
-    } else {
-      PA_CUDA(ctx, cudaMemsetAsync(PH.r1ok, 1, T, ctx->stream));
-    }
+    if (pok_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[0], 0));
+    else if ((rc = pok_all())) return rc;
     // ---- round-two proofs: statements, draws (right after the four key draws), prove, verify -----------------
     PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt_items<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>((int)m, (int)n1, PH.stage, PH.prevstep, d_boff, PH.b, PH.r1, PH.Y, PH.rnd1, d_crec, d_rndc, PH.ebit, PH.bj, PH.stmt, PH.sec, PH.bi, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, (int)T)));
     for (size_t i = 0; i < T; ++i) ictr[i] = key_ctr(i / m, J) + 4, istream[i] = streams[i % m];
