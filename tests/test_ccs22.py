@@ -110,7 +110,7 @@ def test_ccs22_runner_schedules_agree(engine):
     """phase-major == step-major on shapes the goldens do not have: 40 parties, evaluator first / last, the evaluator
     holding the maximum (alpha = 1 steps), everybody bidding 0, and one party alone"""
     rnd = random.Random(4040)
-    for n, c, ev, kind in [(40, 12, 0, "rand"), (9, 10, 8, "evmax"), (6, 7, 2, "zero"), (1, 4, 0, "rand"), (2, 1, 1, "rand"), (12, 32, 5, "rand")]:
+    for n, c, ev, kind in [(40, 12, 0, "rand"), (9, 10, 8, "evmax"), (6, 7, 2, "zero"), (1, 4, 0, "rand"), (2, 1, 1, "rand"), (12, 32, 5, "rand"), (3, 64, 1, "evmax")]:
         bids = [0] * n if kind == "zero" else [rnd.randrange(1 << (c - 1)) for _ in range(n)]
         if kind == "evmax":
             bids[ev] = (1 << c) - 1

@@ -255,7 +255,8 @@ def test_runner_schedules_agree(engine):
     """The phase-major schedule of a single auction publishes the same bytes as the step-major one: junction at
     the first, a middle, the second-to-last and the last step, never (all bids 0), and one bidder alone."""
     rnd = random.Random(88)
-    cases = [(7, 9, None), (5, 8, 0x80), (6, 8, 0x02), (6, 8, 0x01), (4, 6, 0), (1, 5, 0x15), (40, 16, None), (3, 1, 1), (3, 2, 2)]
+    cases = [(7, 9, None), (5, 8, 0x80), (6, 8, 0x02), (6, 8, 0x01), (4, 6, 0), (1, 5, 0x15), (40, 16, None), (3, 1, 1), (3, 2, 2),
+             (3, 64, (1 << 64) - 1), (2, 33, 1 << 32)]
     for n, c, top in cases:
         bids = [rnd.randrange(1 << c) for _ in range(n)] if top is None else [rnd.randrange(top + 1) if top else 0 for _ in range(n)]
         if top:
