@@ -296,16 +296,24 @@ k_seal_decide_shard(int s, int m, int limit, int world, const unsigned char *bit
   __shared__ __align__(16) u32 part[PA_SCAN_T][24];
   __shared__ int s_junc, s_last, s_deciding;
   int t = threadIdx.x;
-  if (t == 0) {
-    s_junc = state[0], s_last = state[1], s_deciding = 0;
-    if (s > 0) {
-      jac a;
-      jac_set_inf(a);
-      for (int r = 0; r < world; ++r) {
+  if (t == 0) s_junc = state[0], s_last = state[1], s_deciding = 0;
+  if (s > 0) {  // fold the ranks' partial sums of step s - 1 (tree over the first `world` threads)
+    jac a;
+    if (t < world) ld_jac(a, recv + 32 * (size_t)t); else jac_set_inf(a);
+    st_jac(part[t], a);
+    __syncthreads();
+    for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
+      if (t < d && t + d < world) {
         jac c;
-        ld_jac(c, recv + 32 * (size_t)r);
+        ld_jac(a, part[t]);
+        ld_jac(c, part[t + d]);
         jac_add(a, a, c);
+        st_jac(part[t], a);
       }
+      __syncthreads();
+    }
+    if (t == 0) {
+      ld_jac(a, part[0]);
       s_deciding = jac_is_inf(a) ? 0 : 1;
       r3[s - 1] = s_deciding;
       if (s_deciding) s_junc = 1, s_last = s - 1;
