@@ -11,7 +11,9 @@
 #pragma once
 #include "pa_proof.cuh"
 
-#define PA_BLOCK 128
+#ifndef PA_BLOCK
+#define PA_BLOCK 128  // 64-thread blocks measure the same (19.5 ms per 2^20 variable-base mults), 256 slightly worse (19.9)
+#endif
 // Resident CTAs per SM the scalar-multiplication kernels are compiled for.  Measured on B200
 // (2^20 variable-base mults): 3 CTAs (136 regs) 21.2 ms, 4 (128 regs) 20.0 ms, 5 (96 regs,
 // 360 B spilled) 19.7 ms — more warps hide the fixed-latency dependency stalls of the
