@@ -790,14 +790,25 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     if (n1) PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream, PH.ictr, nullptr, 5, PH.rnd2, (int)n1)));
     if (n2) PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream + n1, PH.ictr + n1, nullptr, 11, PH.rnd2 + o_rnd, (int)n2)));
     PA_CUDA(ctx, cudaMemcpyAsync(after.data(), PH.ictr, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n1 && (rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
-    if (n2 && (rc = prove_dev<PA_S2>(ctx, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.pid + n1, PH.rnd2 + o_rnd, PH.proof + o_proof, n2))) return rc;
-    if (verify) {
-      if (n1 && (rc = verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1))) return rc;
-      if (n2 && (rc = verify_dev<PA_S2, 16>(ctx, PH.proof + o_proof, PH.stmt + o_stmt, PH.pid + n1, PH.r2ok + n1, n2))) return rc;
-    } else {
-      PA_CUDA(ctx, cudaMemsetAsync(PH.r2ok, 1, T, ctx->stream));
+    if (!verify) PA_CUDA(ctx, cudaMemsetAsync(PH.r2ok, 1, T, ctx->stream));
+    // the two groups are independent: the (small, latency-bound) stage-1 group runs on a lane beside stage 2
+    const bool s1_on_lane = n1 && n2;
+    if (s1_on_lane) {
+      PA_CUDA(ctx, cudaEventRecord(ev_enc[0], ctx->stream));
+      LaneScope ls(ctx, L_prove);
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[0], 0));
+      if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
+      if (verify && (rc = verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1))) return rc;
+      PA_CUDA(ctx, cudaEventRecord(ev_proved[0], ctx->stream));
+    } else if (n1) {
+      if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
+      if (verify && (rc = verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1))) return rc;
     }
+    if (n2) {
+      if ((rc = prove_dev<PA_S2>(ctx, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.pid + n1, PH.rnd2 + o_rnd, PH.proof + o_proof, n2))) return rc;
+      if (verify && (rc = verify_dev<PA_S2, 16>(ctx, PH.proof + o_proof, PH.stmt + o_stmt, PH.pid + n1, PH.r2ok + n1, n2))) return rc;
+    }
+    if (s1_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_proved[0], 0));
     // ---- results ---------------------------------------------------------------------------------------------
     if (verify) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_verified[0], 0));
     if ((rc = collect_commitments())) return rc;
