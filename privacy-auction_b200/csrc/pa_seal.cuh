@@ -609,28 +609,32 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
         PA_CUDA(ctx, cudaMemcpyAsync(d_ctr + s, &cnt, 8, cudaMemcpyHostToDevice, ctx->stream));
       }
     }
-    if ((rc = work_reserve(ctx, 3 * Mb))) return rc;
-    PA_LAUNCH(ctx, PA_K_COMMIT, (k_seal_commit_points<<<grid_for(3 * Mb), PA_BLOCK, 0, ctx->stream>>>(d_rndc, d_bits, ctx->d_comb, work_jac(ctx), (int)Mb)));
-    if ((rc = normalize_to(ctx, d_crec, 3 * Mb, 3, 736))) return rc;
-    // Schnorr proofs of A (alpha, v_A) and B (beta, v_B): 2 per record, one batch
-    if ((rc = prove_dev<PA_POK>(ctx, d_crec + 64, d_rndc, nullptr, nullptr, d_cid, d_rndc + 64, d_crec + 192, 2 * Mb, LC2))) return rc;
-    if ((rc = prove_dev<PA_COM>(ctx, d_crec, d_rndc, d_bits, nullptr, d_cid, d_rndc + 128, d_crec + 384, Mb, LC))) return rc;
-    auto verify_commitments = [&]() -> int {
+    // commitment points, their Schnorr proofs (A: alpha, v_A; B: beta, v_B; 2 per record, one batch), the OR proof,
+    // and the verification of all of it
+    auto commit_work = [&]() -> int {
       int rc2;
+      if ((rc2 = work_reserve(ctx, 3 * Mb))) return rc2;
+      PA_LAUNCH(ctx, PA_K_COMMIT, (k_seal_commit_points<<<grid_for(3 * Mb), PA_BLOCK, 0, ctx->stream>>>(d_rndc, d_bits, ctx->d_comb, work_jac(ctx), (int)Mb)));
+      if ((rc2 = normalize_to(ctx, d_crec, 3 * Mb, 3, 736))) return rc2;
+      PA_CUDA(ctx, cudaEventRecord(ev_enc[1], ctx->stream));  // phi, A, B are in the records
+      if ((rc2 = prove_dev<PA_POK>(ctx, d_crec + 64, d_rndc, nullptr, nullptr, d_cid, d_rndc + 64, d_crec + 192, 2 * Mb, LC2))) return rc2;
+      if ((rc2 = prove_dev<PA_COM>(ctx, d_crec, d_rndc, d_bits, nullptr, d_cid, d_rndc + 128, d_crec + 384, Mb, LC))) return rc2;
+      if (!verify) {
+        PA_CUDA(ctx, cudaMemsetAsync(d_cv + 3 * Mb, 1, Mb, ctx->stream));
+        return PA_OK;
+      }
       if ((rc2 = verify_dev<PA_POK, 1>(ctx, d_crec + 192, d_crec + 64, d_cid, d_cv, 2 * Mb, LC2))) return rc2;  // verdicts interleaved A, B
       if ((rc2 = verify_dev<PA_COM, 4>(ctx, d_crec + 384, d_crec, d_cid, d_cv + 2 * Mb, Mb, LC))) return rc2;
       PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(d_cv, d_cv + 2 * Mb, d_cv + 3 * Mb, (int)Mb)));
       return PA_OK;
     };
-    if (!verify) {
-      PA_CUDA(ctx, cudaMemsetAsync(d_cv + 3 * Mb, 1, Mb, ctx->stream));
-    } else if (phased) {  // on a side lane: it overlaps the keys, candidates and the walk through the steps
+    if (phased) {  // on a side lane: the steps do not need the commitments until the round-two statements are assembled
       PA_CUDA(ctx, cudaEventRecord(ev_r1[0], ctx->stream));
       LaneScope ls(ctx, L_verify);
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[0], 0));
-      if ((rc = verify_commitments())) return rc;
+      if ((rc = commit_work())) return rc;
       PA_CUDA(ctx, cudaEventRecord(ev_verified[0], ctx->stream));
-    } else if ((rc = verify_commitments())) {
+    } else if ((rc = commit_work())) {
       return rc;
     }
     if (!phased) {
@@ -783,6 +787,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     if (pok_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[0], 0));
     else if ((rc = pok_all())) return rc;
     // ---- round-two proofs: statements, draws (right after the four key draws), prove, verify -----------------
+    PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[1], 0));  // the commitment points (side lane)
     PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt_items<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>((int)m, (int)n1, PH.stage, PH.prevstep, d_boff, PH.b, PH.r1, PH.Y, PH.rnd1, d_crec, d_rndc, PH.ebit, PH.bj, PH.stmt, PH.sec, PH.bi, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, (int)T)));
     for (size_t i = 0; i < T; ++i) ictr[i] = key_ctr(i / m, J) + 4, istream[i] = streams[i % m];
     PA_CUDA(ctx, cudaMemcpyAsync(PH.istream, istream.data(), T * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -810,7 +815,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     }
     if (s1_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_proved[0], 0));
     // ---- results ---------------------------------------------------------------------------------------------
-    if (verify) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_verified[0], 0));
+    PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_verified[0], 0));  // the commit phase (side lane)
     if ((rc = collect_commitments())) return rc;
     std::vector<unsigned char> r1ok(T), r2ok(T);
     PA_CUDA(ctx, cudaMemcpyAsync(r1ok.data(), PH.r1ok, T, cudaMemcpyDeviceToHost, ctx->stream));
