@@ -722,13 +722,25 @@ extern "C" int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job) {
         return rc;
       PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    // every party's Y and both B candidates of every step
-    if ((rc = dev_gather(ctx, PH.Xall, d_pub, PH.ixp, 64, TP))) return rc;
-    if ((rc = work_reserve(ctx, 2 * TP + 6 * T))) return rc;
-    PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)pc, PA_SCAN_T, 0, ctx->stream>>>(PH.Xall, 64, PH.soffN, (int)TP, work_jac(ctx))));
-    if ((rc = normalize_to(ctx, PH.Yall, TP))) return rc;
-    PA_LAUNCH(ctx, PA_K_VAR, (k_c22p_bcand<<<grid_for(2 * TP), PA_BLOCK, 0, ctx->stream>>>(PH.Yall, d_sec, d_soff, (int)pc, (int)pn, ctx->d_comb, work_jac(ctx), (int)TP)));
-    if ((rc = normalize_to(ctx, PH.Bcand, 2 * TP))) return rc;
+    // every party's Y and both B candidates of every step: on a side lane, beside the OT candidates below
+    if ((rc = lanes_init(ctx))) return rc;
+    struct LaneDrain {
+      pa_ctx *c;
+      ~LaneDrain() { cudaStreamSynchronize(c->lanes[0].stream); }
+    } drain{ctx};
+    PA_CUDA(ctx, cudaEventRecord(ctx->lane_ev[0], ctx->stream));
+    {
+      LaneScope ls(ctx, &ctx->lanes[0]);
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_ev[0], 0));
+      if ((rc = dev_gather(ctx, PH.Xall, d_pub, PH.ixp, 64, TP))) return rc;
+      if ((rc = work_reserve(ctx, 2 * TP))) return rc;
+      PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)pc, PA_SCAN_T, 0, ctx->stream>>>(PH.Xall, 64, PH.soffN, (int)TP, work_jac(ctx))));
+      if ((rc = normalize_to(ctx, PH.Yall, TP))) return rc;
+      PA_LAUNCH(ctx, PA_K_VAR, (k_c22p_bcand<<<grid_for(2 * TP), PA_BLOCK, 0, ctx->stream>>>(PH.Yall, d_sec, d_soff, (int)pc, (int)pn, ctx->d_comb, work_jac(ctx), (int)TP)));
+      if ((rc = normalize_to(ctx, PH.Bcand, 2 * TP))) return rc;
+      PA_CUDA(ctx, cudaEventRecord(ctx->lane_ev[1], ctx->stream));
+    }
+    if ((rc = work_reserve(ctx, 6 * T + 2))) return rc;
     if (T) {
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.st64, PH.st64 + T, nullptr, 1, PH.kk, (int)T, 1)));
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.st64 + 2 * T, PH.st64 + 3 * T, nullptr, 1, PH.mm, (int)T, 1)));
@@ -741,6 +753,7 @@ extern "C" int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job) {
       if ((rc = normalize_to(ctx, PH.L2, 6 * T))) return rc;
       if ((rc = dev_point_add(ctx, PH.L2, PH.L2 + 64 * 3 * T, PH.V, T, 1))) return rc;   // V = W0 / z^beta
     }
+    PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_ev[1], 0));  // the B candidates (side lane)
     PA_LAUNCH(ctx, PA_K_SUMINF, (k_c22p_walk<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)pn, (int)pc, (int)e, d_bits, d_boff, PH.Bcand, PH.V, d_inrace, PH.dsel, PH.alpha, PH.newd)));
     if (T) {
       PA_LAUNCH(ctx, PA_K_ENCODE, (k_c22p_select<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>((int)T, (int)pn, PH.sp, PH.alpha, PH.dsel, PH.L1, PH.L2, PH.Bcand, PH.r1rec, PH.otsrec, work_jac(ctx))));
