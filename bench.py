@@ -44,6 +44,32 @@ WIDE_VAR, WIDE_FIXED = 98793, 11299
 ECMUL_REF = os.path.join(ROOT, "oracle", "_ref", "ecmul_ref")
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Several ranks on one host: keep this process (and the pinned host buffers it is about to allocate, first
+    touch) on the CPU cores NVML reports as local to its GPU, so that the H2D / D2H copies of the end-to-end
+    figure do not cross sockets.  Returns the number of cores it was pinned to (0: left alone)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = gpu_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                phys = int(ids[gpu_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -395,6 +421,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    pinned_cores = pin_to_gpu_numa_node(local_rank) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -504,7 +531,7 @@ def main():
                        "l2": "working set per step ~420 MB (scalars, points, Jacobian scratch, outputs) > 126 MB L2; kernels are integer-pipe bound"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n, "d2h_bytes_per_step": 128 * n,
-                    "steps": e2e_steps, "bytes_match_device_run": same},
+                    "steps": e2e_steps, "bytes_match_device_run": same, "host_cores_pinned_per_rank": pinned_cores},
             "gpu_launches": int(launches),
             # The path is 256-bit integer arithmetic: neither HBM nor the tensor cores bound it, the
             # integer multiply pipe does ("fmaheavy" in ncu).  achieved = executed 32x32->64 multiply-adds
