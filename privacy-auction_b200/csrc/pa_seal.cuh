@@ -9,9 +9,15 @@
 //               (the reference lets each of the n bidders repeat the same
 //               deterministic checks; the verdicts are identical)
 //
+// Two schedules publish the same bytes: step-major (a batch of auctions in lock step, one kernel
+// sequence per protocol step on four streams) and, for ONE auction, phase-major (keys, Y and both
+// cryptogram candidates of every step in large launches, one thread block walks the steps, then
+// all proofs of all steps in one batch per kind) - see "single-auction schedule" below.
+//
 // Partitioning: independent auctions need no exchange at
-// all; ONE auction can be sharded by bidder slice, in which case the X_i of
-// round one and the b_i of round two are all-gathered once per step through a
+// all; ONE auction can be sharded by bidder slice, in which case published points
+// (step-major: X_i and b_i once per step; phase-major: the X_i of all steps at once,
+// then each rank's partial sum of cryptograms per step) are all-gathered through a
 // caller-supplied callback (NCCL over NVLink in bench.py / tests, see
 // INTEGRATION.md) into the device buffers d_recv.
 #pragma once
