@@ -60,6 +60,9 @@ int pa_sync(pa_ctx *ctx);
 const char *pa_last_error(pa_ctx *ctx);
 /* ABI version, bumped on incompatible change */
 int pa_abi_version(void);
+/* sizeof of the structs that cross the ABI, so that a binding can check its own layout:
+ * which = 0: pa_seal_job, 1: pa_ccs22_job, 2: pa_kernel_stat; anything else: 0 */
+size_t pa_abi_sizeof(int which);
 /* the CUDA stream (cudaStream_t) the context launches on, for callers that
  * time with CUDA events or enqueue their own copies */
 void *pa_ctx_stream(pa_ctx *ctx);

@@ -125,7 +125,10 @@ static int ensure(pa_ctx *ctx, unsigned char **buf, size_t *cap, size_t need) {
 
 extern "C" {
 
-int pa_abi_version(void) { return 1; }
+int pa_abi_version(void) { return 2; }  // 2: pa_seal_job.schedule / xchg_bytes, pa_ccs22_job.schedule
+size_t pa_abi_sizeof(int which) {
+  return which == 0 ? sizeof(pa_seal_job) : which == 1 ? sizeof(pa_ccs22_job) : which == 2 ? sizeof(pa_kernel_stat) : 0;
+}
 
 const char *pa_last_error(pa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     "pa_sync": (ctypes.c_int, [_ctx]),
     "pa_last_error": (ctypes.c_char_p, [_ctx]),
     "pa_abi_version": (ctypes.c_int, []),
+    "pa_abi_sizeof": (ctypes.c_size_t, [ctypes.c_int]),
     "pa_ctx_stream": (ctypes.c_void_p, [_ctx]),
     "pa_ctx_launches": (ctypes.c_uint64, [_ctx]),
     "pa_dev_alloc": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_void_p), _sz]),

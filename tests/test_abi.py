@@ -62,3 +62,15 @@ def test_product_does_not_reference_oracle():
                 if "pa_oracle" in txt or "oracle/" in txt or "libcrypto.so" in txt:
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_struct_layouts_match_the_binding(pa):
+    """the ctypes mirrors of the job structs must have the library's sizes (no GPU needed)"""
+    import ctypes
+    import sys
+    eng = sys.modules[pa.Engine.__module__]
+    lib = pa.load_library()
+    assert lib.pa_abi_sizeof(0) == ctypes.sizeof(eng.SealJob)
+    assert lib.pa_abi_sizeof(1) == ctypes.sizeof(eng.Ccs22Job)
+    assert lib.pa_abi_sizeof(2) == ctypes.sizeof(eng.KernelStat)
+    assert lib.pa_abi_sizeof(9) == 0 and lib.pa_abi_version() == 2
