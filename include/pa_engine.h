@@ -281,7 +281,8 @@ typedef struct {
   const uint32_t *c;            /* [n_auctions] bits per bid (<= 64) */
   const uint64_t *auction_ids;  /* [n_auctions] or NULL for 0 .. n_auctions-1 */
   const uint64_t *bids;         /* bids of the local bidders, auction-major, id order */
-  int verify;                   /* 0: skip verification, 1: verify every proof once */
+  int verify;                   /* 0: skip verification, 1: verify every proof once, k > 1: k times each (k = n - 1
+                                   is the work of the reference's all-pairs verification; same verdicts) */
   /* sharding of one auction (allgather != NULL requires n_auctions == 1) */
   uint32_t lo, hi, slice;
   pa_allgather_fn allgather;

@@ -364,6 +364,13 @@ k_seal_decide_shard(int s, int m, int limit, int world, const unsigned char *bit
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+// repeat a verification launch `vreps` times (see pa_seal_job.verify)
+#define PA_VREP(...)                           \
+  for (int rep_ = 0; rep_ < vreps; ++rep_) {  \
+    int rcv_ = (__VA_ARGS__);                 \
+    if (rcv_) return rcv_;                    \
+  }
+
 namespace {
 
 // Everything the runner needs on the device is carved out of ONE grow-only arena owned by the
@@ -434,6 +441,9 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   const bool sharded = job->allgather != nullptr;
   PA_ARGCHECK(ctx, !sharded || (A == 1 && job->hi > job->lo && job->hi <= job->n[0] && job->d_send && job->d_recv && job->slice >= job->hi - job->lo));
   const bool verify = job->verify != 0;
+  // verify = k > 1: every proof is verified k times (k = n - 1 is the work of the reference, where each of the n
+  // bidders repeats the same deterministic checks on everybody else); the verdicts do not change
+  const int vreps = job->verify > 1 ? job->verify : 1;
   // one unsharded auction: phase-major schedule unless the caller asks for the step-major one
   // (sharded: the exchange buffers must hold the X of all steps, and a Jacobian partial sum)
   bool phased = A == 1 && job->c[0] >= 1 && job->schedule != PA_SEAL_STEP_MAJOR &&
@@ -629,8 +639,8 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
         PA_CUDA(ctx, cudaMemsetAsync(d_cv + 3 * Mb, 1, Mb, ctx->stream));
         return PA_OK;
       }
-      if ((rc2 = verify_dev<PA_POK, 1>(ctx, d_crec + 192, d_crec + 64, d_cid, d_cv, 2 * Mb, LC2))) return rc2;  // verdicts interleaved A, B
-      if ((rc2 = verify_dev<PA_COM, 4>(ctx, d_crec + 384, d_crec, d_cid, d_cv + 2 * Mb, Mb, LC))) return rc2;
+      PA_VREP(verify_dev<PA_POK, 1>(ctx, d_crec + 192, d_crec + 64, d_cid, d_cv, 2 * Mb, LC2));  // verdicts interleaved A, B
+      PA_VREP(verify_dev<PA_COM, 4>(ctx, d_crec + 384, d_crec, d_cid, d_cv + 2 * Mb, Mb, LC));
       PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(d_cv, d_cv + 2 * Mb, d_cv + 3 * Mb, (int)Mb)));
       return PA_OK;
     };
@@ -674,7 +684,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       int rc2;
       if ((rc2 = prove_dev<PA_POK>(ctx, PH.r1, PH.rnd1, nullptr, nullptr, PH.pid, PH.rnd1 + 64, PH.r1 + 128, 2 * T, LR2))) return rc2;
       if (verify) {
-        if ((rc2 = verify_dev<PA_POK, 1>(ctx, PH.r1 + 128, PH.r1, PH.pid, PH.pokv, 2 * T, LR2))) return rc2;
+        PA_VREP(verify_dev<PA_POK, 1>(ctx, PH.r1 + 128, PH.r1, PH.pid, PH.pokv, 2 * T, LR2));
         PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(PH.pokv, nullptr, PH.r1ok, (int)T)));
       } else {
         PA_CUDA(ctx, cudaMemsetAsync(PH.r1ok, 1, T, ctx->stream));
@@ -809,15 +819,15 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       LaneScope ls(ctx, L_prove);
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[0], 0));
       if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
-      if (verify && (rc = verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1))) return rc;
+      if (verify) PA_VREP(verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1));
       PA_CUDA(ctx, cudaEventRecord(ev_proved[0], ctx->stream));
     } else if (n1) {
       if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
-      if (verify && (rc = verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1))) return rc;
+      if (verify) PA_VREP(verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1));
     }
     if (n2) {
       if ((rc = prove_dev<PA_S2>(ctx, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.pid + n1, PH.rnd2 + o_rnd, PH.proof + o_proof, n2))) return rc;
-      if (verify && (rc = verify_dev<PA_S2, 16>(ctx, PH.proof + o_proof, PH.stmt + o_stmt, PH.pid + n1, PH.r2ok + n1, n2))) return rc;
+      if (verify) PA_VREP(verify_dev<PA_S2, 16>(ctx, PH.proof + o_proof, PH.stmt + o_stmt, PH.pid + n1, PH.r2ok + n1, n2));
     }
     if (s1_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_proved[0], 0));
     // ---- results ---------------------------------------------------------------------------------------------
@@ -899,7 +909,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[par], 0));
       if ((rc = prove_dev<PA_POK>(ctx, B.r1, B.rnd1, nullptr, nullptr, B.pid, B.rnd1 + 64, B.r1 + 128, 2 * ma, LR2))) return rc;
       if (verify) {
-        if ((rc = verify_dev<PA_POK, 1>(ctx, B.r1 + 128, B.r1, B.pid, B.pokv, 2 * ma, LR2))) return rc;
+        PA_VREP(verify_dev<PA_POK, 1>(ctx, B.r1 + 128, B.r1, B.pid, B.pokv, 2 * ma, LR2));
         PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.pokv, nullptr, d_r1ok + step * m, (int)ma)));
       }
       if (want_r1) PA_CUDA(ctx, cudaMemcpyAsync(h_stage + off_r1 + step * m * 320, B.r1, ma * 320, cudaMemcpyDeviceToHost, ctx->stream));
@@ -958,11 +968,11 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_proved[par], 0));
       if (verify) {
         if (n1) {
-          if ((rc = verify_dev<PA_S1, 8>(ctx, B.proof, B.stmt, B.gid, B.pv, n1))) return rc;
+          PA_VREP(verify_dev<PA_S1, 8>(ctx, B.proof, B.stmt, B.gid, B.pv, n1));
           PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_scatter_u8<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(B.g, B.pv, d_r2ok + step * m, (int)n1)));
         }
         if (n2) {
-          if ((rc = verify_dev<PA_S2, 16>(ctx, B.proof + o_proof, B.stmt + o_stmt, B.gid + n1, B.pv + o_b, n2))) return rc;
+          PA_VREP(verify_dev<PA_S2, 16>(ctx, B.proof + o_proof, B.stmt + o_stmt, B.gid + n1, B.pv + o_b, n2));
           PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_scatter_u8<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(B.g + n1, B.pv + o_b, d_r2ok + step * m, (int)n2)));
         }
       }

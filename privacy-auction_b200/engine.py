@@ -402,7 +402,7 @@ class Engine:
             aid = (ctypes.c_uint64 * A)(*auction_ids)
             job.auction_ids = ctypes.addressof(aid)
             keep.append(aid)
-        job.verify = 1 if verify else 0
+        job.verify = int(verify)   # False/True, or k > 1: every proof verified k times (k = n - 1: the reference's all-pairs work)
         job.schedule = schedule   # 0 auto, 1 step-major, 2 phase-major (one unsharded auction)
         job.max_bid, job.ok = ctypes.addressof(max_bid), ctypes.addressof(ok)
         cb = None

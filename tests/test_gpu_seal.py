@@ -279,3 +279,15 @@ def test_runner_matches_oracle_n64_c12(engine, oracle):
         res = engine.seal_run(64012, [64], [12], bids, verify=True, sections=True, schedule=schedule)
         got = seal_flow.sections_to_transcripts(64012, [64], [12], bids, res)[0]
         assert got == want and fl.ok and res["ok"] == [True] and res["max_bid"] == [max(bids)], schedule
+
+
+def test_runner_all_pairs_work_same_verdicts(engine):
+    """verify = n - 1 repeats every verification as often as the reference's n bidders do (SURVEY.md Q9);
+    the published bytes and verdicts are those of verify = 1, in both schedules"""
+    rnd = random.Random(31)
+    n, c = 6, 7
+    bids = [rnd.randrange(1 << c) for _ in range(n)]
+    base = engine.seal_run(8, [n], [c], bids, verify=True, sections=True, schedule=1)
+    for schedule in (1, 2):
+        res = engine.seal_run(8, [n], [c], bids, verify=n - 1, sections=True, schedule=schedule)
+        assert res == base
