@@ -69,29 +69,33 @@ PA_HD void jac_dbl(jac &r, const jac &p) { jac_dbl_inl(r, p); }
 
 // r = 2p   (dbl-2009-l, 2M + 5S).  No point of order 2 exists (prime order).
 // Arranged as three stages of two independent products plus one final product.
+// Infinity needs no test: Z = 0 gives Z3 = 2 Y Z = 0, and infinity is recognised by Z alone.
 PA_HD void jac_dbl_inl(jac &r, const jac &p) {
-  if (jac_is_inf(p)) {
-    jac_set_inf(r);
-    return;
-  }
   fe A, B, C, D, E, F, t, yz;
   fe_sqr2(A, p.X, B, p.Y);  // A = X^2, B = Y^2
+#ifdef PA_DBL_2XB
+  // D = 4 X B by one product instead of 2((X + B)^2 - A - C): 3M + 4S, three field additions fewer
+  fe_sqrmul(C, B, t, p.X, B);  // C = B^2, t = X B
+  fe_shl<2>(D, t);
+  fe_mul3(E, A);  // E = 3A
+  fe_sqrmul(F, E, yz, p.Y, p.Z);  // F = E^2, yz = Y*Z
+  fe_dbl(r.Z, yz);  // Z3 = 2YZ
+  fe_shl<3>(t, t);  // 2D
+#else
   fe_add(t, p.X, B);
   fe_sqr2(C, B, t, t);  // C = B^2, t = (X + B)^2
   fe_sub(t, t, A);
   fe_sub(t, t, C);
   fe_dbl(D, t);  // D = 2((X+B)^2 - A - C)
-  fe_dbl(E, A);
-  fe_add(E, E, A);  // E = 3A
+  fe_mul3(E, A);  // E = 3A
   fe_sqrmul(F, E, yz, p.Y, p.Z);  // F = E^2, yz = Y*Z
   fe_dbl(r.Z, yz);  // Z3 = 2YZ
   fe_dbl(t, D);
+#endif
   fe_sub(r.X, F, t);  // X3 = F - 2D
   fe_sub(t, D, r.X);
   fe_mul(t, E, t);
-  fe_dbl(C, C);
-  fe_dbl(C, C);
-  fe_dbl(C, C);
+  fe_shl<3>(C, C);
   fe_sub(r.Y, t, C);  // Y3 = E(D - X3) - 8C
 }
 

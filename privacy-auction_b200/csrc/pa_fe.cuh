@@ -54,18 +54,16 @@ PA_HD void fe_sub(fe &r, const fe &a, const fe &b) {
   t[0] = sub_cc(a.v[0], b.v[0]);
 #pragma unroll
   for (int i = 1; i < 8; ++i) t[i] = subc_cc(a.v[i], b.v[i]);
-  u32 m = 0u - subc(0, 0) /* subc(0,0) = 0 - borrow */;
-  m = 0u - (m & 1u);  // all-ones if it borrowed: wrapped by 2^256 -> subtract C
+  u32 m = subc(0, 0);  // 0 - 0 - borrow: all-ones if it borrowed (wrapped by 2^256 -> subtract C)
   t[0] = sub_cc(t[0], PA_C0 & m);
   t[1] = subc_cc(t[1], 1u & m);
 #pragma unroll
   for (int i = 2; i < 8; ++i) t[i] = subc_cc(t[i], 0);
-  m = 0u - subc(0, 0);
-  m = 0u - (m & 1u);  // only when b was > p + a
+  // A second borrow happens only when the difference was below C (b > p + a): the value is then
+  // 2^256 - (C - t) with C - t < 2^33, so taking C off once more cannot borrow past limb 1.
+  m = subc(0, 0);
   t[0] = sub_cc(t[0], PA_C0 & m);
-  t[1] = subc_cc(t[1], 1u & m);
-#pragma unroll
-  for (int i = 2; i < 8; ++i) t[i] = subc_cc(t[i], 0);
+  t[1] = subc(t[1], 1u & m);
 #pragma unroll
   for (int i = 0; i < 8; ++i) r.v[i] = t[i];
 }
@@ -76,6 +74,42 @@ PA_HD void fe_neg(fe &r, const fe &a) {
   fe_sub(r, z, a);
 }
 PA_HD void fe_dbl(fe &r, const fe &a) { fe_add(r, a, a); }
+
+// t (8 limbs) += q * C for a small q (< 2^3), result weak.  If that wraps, the remainder is
+// < q * C < 2^36, so one more C stays inside limbs 0..1.
+PA_HD void fe_fold_small(fe &r, u32 t[8], u32 q) {
+  t[0] = add_cc(t[0], q * PA_C0);
+  t[1] = addc_cc(t[1], q);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) t[i] = addc_cc(t[i], 0);
+  u32 m = 0u - addc(0, 0);
+  t[0] = add_cc(t[0], PA_C0 & m);
+  t[1] = addc(t[1], 1u & m);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = t[i];
+}
+
+// r = a * 2^K (weak), K = 1..3: shift, then fold the K bits that left the top (q < 2^K) as q * C.
+// One pass instead of K additions (the 8C of a doubling: 23 instructions instead of 72).
+template <int K>
+PA_HD void fe_shl(fe &r, const fe &a) {
+  u32 t[8];
+  u32 q = a.v[7] >> (32 - K);
+#pragma unroll
+  for (int i = 7; i > 0; --i) t[i] = (a.v[i] << K) | (a.v[i - 1] >> (32 - K));
+  t[0] = a.v[0] << K;
+  fe_fold_small(r, t, q);
+}
+
+// r = 3a (weak) in one pass: a + (a << 1), the top (0..2) folded as q * C
+PA_HD void fe_mul3(fe &r, const fe &a) {
+  u32 t[8];
+  t[0] = add_cc(a.v[0], a.v[0] << 1);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t[i] = addc_cc(a.v[i], (a.v[i] << 1) | (a.v[i - 1] >> 31));
+  u32 q = addc(a.v[7] >> 31, 0);
+  fe_fold_small(r, t, q);
+}
 
 // canonical representative in [0, p)
 PA_HD void fe_canon(fe &r, const fe &a) {
@@ -165,28 +199,32 @@ PA_HD void mp_mul8(u32 t[16], const u32 a[8], const u32 b[8]) {
 PA_HD void fe_reduce512(fe &r, const u32 t[16]) {
   const u32 *hi = t + 8;
   u32 s[10];
-  // s = lo + 977 * hi   (even products then odd products, as in mp_mul8)
-  s[0] = mad_lo_cc(hi[0], PA_C0, t[0]);
-  s[1] = madc_hi_cc(hi[0], PA_C0, t[1]);
+  // s = lo + 977 * hi + (hi << 32) as two independent chains whose 64-bit addends are the naturally
+  // aligned limb pairs of t (no re-pairing moves between the passes):
+  //   e = lo + 977 * (hi[0], hi[2], hi[4], hi[6]) << (0, 64, 128, 192)
+  //   o = hi + 977 * (hi[1], hi[3], hi[5], hi[7]) << (0, 64, 128, 192),  standing one limb up
+  u32 e[9], o[9];
+  e[0] = mad_lo_cc(hi[0], PA_C0, t[0]);
+  e[1] = madc_hi_cc(hi[0], PA_C0, t[1]);
 #pragma unroll
   for (int j = 2; j < 8; j += 2) {
-    s[j] = madc_lo_cc(hi[j], PA_C0, t[j]);
-    s[j + 1] = madc_hi_cc(hi[j], PA_C0, t[j + 1]);
+    e[j] = madc_lo_cc(hi[j], PA_C0, t[j]);
+    e[j + 1] = madc_hi_cc(hi[j], PA_C0, t[j + 1]);
   }
-  s[8] = addc(0, 0);
-  s[1] = mad_lo_cc(hi[1], PA_C0, s[1]);
-  s[2] = madc_hi_cc(hi[1], PA_C0, s[2]);
+  e[8] = addc(0, 0);
+  o[0] = mad_lo_cc(hi[1], PA_C0, hi[0]);
+  o[1] = madc_hi_cc(hi[1], PA_C0, hi[1]);
 #pragma unroll
   for (int j = 3; j < 8; j += 2) {
-    s[j] = madc_lo_cc(hi[j], PA_C0, s[j]);
-    s[j + 1] = madc_hi_cc(hi[j], PA_C0, s[j + 1]);
+    o[j - 1] = madc_lo_cc(hi[j], PA_C0, hi[j - 1]);
+    o[j] = madc_hi_cc(hi[j], PA_C0, hi[j]);
   }
-  s[9] = addc(0, 0);
-  // s += hi << 32
-  s[1] = add_cc(s[1], hi[0]);
+  o[8] = addc(0, 0);
+  s[0] = e[0];
+  s[1] = add_cc(e[1], o[0]);
 #pragma unroll
-  for (int j = 2; j < 9; ++j) s[j] = addc_cc(s[j], hi[j - 1]);
-  s[9] = addc(s[9], 0);
+  for (int j = 2; j < 9; ++j) s[j] = addc_cc(e[j], o[j - 1]);
+  s[9] = addc(o[8], 0);
   // second fold: q = s[9]:s[8] (< 2^34);  s[0..7] += q * (2^32 + 977)
   u32 m0 = mul_lo(s[8], PA_C0);
   u32 m1 = mul_hi(s[8], PA_C0) + s[9] * PA_C0;  // < 2^11
@@ -306,8 +344,33 @@ static __device__ __noinline__ fe fe_sqr_call(fe a) {
   fe_sqr_inl(r, a);
   return r;
 }
-PA_D void fe_mul(fe &r, const fe &a, const fe &b) { r = fe_mul_call(a, b); }
-PA_D void fe_sqr(fe &r, const fe &a) { r = fe_sqr_call(a); }
+// The caller copies every operand into the callee's argument registers and every result out of
+// them, and ptxas emits those copies as IMAD.MOV — on the multiplier pipe, the one these kernels are
+// bound by (r01 ncu: 21 % of its cycles).  PA_OPQ_MODE makes the copies explicit as `or x, 0` with a
+// zero ptxas cannot see through (a __constant__ word), which can only issue on the ALU pipe (LOP3):
+// 1 = operands, 2 = results, 3 = both, 0 = leave the copies to ptxas.
+#ifndef PA_OPQ_MODE
+#define PA_OPQ_MODE 0
+#endif
+PA_D fe fe_opq(const fe &a) {
+  fe r;
+  u32 z = pa_opq_z;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm volatile("or.b32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(z));
+  return r;
+}
+PA_D void fe_mul(fe &r, const fe &a, const fe &b) {
+  if (PA_OPQ_MODE == 3) r = fe_opq(fe_mul_call(fe_opq(a), fe_opq(b)));
+  else if (PA_OPQ_MODE == 2) r = fe_opq(fe_mul_call(a, b));
+  else if (PA_OPQ_MODE == 1) r = fe_mul_call(fe_opq(a), fe_opq(b));
+  else r = fe_mul_call(a, b);
+}
+PA_D void fe_sqr(fe &r, const fe &a) {
+  if (PA_OPQ_MODE == 3) r = fe_opq(fe_sqr_call(fe_opq(a)));
+  else if (PA_OPQ_MODE == 2) r = fe_opq(fe_sqr_call(a));
+  else if (PA_OPQ_MODE == 1) r = fe_sqr_call(fe_opq(a));
+  else r = fe_sqr_call(a);
+}
 #else
 PA_HD void fe_mul(fe &r, const fe &a, const fe &b) { fe_mul_inl(r, a, b); }
 PA_HD void fe_sqr(fe &r, const fe &a) { fe_sqr_inl(r, a); }
@@ -323,17 +386,23 @@ struct fe2 {
 };
 #if defined(__CUDA_ARCH__) && !defined(PA_FE_PAIRS) && !defined(PA_FE_INLINE)  // default: the two products as two calls
 PA_D void fe_mul2(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1) {
-  fe x = fe_mul_call(a0, b0), y = fe_mul_call(a1, b1);
+  fe x, y;
+  fe_mul(x, a0, b0);
+  fe_mul(y, a1, b1);
   r0 = x;
   r1 = y;
 }
 PA_D void fe_sqr2(fe &r0, const fe &a0, fe &r1, const fe &a1) {
-  fe x = fe_sqr_call(a0), y = fe_sqr_call(a1);
+  fe x, y;
+  fe_sqr(x, a0);
+  fe_sqr(y, a1);
   r0 = x;
   r1 = y;
 }
 PA_D void fe_sqrmul(fe &r0, const fe &a0, fe &r1, const fe &a1, const fe &b1) {
-  fe x = fe_sqr_call(a0), y = fe_mul_call(a1, b1);
+  fe x, y;
+  fe_sqr(x, a0);
+  fe_mul(y, a1, b1);
   r0 = x;
   r1 = y;
 }

@@ -24,6 +24,10 @@
 typedef uint32_t u32;
 typedef uint64_t u64;
 
+#if defined(__CUDACC__)
+__constant__ u32 pa_opq_z;  // always 0, never written: an operand ptxas cannot fold (pa_fe.cuh, PA_OPQ_MODE)
+#endif
+
 #if defined(__CUDA_ARCH__)
 
 PA_D u32 add_cc(u32 a, u32 b) { u32 r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }

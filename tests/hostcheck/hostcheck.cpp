@@ -21,6 +21,10 @@ void hc_fe_op(int op, const unsigned char *a, const unsigned char *b, unsigned c
   case 6: r = x; break;
   case 7: { fe_set_zero(r); r.v[0] = fe_is_zero(x); fe_to_be(out, r); return; }
   case 8: { fe_set_zero(r); r.v[0] = fe_eq(x, y); fe_to_be(out, r); return; }
+  case 9: fe_shl<1>(r, x); break;
+  case 10: fe_shl<2>(r, x); break;
+  case 11: fe_shl<3>(r, x); break;
+  case 12: fe_mul3(r, x); break;
   default: fe_set_zero(r);
   }
   fe_canon(r, r);

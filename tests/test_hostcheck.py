@@ -58,6 +58,9 @@ def test_field_ops(hc):
         assert mp(a, a, 1) == a * a
         assert op(1, a) == a * a % P
         assert op(5, a) == (-a) % P
+        for k in (1, 2, 3):
+            assert op(8 + k, a) == (a << k) % P
+        assert op(12, a) == 3 * a % P
         assert op(6, a) == a % P
         assert op(7, a) == int(a % P == 0)
     for a in vals[:40]:
