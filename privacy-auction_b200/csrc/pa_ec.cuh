@@ -73,15 +73,6 @@ PA_HD void jac_dbl(jac &r, const jac &p) { jac_dbl_inl(r, p); }
 PA_HD void jac_dbl_inl(jac &r, const jac &p) {
   fe A, B, C, D, E, F, t, yz;
   fe_sqr2(A, p.X, B, p.Y);  // A = X^2, B = Y^2
-#ifdef PA_DBL_2XB
-  // D = 4 X B by one product instead of 2((X + B)^2 - A - C): 3M + 4S, three field additions fewer
-  fe_sqrmul(C, B, t, p.X, B);  // C = B^2, t = X B
-  fe_shl<2>(D, t);
-  fe_mul3(E, A);  // E = 3A
-  fe_sqrmul(F, E, yz, p.Y, p.Z);  // F = E^2, yz = Y*Z
-  fe_dbl(r.Z, yz);  // Z3 = 2YZ
-  fe_shl<3>(t, t);  // 2D
-#else
   fe_add(t, p.X, B);
   fe_sqr2(C, B, t, t);  // C = B^2, t = (X + B)^2
   fe_sub(t, t, A);
@@ -91,7 +82,6 @@ PA_HD void jac_dbl_inl(jac &r, const jac &p) {
   fe_sqrmul(F, E, yz, p.Y, p.Z);  // F = E^2, yz = Y*Z
   fe_dbl(r.Z, yz);  // Z3 = 2YZ
   fe_dbl(t, D);
-#endif
   fe_sub(r.X, F, t);  // X3 = F - 2D
   fe_sub(t, D, r.X);
   fe_mul(t, E, t);
@@ -100,8 +90,10 @@ PA_HD void jac_dbl_inl(jac &r, const jac &p) {
 }
 
 // r = p + q, q affine   (8M + 3S), in six stages of (mostly) two independent products
-PA_HD void jac_madd_inl(jac &r, const jac &p, const aff &q) {
-  if (aff_is_inf(q)) {
+// Q_NOT_INF: the caller knows q is a real point (window-table entries), so the test is left out.
+template <bool Q_NOT_INF>
+PA_HD void jac_madd_t(jac &r, const jac &p, const aff &q) {
+  if (!Q_NOT_INF && aff_is_inf(q)) {
     r = p;
     return;
   }
@@ -136,6 +128,8 @@ PA_HD void jac_madd_inl(jac &r, const jac &p, const aff &q) {
   r.Z = z3;
   fe_sub(r.Y, v, yh);  // Y3 = R(V - X3) - Y1 H^3
 }
+
+PA_HD void jac_madd_inl(jac &r, const jac &p, const aff &q) { jac_madd_t<false>(r, p, q); }
 
 // r = p + q   (12M + 4S)
 PA_HD void jac_add_inl(jac &r, const jac &p, const jac &q) {

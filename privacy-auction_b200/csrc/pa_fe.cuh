@@ -68,10 +68,19 @@ PA_HD void fe_sub(fe &r, const fe &a, const fe &b) {
   for (int i = 0; i < 8; ++i) r.v[i] = t[i];
 }
 
+// r = -a (weak): p - a = ~a - (C - 1) mod 2^256.  It borrows only for a > p (a = p + e, e < C);
+// the wrapped value 2^256 - e then needs C taken off once more, which stays inside limbs 0..1.
 PA_HD void fe_neg(fe &r, const fe &a) {
-  fe z;
-  fe_set_zero(z);
-  fe_sub(r, z, a);
+  u32 t[8];
+  t[0] = sub_cc(~a.v[0], PA_C0 - 1u);
+  t[1] = subc_cc(~a.v[1], 1u);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) t[i] = subc_cc(~a.v[i], 0);
+  u32 m = subc(0, 0);
+  t[0] = sub_cc(t[0], PA_C0 & m);
+  t[1] = subc(t[1], 1u & m);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = t[i];
 }
 PA_HD void fe_dbl(fe &r, const fe &a) { fe_add(r, a, a); }
 
@@ -148,19 +157,15 @@ PA_HD void mp_mul8(u32 t[16], const u32 a[8], const u32 b[8]) {
   u32 ev[16], od[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) ev[i] = od[i] = 0;
+  // After row i the partial product is below 2^(32 (i + 9)), so neither accumulator can pass limb
+  // i + 8.  The chain that could carry out of limb i + 7 runs second, and its carry is added into
+  // the OTHER accumulator's word for limb i + 8, which the first chain has just written as the high
+  // half of its top pair: one add, and the words above stay untouched zeros, so the next row's top
+  // product takes a zero addend (no carry word and no zero register to pair it with).
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if ((i & 1) == 0) {
-      // a[even] * b[i] -> ev[i+j .. i+j+1]
-      ev[i + 0] = mad_lo_cc(a[0], b[i], ev[i + 0]);
-      ev[i + 1] = madc_hi_cc(a[0], b[i], ev[i + 1]);
-#pragma unroll
-      for (int j = 2; j < 8; j += 2) {
-        ev[i + j] = madc_lo_cc(a[j], b[i], ev[i + j]);
-        ev[i + j + 1] = madc_hi_cc(a[j], b[i], ev[i + j + 1]);
-      }
-      ev[i + 8] = addc(ev[i + 8], 0);
-      // a[odd] * b[i] -> limb i+j (odd) = od[i+j-1 .. i+j]
+      // a[odd] * b[i] -> limb i+j (odd) = od[i+j-1 .. i+j]; top word od[i+7] is limb i+8
       od[i + 0] = mad_lo_cc(a[1], b[i], od[i + 0]);
       od[i + 1] = madc_hi_cc(a[1], b[i], od[i + 1]);
 #pragma unroll
@@ -168,18 +173,17 @@ PA_HD void mp_mul8(u32 t[16], const u32 a[8], const u32 b[8]) {
         od[i + j - 1] = madc_lo_cc(a[j], b[i], od[i + j - 1]);
         od[i + j] = madc_hi_cc(a[j], b[i], od[i + j]);
       }
-      // partial sums so far fit below limb i+9, so no carry leaves od[i+7]
-    } else {
-      // a[even] * b[i] -> limb i+j (odd) = od[i+j-1 .. i+j]
-      od[i - 1] = mad_lo_cc(a[0], b[i], od[i - 1]);
-      od[i + 0] = madc_hi_cc(a[0], b[i], od[i + 0]);
+      // a[even] * b[i] -> ev[i+j .. i+j+1]; carry out of limb i+7 goes to od's limb i+8
+      ev[i + 0] = mad_lo_cc(a[0], b[i], ev[i + 0]);
+      ev[i + 1] = madc_hi_cc(a[0], b[i], ev[i + 1]);
 #pragma unroll
       for (int j = 2; j < 8; j += 2) {
-        od[i + j - 1] = madc_lo_cc(a[j], b[i], od[i + j - 1]);
-        od[i + j] = madc_hi_cc(a[j], b[i], od[i + j]);
+        ev[i + j] = madc_lo_cc(a[j], b[i], ev[i + j]);
+        ev[i + j + 1] = madc_hi_cc(a[j], b[i], ev[i + j + 1]);
       }
       od[i + 7] = addc(od[i + 7], 0);
-      // a[odd] * b[i] -> ev[i+j .. i+j+1]
+    } else {
+      // a[odd] * b[i] -> ev[i+j .. i+j+1]; top word ev[i+8] is limb i+8
       ev[i + 1] = mad_lo_cc(a[1], b[i], ev[i + 1]);
       ev[i + 2] = madc_hi_cc(a[1], b[i], ev[i + 2]);
 #pragma unroll
@@ -187,6 +191,15 @@ PA_HD void mp_mul8(u32 t[16], const u32 a[8], const u32 b[8]) {
         ev[i + j] = madc_lo_cc(a[j], b[i], ev[i + j]);
         ev[i + j + 1] = madc_hi_cc(a[j], b[i], ev[i + j + 1]);
       }
+      // a[even] * b[i] -> limb i+j (odd) = od[i+j-1 .. i+j]; carry out of limb i+7 goes to ev's limb i+8
+      od[i - 1] = mad_lo_cc(a[0], b[i], od[i - 1]);
+      od[i + 0] = madc_hi_cc(a[0], b[i], od[i + 0]);
+#pragma unroll
+      for (int j = 2; j < 8; j += 2) {
+        od[i + j - 1] = madc_lo_cc(a[j], b[i], od[i + j - 1]);
+        od[i + j] = madc_hi_cc(a[j], b[i], od[i + j]);
+      }
+      ev[i + 8] = addc(ev[i + 8], 0);
     }
   }
   t[0] = ev[0];
@@ -261,44 +274,33 @@ PA_HD void mp_sqr8(u32 t[16], const u32 a[8]) {
   u32 ev[16], od[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) ev[i] = od[i] = 0;
+  // Rows 0..i of the cross products sum to less than 2^(32 (i + 9)).  In row i the chain that
+  // contains j = 7 ends on limbs (i+7, i+8) and cannot carry out; it runs first.  The other chain
+  // ends on limbs (i+6, i+7) and its carry is added into the first chain's accumulator at limb
+  // i + 8 (as in mp_mul8: no carry word, no zero register to pair it with).
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
-    // row i: products a[j]*a[i] for j > i, landing on limb i+j
-    // first the j with (i+j) even, then the j with (i+j) odd
-    bool first = true;
 #pragma unroll
-    for (int j = i + 1; j < 8; ++j) {
-      if (((i + j) & 1) == 0) {
-        if (first) {
-          ev[i + j] = mad_lo_cc(a[j], a[i], ev[i + j]);
-          first = false;
-        } else {
-          ev[i + j] = madc_lo_cc(a[j], a[i], ev[i + j]);
-        }
-        ev[i + j + 1] = madc_hi_cc(a[j], a[i], ev[i + j + 1]);
-      }
-    }
-    if (!first) {
-      // highest even landing limb of this row is h = i + jmax; carry into h+2
-      int jmax = ((i + 7) & 1) == 0 ? 7 : 6;
-      if (i + jmax + 2 < 16) ev[i + jmax + 2] = addc(ev[i + jmax + 2], 0);
-    }
-    first = true;
+    for (int pass = 0; pass < 2; ++pass) {
+      // pass 0: landing parity of j = 7; pass 1: the other parity
+      const int par = (pass == 0) ? ((i + 7) & 1) : ((i + 6) & 1);
+      bool first = true;
 #pragma unroll
-    for (int j = i + 1; j < 8; ++j) {
-      if (((i + j) & 1) == 1) {
-        if (first) {
-          od[i + j - 1] = mad_lo_cc(a[j], a[i], od[i + j - 1]);
-          first = false;
+      for (int j = i + 1; j < 8; ++j) {
+        if (((i + j) & 1) != par) continue;
+        if (par == 0) {
+          ev[i + j] = first ? mad_lo_cc(a[j], a[i], ev[i + j]) : madc_lo_cc(a[j], a[i], ev[i + j]);
+          ev[i + j + 1] = madc_hi_cc(a[j], a[i], ev[i + j + 1]);
         } else {
-          od[i + j - 1] = madc_lo_cc(a[j], a[i], od[i + j - 1]);
+          od[i + j - 1] = first ? mad_lo_cc(a[j], a[i], od[i + j - 1]) : madc_lo_cc(a[j], a[i], od[i + j - 1]);
+          od[i + j] = madc_hi_cc(a[j], a[i], od[i + j]);
         }
-        od[i + j] = madc_hi_cc(a[j], a[i], od[i + j]);
+        first = false;
       }
-    }
-    if (!first) {
-      int jmax = ((i + 7) & 1) == 1 ? 7 : 6;
-      if (i + jmax + 1 < 16) od[i + jmax + 1] = addc(od[i + jmax + 1], 0);
+      if (pass == 1 && !first) {  // carry out of limb i + 7 -> limb i + 8 of the other accumulator
+        if (par == 0) od[i + 7] = addc(od[i + 7], 0);
+        else ev[i + 8] = addc(ev[i + 8], 0);
+      }
     }
   }
   // cross = ev + (od << 32)

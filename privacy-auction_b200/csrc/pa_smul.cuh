@@ -331,7 +331,7 @@ PA_HD void strauss(jac &r, const jac &P, const sc &a, const jac &Q, const sc &b)
       aff q;
       q.x = lam ? T.bx[idx] : T.x[idx];
       if ((d < 0) != neg) fe_neg(q.y, T.y[idx]); else q.y = T.y[idx];
-      jac_madd_inl(r, r, q);
+      jac_madd_t<true>(r, r, q);  // k * P' is never infinity for k = 1..8 (prime order)
     }
   }
   if (!jac_is_inf(r)) fe_mul(r.Z, r.Z, zeta);  // back from the isomorphic curve
