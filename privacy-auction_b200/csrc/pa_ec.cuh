@@ -75,14 +75,12 @@ PA_HD void jac_dbl_inl(jac &r, const jac &p) {
   fe_sqr2(A, p.X, B, p.Y);  // A = X^2, B = Y^2
   fe_add(t, p.X, B);
   fe_sqr2(C, B, t, t);  // C = B^2, t = (X + B)^2
-  fe_sub(t, t, A);
-  fe_sub(t, t, C);
+  fe_sub2(t, t, A, C);
   fe_dbl(D, t);  // D = 2((X+B)^2 - A - C)
   fe_mul3(E, A);  // E = 3A
   fe_sqrmul(F, E, yz, p.Y, p.Z);  // F = E^2, yz = Y*Z
   fe_dbl(r.Z, yz);  // Z3 = 2YZ
-  fe_dbl(t, D);
-  fe_sub(r.X, F, t);  // X3 = F - 2D
+  fe_sub2(r.X, F, D, D);  // X3 = F - 2D
   fe_sub(t, D, r.X);
   fe_mul(t, E, t);
   fe_shl<3>(C, C);
@@ -119,9 +117,7 @@ PA_HD void jac_madd_t(jac &r, const jac &p, const aff &q) {
   }
   fe_sqr2(hh, h, r2, rr);              // H^2, R^2
   fe_mul2(hhh, h, hh, v, p.X, hh);     // H^3, V = X1 H^2
-  fe_sub(t, r2, hhh);
-  fe_sub(t, t, v);
-  fe_sub(t, t, v);  // X3 = R^2 - H^3 - 2V
+  fe_sub3(t, r2, hhh, v, v);  // X3 = R^2 - H^3 - 2V
   fe_sub(v, v, t);
   fe_mul2(yh, p.Y, hhh, v, rr, v);     // Y1 H^3, R (V - X3)
   r.X = t;
@@ -166,9 +162,7 @@ PA_HD void jac_add_inl(jac &r, const jac &p, const jac &q) {
   fe_mul(t, p.Z, q.Z);
   fe_mul(r.Z, t, h);
   fe_sqr(t, rr);
-  fe_sub(t, t, hhh);
-  fe_sub(t, t, v);
-  fe_sub(t, t, v);
+  fe_sub3(t, t, hhh, v, v);
   fe_mul(hhh, s1, hhh);
   r.X = t;
   fe_sub(v, v, t);

@@ -68,6 +68,42 @@ PA_HD void fe_sub(fe &r, const fe &a, const fe &b) {
   for (int i = 0; i < 8; ++i) r.v[i] = t[i];
 }
 
+// r = a - b - c [- d] (weak) with ONE fold: the subtractions run mod 2^256 while the borrows are
+// counted (n <= 3), then n * C is taken off.  If that borrows, the value is 2^256 - e with
+// e < n C < 2^34, and one more C stays inside limbs 0..1.
+template <int N>
+PA_HD void fe_sub_n(fe &r, const fe &a, const fe *const *s) {
+  u32 t[8];
+  u32 q = 0;  // minus the number of borrows
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = a.v[i];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    t[0] = sub_cc(t[0], s[k]->v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t[i] = subc_cc(t[i], s[k]->v[i]);
+    q = subc(q, 0);
+  }
+  u32 n = 0u - q;
+  t[0] = sub_cc(t[0], n * PA_C0);
+  t[1] = subc_cc(t[1], n);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) t[i] = subc_cc(t[i], 0);
+  u32 m = subc(0, 0);
+  t[0] = sub_cc(t[0], PA_C0 & m);
+  t[1] = subc(t[1], 1u & m);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = t[i];
+}
+PA_HD void fe_sub2(fe &r, const fe &a, const fe &b, const fe &c) {
+  const fe *s[2] = {&b, &c};
+  fe_sub_n<2>(r, a, s);
+}
+PA_HD void fe_sub3(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+  const fe *s[3] = {&b, &c, &d};
+  fe_sub_n<3>(r, a, s);
+}
+
 // r = -a (weak): p - a = ~a - (C - 1) mod 2^256.  It borrows only for a > p (a = p + e, e < C);
 // the wrapped value 2^256 - e then needs C taken off once more, which stays inside limbs 0..1.
 PA_HD void fe_neg(fe &r, const fe &a) {

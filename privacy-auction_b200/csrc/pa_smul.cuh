@@ -75,7 +75,7 @@ PA_HD void fixed_base_mul(jac &r, const sc &k, const u32 *tab) {
       aff q;
       comb_load(q, tab, w, (u32)(sd < 0 ? -sd : sd));
       if (sd < 0) fe_neg(q.y, q.y);
-      jac_madd(r, r, q);
+      jac_madd_t<true>(r, r, q);  // inlined once in this loop; comb entries are never infinity
     }
   }
 }
@@ -216,9 +216,7 @@ PA_HD void jac_madd_zr(jac &r, fe &zr, const jac &p, const fe &qx, const fe &qy)
   fe_mul(v, p.X, hh);
   fe_mul(r.Z, p.Z, h);
   fe_sqr(t, rr);
-  fe_sub(t, t, hhh);
-  fe_sub(t, t, v);
-  fe_sub(t, t, v);
+  fe_sub3(t, t, hhh, v, v);
   fe_mul(hhh, p.Y, hhh);
   r.X = t;
   fe_sub(v, v, t);

@@ -25,6 +25,9 @@ void hc_fe_op(int op, const unsigned char *a, const unsigned char *b, unsigned c
   case 10: fe_shl<2>(r, x); break;
   case 11: fe_shl<3>(r, x); break;
   case 12: fe_mul3(r, x); break;
+  case 13: fe_sub2(r, x, y, y); break;
+  case 14: fe_sub3(r, x, y, x, y); break;
+  case 15: { fe z; fe_neg(z, x); fe_sub3(r, z, y, y, y); break; }
   default: fe_set_zero(r);
   }
   fe_canon(r, r);

@@ -54,6 +54,9 @@ def test_field_ops(hc):
             assert op(0, a, b) == a * b % P
             assert op(2, a, b) == (a + b) % P
             assert op(3, a, b) == (a - b) % P
+            assert op(13, a, b) == (a - 2 * b) % P
+            assert op(14, a, b) == (-2 * b) % P
+            assert op(15, a, b) == (-a - 3 * b) % P
             assert op(8, a, b) == int((a - b) % P == 0)
         assert mp(a, a, 1) == a * a
         assert op(1, a) == a * a % P
