@@ -274,25 +274,21 @@ PA_HD void fe_reduce512(fe &r, const u32 t[16]) {
 #pragma unroll
   for (int j = 2; j < 9; ++j) s[j] = addc_cc(e[j], o[j - 1]);
   s[9] = addc(o[8], 0);
-  // second fold: q = s[9]:s[8] (< 2^34);  s[0..7] += q * (2^32 + 977)
+  // second fold: q = s[9]:s[8] (< 2^34);  s[0..7] += q * (2^32 + 977) = w2:w1:w0 (< 2^67), one chain
   u32 m0 = mul_lo(s[8], PA_C0);
-  u32 m1 = mul_hi(s[8], PA_C0) + s[9] * PA_C0;  // < 2^11
+  u32 m1 = mul_hi(s[8], PA_C0) + s[9] * PA_C0;  // < 2^13
+  u32 w1 = add_cc(m1, s[8]);
+  u32 w2 = addc(s[9], 0);
   s[0] = add_cc(s[0], m0);
-  s[1] = addc_cc(s[1], m1);
-#pragma unroll
-  for (int j = 2; j < 8; ++j) s[j] = addc_cc(s[j], 0);
-  u32 c1 = addc(0, 0);
-  s[1] = add_cc(s[1], s[8]);
-  s[2] = addc_cc(s[2], s[9]);
+  s[1] = addc_cc(s[1], w1);
+  s[2] = addc_cc(s[2], w2);
 #pragma unroll
   for (int j = 3; j < 8; ++j) s[j] = addc_cc(s[j], 0);
-  u32 c2 = addc(0, 0);
-  // at most one of c1, c2 is set and then the remainder is < 2^68
-  u32 m = 0u - (c1 | c2);
+  // if that wrapped, the remainder is < 2^67 and one more C stays inside limbs 0..2
+  u32 m = 0u - addc(0, 0);
   s[0] = add_cc(s[0], PA_C0 & m);
   s[1] = addc_cc(s[1], 1u & m);
-  s[2] = addc_cc(s[2], 0);
-  s[3] = addc(s[3], 0);
+  s[2] = addc(s[2], 0);
 #pragma unroll
   for (int i = 0; i < 8; ++i) r.v[i] = s[i];
 }
