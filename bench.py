@@ -39,8 +39,8 @@ WORKLOAD = "configs[2]: batched EC microbench, 2^20 fixed-base + 2^20 variable-b
 # SURVEY.md §8(d) algorithmic work figures (nominal double-and-add / comb on 32-bit IMAD)
 FM_VAR, FM_FIXED, IMAD_PER_FM = 2900, 712, 272
 # Executed 32x32->64 multiply-adds (SASS IMAD.WIDE) per scalar multiplication, counted by ncu on the
-# shipped kernels (profiles/r01d_k_var_base_opcode_mix.txt; the fixed-base figure from the same capture)
-WIDE_VAR, WIDE_FIXED = 98793, 11299
+# shipped kernels (profiles/r01f_opcode_mix.txt, both kernels from the same capture)
+WIDE_VAR, WIDE_FIXED = 100233, 11299
 ECMUL_REF = os.path.join(ROOT, "oracle", "_ref", "ecmul_ref")
 
 
@@ -544,14 +544,14 @@ def main():
             # per second, peak = the same instruction in a register-only loop on this GPU.
             "roofline": {"bound": "int-multiply pipe (IMAD.WIDE on fmaheavy); not hbm, not tensor", "kernel": "k_var_base",
                          "achieved": achieved / 1e12, "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE/s", "frac": achieved / peak_wide,
-                         "traffic": 2.27e9,  # dram read + write per launch, ncu --set full (profiles/r01d_ncu_full_k_var_base_summary.csv)
+                         "traffic": 3.53e9,  # dram read + write per launch, ncu --set full (profiles/r01f_ncu_full_k_var_base_summary.csv)
                          "traffic_note": "algorithmic bytes are 0.2 GB per launch (64 B point + 32 B scalar in, 96 B Jacobian out); the rest is "
-                                         "write-back and refill of per-thread stack lines (window tables and register spills at 96 registers), "
-                                         "116 GB/s = 1.5 % of HBM bandwidth, not on the critical path",
+                                         "write-back and refill of per-thread stack lines (window tables and register spills at 80 registers), "
+                                         "206 GB/s = 3.1 % of HBM bandwidth, not on the critical path (long_scoreboard 0.48 of 11.6 stall cycles per issue)",
                          "peak_source": "measured on this GPU by pa_measure_int_peak (register-only IMAD.WIDE loop); MEASURED_PEAKS.json has no integer figure",
                          "units_per_launch": n, "per_unit": f"{WIDE_VAR} IMAD.WIDE per variable-base mult (ncu count on this kernel)",
                          "avg_launch_ms": var_ms, "share_of_kernel_time": var["total_ms"] / total_k_ms,
-                         "ncu": "fmaheavy pipe 81.0 % active, top stall math_pipe_throttle; 21 % of the pipe's cycles are IMAD.MOV register moves",
+                         "ncu": "fmaheavy pipe 85.1 % active, top stalls math_pipe_throttle and wait; 298 k instructions per multiplication, a third of them IMAD.WIDE",
                          "nominal_algorithm": {"per_unit": f"{FM_VAR} field mults x {IMAD_PER_FM} 32-bit IMAD (SURVEY.md 8d, plain double-and-add)",
                                                "achieved_timad_s": nominal / 1e12, "peak_timad_s": peak_imad / 1e12, "frac": nominal / peak_imad,
                                                "note": "above 1 because GLV + co-Z tables execute ~1,800 field mults instead of 2,900"}},

@@ -334,8 +334,14 @@ struct PArg {
 // Measured end to end (2^20 + 2^20 mults per step): 2^17 items 82.7 M/s, 10 blocks per SM 84.7, 20: 85.2;
 // a short first and last chunk (5 blocks per SM) shortens the copies that nothing overlaps: 86.5; chunks alternating
 // between two compute streams (the next chunk's blocks fill the SMs while the previous chunk's last wave drains): 90.1.
+#ifndef PA_PIPE_CHUNK_BLOCKS
+#define PA_PIPE_CHUNK_BLOCKS 20  // blocks per SM in a chunk
+#endif
+#ifndef PA_PIPE_EDGE_BLOCKS
+#define PA_PIPE_EDGE_BLOCKS 5  // ... in the first and the last chunk
+#endif
 const size_t PA_PIPE_UNIT = (size_t)148 * PA_BLOCK;
-const size_t PA_PIPE_CHUNK = PA_PIPE_UNIT * 20, PA_PIPE_EDGE = PA_PIPE_UNIT * 5;
+const size_t PA_PIPE_CHUNK = PA_PIPE_UNIT * PA_PIPE_CHUNK_BLOCKS, PA_PIPE_EDGE = PA_PIPE_UNIT * PA_PIPE_EDGE_BLOCKS;
 
 template <typename F>
 int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
