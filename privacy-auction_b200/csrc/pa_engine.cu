@@ -334,6 +334,7 @@ struct PArg {
 // Measured end to end (2^20 + 2^20 mults per step): 2^17 items 82.7 M/s, 10 blocks per SM 84.7, 20: 85.2;
 // a short first and last chunk (5 blocks per SM) shortens the copies that nothing overlaps: 86.5; chunks alternating
 // between two compute streams (the next chunk's blocks fill the SMs while the previous chunk's last wave drains): 90.1.
+// With k_var_base at 6 resident blocks (end of r01: 100.7 M/s), chunks of 24 / 6 blocks per SM measured 100.5: left at 20 / 5.
 #ifndef PA_PIPE_CHUNK_BLOCKS
 #define PA_PIPE_CHUNK_BLOCKS 20  // blocks per SM in a chunk
 #endif

@@ -18,7 +18,7 @@
 // (2^20 variable-base mults): 3 CTAs (136 regs) 21.2 ms, 4 (128 regs) 20.0 ms, 5 (96 regs,
 // 360 B spilled) 19.7 ms — more warps hide the fixed-latency dependency stalls of the
 // multiply-add chains better than the spills cost.  With the leaner field arithmetic of late r01:
-// 5 CTAs 17.62 ms, 6 CTAs (80 regs) 17.48 ms.
+// 5 CTAs 17.21 ms, 6 CTAs (80 regs) 17.12 ms.
 #ifndef PA_VAR_MINBLOCKS
 #define PA_VAR_MINBLOCKS 6
 #endif
