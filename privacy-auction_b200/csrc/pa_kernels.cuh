@@ -22,6 +22,8 @@
 #ifndef PA_VAR_MINBLOCKS
 #define PA_VAR_MINBLOCKS 6
 #endif
+// The two-base kernels (proof checks and proof ops: two window tables per thread) stay at 4: the
+// n = 1000 auction takes 37.3 ms at 4, 39.8 at 5, 42.3 at 6 resident blocks (end of r01).
 #ifndef PA_OP_MINBLOCKS
 #define PA_OP_MINBLOCKS 4
 #endif
