@@ -38,10 +38,20 @@ UNIT = "scalar-mults/s"
 WORKLOAD = "configs[2]: batched EC microbench, 2^20 fixed-base + 2^20 variable-base scalar mults on secp256k1 per GPU per step"
 # SURVEY.md §8(d) algorithmic work figures (nominal double-and-add / comb on 32-bit IMAD)
 FM_VAR, FM_FIXED, IMAD_PER_FM = 2900, 712, 272
-# Executed 32x32->64 multiply-adds (SASS IMAD.WIDE) per scalar multiplication, counted by ncu on the
-# shipped kernels (profiles/r01f_opcode_mix.txt, both kernels from the same capture)
+# Executed 32x32->64 multiply-adds (SASS IMAD.WIDE) per scalar multiplication and DRAM bytes per launch, counted by
+# ncu on the shipped kernels: profiles/kernel_work.json, regenerated from an `ncu --set full` report by
+# tools/ncu_opcode_mix.py --json (the r01f figures are the fall-back when the file is absent)
 WIDE_VAR, WIDE_FIXED = 100233, 11299
+KERNEL_WORK = {}
+try:
+    KERNEL_WORK = json.load(open(os.path.join(ROOT, "profiles", "kernel_work.json")))
+    WIDE_VAR = int(KERNEL_WORK["k_var_base"]["imad_wide_per_item"])
+    WIDE_FIXED = int(KERNEL_WORK["k_fixed_base"]["imad_wide_per_item"])
+except Exception:
+    pass
 ECMUL_REF = os.path.join(ROOT, "oracle", "_ref", "ecmul_ref")
+SEAL_REF = os.path.join(ROOT, "oracle", "_ref", "seal_ref")
+CCS22_REF = os.path.join(ROOT, "oracle", "_ref", "ccs22_ref")
 
 
 def pin_to_gpu_numa_node(gpu_index):
@@ -245,10 +255,103 @@ def proof_throughput(eng, torch, n=1 << 15, seed=77):
     return out
 
 
-def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096):
+def _bidder_digests(res, m, c):
+    """SHA-256 of what each local bidder published (tests/golden/make_large_digests.py:bidder_digest)"""
+    import hashlib
+    out = []
+    for q in range(m):
+        h = hashlib.sha256(res["commit"][736 * c * q:736 * c * (q + 1)])
+        for step in range(c):
+            o = step * m + q
+            tag = res["r2_tag"][o]
+            h.update(res["r1"][320 * o:320 * (o + 1)] + int(tag).to_bytes(4, "little") + res["r2_b"][64 * o:64 * (o + 1)] +
+                     res["r2_proof"][1344 * o:1344 * o + (672 if tag == 1 else 1344)])
+        out.append(h.hexdigest())
+    return out
+
+
+def _tierb_auction(args):
+    """one SEAL auction on the Tier-B oracle port (CPU, libcrypto): seconds"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib
+    import seal_flow
+    seed, a, n, c, bids = args
+    t0 = time.perf_counter()
+    fl = seal_flow.SealFlow(oracle_lib.Oracle(), n, c, seed, bids, auction=a)
+    fl.run()
+    assert fl.ok
+    return time.perf_counter() - t0
+
+
+def cpu_auction_baselines(cores):
+    """The reference's CPU path for the auction configs, timed HERE on the box's host cores (north_star: "alongside it
+    runs the reference OpenSSL CPU path timed on the box's host cores in the same run"):
+      config 1  ./SEAL 10 20: the UNMODIFIED reference (oracle/_ref/seal_ref, Tier A), whole, one process per core
+      config 2  ./CCS22 20 32: the unmodified reference (oracle/_ref/ccs22_ref), whole, one process per core
+      config 4  n = 1000 x 32 bits is ~10 core-days all-pairs: a Tier-B (libcrypto port, every proof verified ONCE)
+                auction of 8 bidders x 32 bits is timed and scaled by bidders (per-bidder work does not depend on n
+                except the O(n^2) additions of the reference's Y loops, which are left out): labelled extrapolation
+      config 5  a sample of the genTests-shaped auctions of tests/golden/large_config_digests.json on Tier B, one
+                process per core."""
+    import concurrent.futures as cf
+    out = {"cores": cores}
+    D = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_config_digests.json")))
+    L = json.load(open(os.path.join(ROOT, "tests", "golden", "large_config_digests.json")))
+
+    def run_many(cmd, count):
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True) for _ in range(count)]
+        outs = [p.communicate()[1] for p in ps]
+        wall = time.perf_counter() - t0
+        recs = [json.loads([l for l in o.splitlines() if l.startswith("{")][-1]) for o in outs]
+        assert all(p.returncode == 0 for p in ps)
+        return wall, recs
+
+    if os.path.exists(SEAL_REF):
+        g = D["seal_10_20"]
+        wall, recs = run_many([SEAL_REF, "10", "20", str(g["seed"]), ",".join(map(str, g["bids"])), "-"], cores)
+        per = statistics.median(r["t_total_s"] for r in recs)
+        out["config1_seal_n10_c20"] = {"kind": "reference", "binary": "oracle/_ref/seal_ref 10 20 (unmodified SEAL/*.cpp, all-pairs verification)",
+                                       "processes": cores, "seconds_per_auction_per_core": per, "wall_s": wall,
+                                       "auctions_per_s_aggregate": cores / wall, "sha256_matches_golden": all(r["sha256"] == g["sha256"] for r in recs)}
+    if os.path.exists(CCS22_REF):
+        g = D["ccs22_20_32"]
+        t0 = time.perf_counter()
+        wall, recs = run_many([CCS22_REF, "20", "32", str(g["seed"]), str(g["evaluator"]), ",".join(map(str, g["bids"])), "-"], cores)
+        out["config2_ccs22_n20_c32"] = {"kind": "reference", "binary": "oracle/_ref/ccs22_ref 20 32 (unmodified CCS22/*.cpp)", "processes": cores,
+                                        "seconds_per_auction_per_core": wall, "wall_s": wall, "auctions_per_s_aggregate": cores / wall,
+                                        "sha256_matches_golden": all(r["sha256"] == g["sha256"] for r in recs)}
+    with cf.ProcessPoolExecutor(max_workers=cores) as pool:
+        g4 = L["config4_uniform"]
+        nb, c4 = 8, g4["c"]
+        t4 = list(pool.map(_tierb_auction, [(g4["seed"], 0, nb, c4, g4["bids"][:nb])]))[0]
+        per_bidder = t4 / nb
+        out["config4_seal_n1000_c32"] = {
+            "kind": "port", "sample": f"Tier-B auction of {nb} bidders x {c4} bits, every proof verified once, 1 core: {t4:.1f} s",
+            "seconds_per_bidder_verify_once": per_bidder,
+            "extrapolated_seconds_n1000_verify_once_1core": per_bidder * g4["n"],
+            "extrapolated_seconds_n1000_verify_once_all_cores": per_bidder * g4["n"] / cores,
+            "note": "EXTRAPOLATION (labelled): per-bidder proving and verify-once work x 1000; the reference itself verifies all pairs "
+                    "(x 999 on the verification part, ~10 core-days) and spends another ~12 core-hours in its O(n^2) Y loops"}
+        g5 = L["config5_sample"]
+        k = min(len(g5["n"]), 2 * cores)
+        jobs = [(g5["seed"], a, g5["n"][a], g5["c"][a], g5["bids"][a]) for a in range(4, 4 + k)]
+        t0 = time.perf_counter()
+        ts = list(pool.map(_tierb_auction, jobs))
+        wall = time.perf_counter() - t0
+        out["config5_gentests"] = {"kind": "port", "sample": f"{k} genTests-shaped auctions (n ~ U{{1..20}}, c ~ U{{1..32}}) on Tier B, verify-once, {cores} processes",
+                                   "auctions_per_s_per_core": k / sum(ts), "auctions_per_s_aggregate": k / wall, "wall_s": wall,
+                                   "note": "the reference verifies all pairs: multiply the verification share by (n - 1) for its own cost"}
+    return out
+
+
+def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096, transport="auto"):
     """Secondary figures (not the headline `value`): SEAL auctions through pa_seal_run.
-      config4: ONE auction, n = 1000 bidders x 32-bit bids, sharded by bidder slice over the ranks
-               (one NCCL all-gather of the X of all steps, then 128 B of partial sums per rank and step), every proof verified once;
+      config4: ONE auction, n = 1000 bidders x 32-bit bids, sharded by bidder slice over the ranks; the ranks' kernels
+               exchange 96 bytes per rank and step through peer windows (no host round trip per step), every proof
+               verified once.  The published records are compared with the oracle's digests (Tier B at full size,
+               tests/golden/large_config_digests.json) on every rank: `matches_golden`;
       config5: a lock-step batch of independent genTests-style auctions (n ~ U{1..20}, c ~ U{1..32},
                reference tests/genTests.py:15-16) per rank, no exchange;
       verifies/s per proof kind from the CUDA-event time of the verify kernels inside the config4 run."""
@@ -256,36 +359,56 @@ def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096):
     import random
     D = importlib.import_module("privacy-auction_b200.distributed")
     out = {}
-    rnd = random.Random(2024)
-    n4, c4 = 1000, 32
-    bids = [rnd.randrange(1 << 31) for _ in range(n4)]
+    G4 = json.load(open(os.path.join(ROOT, "tests", "golden", "large_config_digests.json")))["config4_uniform"]
+    n4, c4, seed4, bids = G4["n"], G4["c"], G4["seed"], G4["bids"]
     sync = lambda: (dist.barrier() if dist else None, torch.cuda.synchronize(), eng.sync())
+    if world > 1 and transport != "nccl":
+        D.connect_peer_windows(eng)
 
-    def run4():
+    def run4(sections=False):
         if world == 1:
-            return eng.seal_run(7, [n4], [c4], bids, verify=True)
-        r = D.seal_run_sharded(eng, 7, n4, c4, bids, verify=True)
-        return {"ok": [r["ok_all"]], "max_bid": [r["max_bid_all"]]}
+            r = eng.seal_run(seed4, [n4], [c4], bids, verify=True, sections=sections)
+            r["slice"], r["ok_all"], r["max_bid_all"], r["transport"] = (0, n4), r["ok"][0], r["max_bid"][0], "single GPU"
+            return r
+        return D.seal_run_sharded(eng, seed4, n4, c4, bids, verify=True, sections=sections, transport=transport)
 
-    run4()  # warm-up (arena growth, module load)
-    sync()
-    eng.profile_begin()
-    t0 = time.perf_counter()
-    r = run4()
-    sync()
-    dt = time.perf_counter() - t0
-    ks = eng.profile_end()
-    assert r["ok"] == [True] and r["max_bid"] == [max(bids)], "SEAL n=1000 run failed its own checks"
-    t_dt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    # parity first (also the warm-up: arena growth, module load): every rank checks what ITS bidders published
+    r = run4(sections=True)
+    lo, hi = r["slice"]
+    mine = _bidder_digests(r, hi - lo, c4)
+    good = mine == G4["bidder_sha256"][lo:hi] and list(r["r3"][:c4]) == G4["r3"] and bool(r["ok_all"]) and r["max_bid_all"] == max(bids) \
+        and all(r["commit_ok"]) and all(r["r1_ok"]) and all(r["r2_ok"])
+    t_good = torch.tensor([1 if good else 0], dtype=torch.int32, device="cuda")
     if dist:
-        dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
-    dt = float(t_dt.item())
-    out["config4_seal_n1000_c32"] = {"auctions_per_s": 1.0 / dt, "seconds": dt, "bidders": n4, "bits": c4,
-                                     "partition": "single GPU" if world == 1 else f"bidder slices over {world} GPUs, one NCCL all-gather of the X of all steps, then 128 B of partial sums per rank and step",
+        dist.all_reduce(t_good, op=dist.ReduceOp.MIN)
+    matches = bool(t_good.item())
+    assert matches, "SEAL n=1000 x 32: the published records differ from the oracle's (tests/golden/large_config_digests.json)"
+    sync()
+    times = []
+    for rep in range(3):
+        if rep == 2:
+            eng.profile_begin()
+        sync()
+        t0 = time.perf_counter()
+        r = run4()
+        sync()
+        dt = time.perf_counter() - t0
+        t_dt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
+        times.append(float(t_dt.item()))
+        assert r["ok_all"] and r["max_bid_all"] == max(bids), "SEAL n=1000 run failed its own checks"
+    ks = eng.profile_end()
+    dt = min(times)
+    out["config4_seal_n1000_c32"] = {"auctions_per_s": 1.0 / dt, "seconds": dt, "seconds_all_runs": times, "bidders": n4, "bits": c4,
+                                     "matches_golden": matches,
+                                     "golden": "per-bidder SHA-256 of every published record + round-three bits vs the Tier-B oracle at full size "
+                                               f"(transcript sha256 {G4['sha256'][:16]}..., tests/golden/large_config_digests.json)",
+                                     "transport": r["transport"],
+                                     "partition": "single GPU" if world == 1 else f"bidder slices over {world} GPUs; per step each rank's 96-byte sum of cryptograms (and per pass its sum of public keys) is written into every peer's HBM by the walking kernel itself",
                                      "verification": "every proof once (the reference repeats each check n-1 times)"}
     # proofs verified on this rank during the run, per kind
-    m = n4 if world == 1 else (min(n4, (rank + 1) * ((n4 + world - 1) // world)) - min(n4, rank * ((n4 + world - 1) // world)))
-    decided = sum(1 for s in range(c4) if (max(bids) >> (c4 - 1 - s)) & 1)
+    m = hi - lo
     first = next(s for s in range(c4) if (max(bids) >> (c4 - 1 - s)) & 1)
     n_s1, n_s2 = m * (first + 1), m * (c4 - first - 1)
     counts = {"pok": 2 * m * c4 + 2 * m * c4, "com": m * c4, "s1": n_s1, "s2": n_s2}
@@ -322,9 +445,9 @@ def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096):
         assert rap["ok"] == [True] and rap["max_bid"] == [max(b1)]
         out["config1_seal_n10_c20_one_auction"] = {"seconds": dt1, "seconds_all_pairs_work": dt1p,
                                                    "path": "pa_seal_run, phase-major schedule, every proof verified once (all_pairs_work: n - 1 = 9 times each, what the reference's 10 bidders do)",
-                                                   "reference": "./SEAL 10 20: 51.6-60.6 s on one core (all-pairs verification); per-party CLI on the engine: 2.6 s"}
-        out["config2_ccs22_n20_c32_one_auction"] = {"seconds": dt2c, "path": "pa_ccs22_run, phase-major schedule (step-major: 0.207 s)",
-                                                    "reference": "./CCS22 20 32: 4.46 s on one core; per-party CLI on the engine: 2.7 s"}
+                                                   "reference": "see cpu_auction_baselines.config1_seal_n10_c20 (timed in this run when N = 1)"}
+        out["config2_ccs22_n20_c32_one_auction"] = {"seconds": dt2c, "path": "pa_ccs22_run, phase-major schedule",
+                                                    "reference": "see cpu_auction_baselines.config2_ccs22_n20_c32 (timed in this run when N = 1)"}
 
     # config 5 sample: independent auctions, each rank its own batch
     A = config5_auctions
@@ -410,6 +533,9 @@ def main():
     ap.add_argument("--no-seal", action="store_true", help="skip the SEAL auction / proof-verify figures")
     ap.add_argument("--config5-auctions", type=int, default=4096,
                     help="genTests-style auctions per GPU in the config-5 figure (12500 per GPU on 8 GPUs = BASELINE's 10^5)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "xchg", "nccl"],
+                    help="exchange of the bidder-sharded auction: peer windows written by the kernels (xchg) or NCCL call-backs")
+    ap.add_argument("--no-cpu-auctions", action="store_true", help="skip the CPU runs of the auction configs (about 90 s)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -501,7 +627,7 @@ def main():
     step_e2e()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     for _ in range(e2e_steps):
         step_e2e()
     barrier()
@@ -515,7 +641,7 @@ def main():
     # ---- secondary figures of BASELINE.json's metric: proof-verifies/s and auctions/s --------------
     seal = None
     if not args.no_seal:
-        seal = seal_figures(eng, pa, rank, world, dist if world > 1 else None, torch, args.config5_auctions)
+        seal = seal_figures(eng, pa, rank, world, dist if world > 1 else None, torch, args.config5_auctions, args.transport)
 
     if rank == 0:
         var = kstats.get("k_var_base", {"launches": 1, "total_ms": float("nan")})
@@ -525,7 +651,12 @@ def main():
         sm_max = clocks.get("sm_max_mhz") or 1965.0
         nominal_peak = 64.0 * 148 * sm_max * 1e6
         peak_imad = peak["imad_per_s"]
-        peak_wide = peak["imad_wide_per_s"]
+        # the denominator: the larger of the register-only IMAD.WIDE microbenchmark on this GPU and the pipe's own ceiling
+        # (one IMAD.WIDE occupies the multiplier pipe of an SM sub-partition for 4 cycles: 148 SMs x 4 x 32 lanes / 4 per clock)
+        wide_measured = peak["imad_wide_per_s"]
+        wide_ceiling = 148 * 4 * 32 / 4.0 * sm_max * 1e6
+        peak_wide = max(wide_measured, wide_ceiling)
+        kw = KERNEL_WORK.get("k_var_base", {})
         achieved = n * WIDE_VAR / (var_ms * 1e-3)
         nominal = n * FM_VAR * IMAD_PER_FM / (var_ms * 1e-3)
         total_k_ms = sum(v["total_ms"] for v in kstats.values()) or 1.0
@@ -534,7 +665,7 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (256-bit integers in 32-bit limbs)", "data": "synthetic (seeded scalars; variable bases g^k' from the fixed-base kernel)",
             "config": {"workload": WORKLOAD, "n_fixed_per_gpu": n, "n_var_per_gpu": n,
-                       "l2": "working set per step ~420 MB (scalars, points, Jacobian scratch, outputs) > 126 MB L2; kernels are integer-pipe bound"},
+                       "l2": "working set per step ~270 MB (scalars, bases, affine outputs) > 126 MB L2; kernels are integer-pipe bound"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n, "d2h_bytes_per_step": 128 * n,
                     "steps": e2e_steps, "bytes_match_device_run": same, "host_cores_pinned_per_rank": pinned_cores},
@@ -544,14 +675,19 @@ def main():
             # per second, peak = the same instruction in a register-only loop on this GPU.
             "roofline": {"bound": "int-multiply pipe (IMAD.WIDE on fmaheavy); not hbm, not tensor", "kernel": "k_var_base",
                          "achieved": achieved / 1e12, "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE/s", "frac": achieved / peak_wide,
-                         "traffic": 3.53e9,  # dram read + write per launch, ncu --set full (profiles/r01f_ncu_full_k_var_base_summary.csv)
-                         "traffic_note": "algorithmic bytes are 0.2 GB per launch (64 B point + 32 B scalar in, 96 B Jacobian out); the rest is "
-                                         "write-back and refill of per-thread stack lines (window tables and register spills at 80 registers), "
-                                         "206 GB/s = 3.1 % of HBM bandwidth, not on the critical path (long_scoreboard 0.48 of 11.6 stall cycles per issue)",
-                         "peak_source": "measured on this GPU by pa_measure_int_peak (register-only IMAD.WIDE loop); MEASURED_PEAKS.json has no integer figure",
-                         "units_per_launch": n, "per_unit": f"{WIDE_VAR} IMAD.WIDE per variable-base mult (ncu count on this kernel)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch in the ncu --set full capture of this kernel
+                         # (profiles/kernel_work.json names the report it was read from); null when no capture of this build exists
+                         "traffic": kw.get("dram_bytes_per_launch"),
+                         "traffic_note": f"algorithmic bytes are {160 * n / 1e9:.2f} GB per launch (64 B point + 32 B scalar in, 64 B affine point out); anything above is "
+                                         "write-back and refill of per-thread stack lines (window tables in local memory, register spills at 80 registers); "
+                                         "the kernel is bound by the integer multiplier pipe, not by HBM",
+                         "peak_source": "max(register-only mad.wide.u32 loop measured on this GPU by pa_measure_int_peak, 4-cycle pipe ceiling at the sampled max SM clock); "
+                                        "MEASURED_PEAKS.json has no integer figure",
+                         "peak_measured_loop": wide_measured / 1e12, "peak_pipe_ceiling": wide_ceiling / 1e12,
+                         "units_per_launch": n, "per_unit": f"{WIDE_VAR} IMAD.WIDE per variable-base mult ({kw.get('source', 'profiles/r01f_opcode_mix.txt')})",
                          "avg_launch_ms": var_ms, "share_of_kernel_time": var["total_ms"] / total_k_ms,
-                         "ncu": "fmaheavy pipe 85.1 % active, top stalls math_pipe_throttle and wait; 298 k instructions per multiplication, a third of them IMAD.WIDE",
+                         "issue_slot_frac": (kw.get("instr_per_item", 298000) * n / 32.0) / (var_ms * 1e-3 * sm_max * 1e6 * 148 * 4),
+                         "ncu": kw.get("ncu_note", "fmaheavy pipe 85.1 % active (r01f capture), top stalls math_pipe_throttle and wait"),
                          "nominal_algorithm": {"per_unit": f"{FM_VAR} field mults x {IMAD_PER_FM} 32-bit IMAD (SURVEY.md 8d, plain double-and-add)",
                                                "achieved_timad_s": nominal / 1e12, "peak_timad_s": peak_imad / 1e12, "frac": nominal / peak_imad,
                                                "note": "above 1 because GLV + co-Z tables execute ~1,800 field mults instead of 2,900"}},
@@ -565,11 +701,21 @@ def main():
         }
         if seal is not None:
             line["seal"] = seal
+        if seal is not None:
+            # the auction figures of BASELINE.json's metric, where the driver keeps them: measured through the public call
+            # with host inputs (bids) and host outputs (verdicts, maximum), i.e. end to end by construction
+            c4 = seal["config4_seal_n1000_c32"]
+            line["e2e"]["auction_seal_n1000_c32"] = {"seconds": c4["seconds"], "auctions_per_s": c4["auctions_per_s"], "n_gpus": world,
+                                                      "matches_golden": c4["matches_golden"], "transport": c4["transport"]}
+            line["config"]["also_measured"] = {"seal_n1000_c32_seconds": c4["seconds"], "seal_n1000_c32_matches_golden": c4["matches_golden"],
+                                               "config5_auctions_per_s": seal["config5_gentests_batch"]["auctions_per_s"]}
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
             r = run_ecmul_ref(cores, 20000)  # 40000 EC_POINT_mul per thread, ~12 s on every core
             line["cpu_baseline"] = {"value": r["mults"] / r["seconds"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
                                     "sample": f"{int(r['mults'])} libcrypto EC_POINT_mul (half fixed-base, half variable-base) in {r['seconds']:.1f} s"}
+            if not args.no_cpu_auctions:
+                line["cpu_auction_baselines"] = cpu_auction_baselines(cores)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

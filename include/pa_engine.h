@@ -69,6 +69,43 @@ void *pa_ctx_stream(pa_ctx *ctx);
 /* number of kernel launches issued through this context so far */
 uint64_t pa_ctx_launches(pa_ctx *ctx);
 
+/* Entropy.  The draw stream that replaces BN_rand_range (see "seeded randomness" below) is a function of a
+ * 64-bit seed only, which is what tests and benchmarks need and what no deployment may use: whoever knows
+ * the seed knows every secret.  pa_ctx_set_entropy installs a 32-byte key (from getrandom(2), per process,
+ * never published) that is mixed into every draw on this device:
+ *   draw = SHA-256("PAv2" || key || LE64 seed || LE64 stream || LE64 ctr).
+ * key32 == NULL goes back to the seeded test stream.  The reference draws from OpenSSL's DRBG
+ * (BN_rand_range, SEAL/bidder.cpp:97) and std::random_device (SEAL/bidder.cpp:27); the host classes and the
+ * CLIs of this repository install a key unless --seed is given. */
+int pa_ctx_set_entropy(pa_ctx *ctx, const uint8_t *key32);
+
+/* TEST HOOKS (never needed by a caller of the reference's path):
+ *   PA_DBG_REJECT_BITS  a = k: a draw whose top k bits are all ones is redrawn as if it were >= the group
+ *                       order (probability 2^-k instead of 2^-128), to exercise the redraw logic; 0 = off
+ *   PA_DBG_CORRUPT      a = section (0 off, 1 commitment record, 2 round-one record, 3 round-two proof),
+ *                       b = step << 32 | local bidder (section 1: step = bit index), c = byte offset in the
+ *                       record: pa_seal_run flips the lowest bit of that byte between proving and verifying */
+enum { PA_DBG_REJECT_BITS = 1, PA_DBG_CORRUPT = 2 };
+int pa_debug_set(pa_ctx *ctx, int what, uint64_t a, uint64_t b, uint64_t c);
+/* how many times pa_seal_run ran an auction again step-major because a draw was rejected */
+uint64_t pa_ctx_reruns(pa_ctx *ctx);
+
+/* Peer exchange window (one process per GPU, all GPUs of one node): lets the kernels of a bidder-sharded
+ * auction exchange their per-step sums by writing into each other's HBM over NVLink instead of returning
+ * to the host for a collective call per step (pa_seal_job.use_xchg).
+ *   pa_xchg_create   allocates this rank's window (PA_XCHG_BYTES) and returns its 64-byte CUDA IPC handle;
+ *   pa_xchg_connect  handles = world x 64 bytes, every rank's handle in rank order (exchange them with
+ *                    whatever the host program has: MPI_Allgather, torch.distributed, a file);
+ *   pa_xchg_skip     a rank that owns no bidder of a sharded auction calls this instead of pa_seal_run
+ *                    (keeps the run counter the ranks share in step);
+ *   pa_xchg_close    unmaps and frees (also done by pa_ctx_destroy). */
+#define PA_XCHG_BYTES ((size_t)4 << 20)
+#define PA_XCHG_MAX_WORLD 16
+int pa_xchg_create(pa_ctx *ctx, uint8_t *handle64);
+int pa_xchg_connect(pa_ctx *ctx, const uint8_t *handles, int world, int rank);
+int pa_xchg_skip(pa_ctx *ctx);
+int pa_xchg_close(pa_ctx *ctx);
+
 /* device memory helpers for the _dev entry points (cudaMalloc / cudaMemcpyAsync
  * on the context's stream) so that a host program needs no CUDA headers */
 int pa_dev_alloc(pa_ctx *ctx, void **dptr, size_t bytes);
@@ -104,9 +141,10 @@ int pa_lincomb2_dev(pa_ctx *ctx, const uint8_t *d_p, const uint8_t *d_a, const u
 int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, int sub);
 
 /* ok[i] = 1 if points[i] is the point at infinity or a valid curve point (both coordinates < p and
- * y^2 = x^3 + 7): what EC_POINT_set_affine_coordinates checks when a point enters libcrypto.  The
- * other entry points do NOT validate their inputs (the reference only ever feeds them points it
- * computed itself); call this on anything received from outside. */
+ * y^2 = x^3 + 7): what EC_POINT_set_affine_coordinates checks when a point enters libcrypto.  The four
+ * proof VERIFIERS apply this test to every point of the proof and of the statement themselves (a proof
+ * with an off-curve or non-canonical point gets verdict 0); the scalar-multiplication entry points do
+ * not validate their inputs (the reference only ever feeds them points it computed itself). */
 int pa_point_on_curve(pa_ctx *ctx, const uint8_t *points, size_t n, uint8_t *ok);
 
 /* EC_POINT_point2oct, SEAL/hash.cpp:27-29, SEAL/bulletinBoard.cpp:277.
@@ -138,7 +176,9 @@ int pa_challenge_dev(pa_ctx *ctx, const uint8_t *d_points, size_t k, const uint6
  * draw order), which makes it a pure function of its
  * inputs; pa_rng_fill produces such arrays from a seed.  A verifier writes one
  * byte per proof (1 = every check holds); like the reference it evaluates all
- * checks, no early exit (SEAL/bidder.cpp:244-298). */
+ * checks, no early exit (SEAL/bidder.cpp:244-298).  Every point a verifier receives (eps and
+ * statement) must be the 64 zero bytes of infinity or canonical coordinates on the curve, as
+ * EC_POINT_set_affine_coordinates would demand of a received point: otherwise the verdict is 0. */
 
 /* genNIZKPoKDLog SEAL/bidder.cpp:90-107; X = g^x; rnd: v */
 int pa_pokdlog_prove(pa_ctx *ctx, const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n);
@@ -306,6 +346,13 @@ typedef struct {
    * 0 picks phase-major where it applies. */
   int schedule;
   size_t xchg_bytes;            /* capacity of d_send; d_recv holds world times as much (0: slice * 64) */
+  /* use_xchg != 0: the sharded auction exchanges through the peer window of this context (pa_xchg_connect)
+   * instead of the callback: allgather, user, d_send, d_recv are ignored, nothing returns to the host per
+   * step.  Rank r must own bidders [r * slice, min(n, (r + 1) * slice)); ranks beyond ceil(n / slice) call
+   * pa_xchg_skip.  Phase-major: the Y reconstruction is sharded too (only the ranks' sums of public keys and
+   * of cryptograms cross the link, 96 bytes per rank and step). */
+  int use_xchg;
+  uint8_t *ok_all;              /* use_xchg: 1 = every verification on every rank held (NULL to skip) */
 } pa_seal_job;
 enum { PA_SEAL_AUTO = 0, PA_SEAL_STEP_MAJOR = 1, PA_SEAL_PHASE_MAJOR = 2 };
 int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job);

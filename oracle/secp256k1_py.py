@@ -114,6 +114,9 @@ def pa_draw(seed, stream, ctr):
     return int.from_bytes(hashlib.sha256(msg).digest(), "big")
 
 
+REJECT_BITS = 0
+
+
 class PaStream:
     """BN_rand_range(., order) replacement of oracle/shim/pa_seed_shim.cpp."""
 
@@ -124,6 +127,10 @@ class PaStream:
         while True:
             v = pa_draw(self.seed, self.stream, self.ctr)
             self.ctr += 1
+            # REJECT_BITS mirrors the engine's test hook PA_DBG_REJECT_BITS: a draw whose top k bits are all
+            # ones counts as out of range, so that the redraw paths are exercised (normally 2^-128 per draw)
+            if REJECT_BITS and (v >> (256 - REJECT_BITS)) == (1 << REJECT_BITS) - 1:
+                continue
             if v < rng:
                 return v
 

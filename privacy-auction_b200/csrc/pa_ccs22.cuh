@@ -489,6 +489,7 @@ int dev_gather(pa_ctx *ctx, unsigned char *dst, const unsigned char *src, const 
 
 extern "C" int pa_ccs22_ot_send_dev(pa_ctx *ctx, const uint8_t *r1, const uint8_t *params, const uint8_t *B, const uint8_t *st,
                                     const uint8_t *m, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (r1 && params && B && st && m && out)) && n < (1u << 26));
   if (n == 0) return PA_OK;
   int rc = work_reserve(ctx, 3 * n);
@@ -498,12 +499,14 @@ extern "C" int pa_ccs22_ot_send_dev(pa_ctx *ctx, const uint8_t *r1, const uint8_
 }
 extern "C" int pa_ccs22_ot_send(pa_ctx *ctx, const uint8_t *r1, const uint8_t *params, const uint8_t *B, const uint8_t *st,
                                 const uint8_t *m, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (r1 && params && B && st && m && out)));
   HArg a[] = {{r1, 0, n * 192}, {params, 0, n * 128}, {B, 0, n * 64}, {st, 0, n * 64}, {m, 0, n * 32}, {0, out, n * 192}};
   return staged(ctx, a, 6, [&](unsigned char **d) { return pa_ccs22_ot_send_dev(ctx, d[0], d[1], d[2], d[3], d[4], d[5], n); });
 }
 extern "C" int pa_ccs22_ot_recv1_dev(pa_ctx *ctx, const uint8_t *k, const uint8_t *beta, const uint8_t *alpha, const uint8_t *params,
                                      uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (k && beta && alpha && params && out)) && n < (1u << 26));
   if (n == 0) return PA_OK;
   int rc = work_reserve(ctx, 3 * n);
@@ -513,6 +516,7 @@ extern "C" int pa_ccs22_ot_recv1_dev(pa_ctx *ctx, const uint8_t *k, const uint8_
 }
 extern "C" int pa_ccs22_ot_recv1(pa_ctx *ctx, const uint8_t *k, const uint8_t *beta, const uint8_t *alpha, const uint8_t *params,
                                  uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (k && beta && alpha && params && out)));
   HArg a[] = {{k, 0, n * 32}, {beta, 0, n * 32}, {alpha, 0, n * 32}, {params, 0, n * 128}, {0, out, n * 192}};
   return staged(ctx, a, 5, [&](unsigned char **d) { return pa_ccs22_ot_recv1_dev(ctx, d[0], d[1], d[2], d[3], d[4], n); });
@@ -520,6 +524,7 @@ extern "C" int pa_ccs22_ot_recv1(pa_ctx *ctx, const uint8_t *k, const uint8_t *b
 
 extern "C" int pa_ccs22_bes_encode_dev(pa_ctx *ctx, const uint8_t *X, size_t n, const uint64_t *ids, const uint8_t *d, const uint8_t *x,
                                        const uint8_t *r, uint8_t *out, size_t m) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && n >= 1 && n < (1u << 26) && m < (1u << 26) && X && (m == 0 || (ids && d && x && r && out)));
   if (m == 0) return PA_OK;
   int rc = ensure(ctx, &ctx->d_aux, &ctx->aux_bytes, n * 64);
@@ -531,6 +536,7 @@ extern "C" int pa_ccs22_bes_encode_dev(pa_ctx *ctx, const uint8_t *X, size_t n, 
 }
 extern "C" int pa_ccs22_bes_encode(pa_ctx *ctx, const uint8_t *X, size_t n, const uint64_t *ids, const uint8_t *d, const uint8_t *x,
                                    const uint8_t *r, uint8_t *out, size_t m) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && n >= 1 && X && (m == 0 || (ids && d && x && r && out)));
   for (size_t i = 0; i < m; ++i) PA_ARGCHECK(ctx, ids[i] < n);
   HArg a[] = {{X, 0, n * 64}, {ids, 0, m * 8}, {d, 0, m}, {x, 0, m * 32}, {r, 0, m * 32}, {0, out, m * 64}};
@@ -538,6 +544,7 @@ extern "C" int pa_ccs22_bes_encode(pa_ctx *ctx, const uint8_t *X, size_t n, cons
 }
 extern "C" int pa_ccs22_commit_dev(pa_ctx *ctx, const uint8_t *scalars, size_t k, const uint8_t *bid, const uint8_t *R, const uint8_t *params,
                                    uint8_t *out_H, uint8_t *out_com, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && k >= 1 && n < (1u << 26) && (n == 0 || (scalars && bid && R && params && out_H && out_com)));
   if (n == 0) return PA_OK;
   int rc = pa_ccs22_setup_hash_dev(ctx, scalars, k, out_H, n);
@@ -548,11 +555,13 @@ extern "C" int pa_ccs22_commit_dev(pa_ctx *ctx, const uint8_t *scalars, size_t k
 }
 extern "C" int pa_ccs22_commit(pa_ctx *ctx, const uint8_t *scalars, size_t k, const uint8_t *bid, const uint8_t *R, const uint8_t *params,
                                uint8_t *out_H, uint8_t *out_com, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && k >= 1 && (n == 0 || (scalars && bid && R && params && out_H && out_com)));
   HArg a[] = {{scalars, 0, n * k * 32}, {bid, 0, n * 32}, {R, 0, n * 32}, {params, 0, n * 128}, {0, out_H, n * 32}, {0, out_com, n * 64}};
   return staged(ctx, a, 6, [&](unsigned char **p) { return pa_ccs22_commit_dev(ctx, p[0], k, p[1], p[2], p[3], p[4], p[5], n); });
 }
 extern "C" int pa_ccs22_ot_recv2_dev(pa_ctx *ctx, const uint8_t *ots, const uint8_t *beta, const uint8_t *B, size_t n, int32_t *d_is_inf) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && B && d_is_inf && n < (1u << 26) && (n == 0 || (ots && beta)));
   int rc = ensure(ctx, &ctx->d_aux, &ctx->aux_bytes, (n + 1) * 64);
   if (rc) return rc;
@@ -565,6 +574,7 @@ extern "C" int pa_ccs22_ot_recv2_dev(pa_ctx *ctx, const uint8_t *ots, const uint
   return pa_point_sum_is_inf_dev(ctx, ctx->d_aux, nullptr, 1, n + 1, d_is_inf);
 }
 extern "C" int pa_ccs22_ot_recv2(pa_ctx *ctx, const uint8_t *ots, const uint8_t *beta, const uint8_t *B, size_t n, int *is_inf) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && B && is_inf && (n == 0 || (ots && beta)));
   int32_t flag = 0;
   HArg a[] = {{ots, 0, n * 192}, {beta, 0, n * 32}, {B, 0, 64}, {0, &flag, 4}};
@@ -574,6 +584,7 @@ extern "C" int pa_ccs22_ot_recv2(pa_ctx *ctx, const uint8_t *ots, const uint8_t 
 }
 
 extern "C" int pa_ccs22_run(pa_ctx *ctx, const pa_ccs22_job *job) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && job && job->n_auctions >= 1 && job->n && job->c && job->bids && job->evaluator);
   const size_t A = job->n_auctions;
   int rc;

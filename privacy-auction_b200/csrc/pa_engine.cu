@@ -37,7 +37,21 @@ struct pa_ctx {
   size_t work_alt_bytes = 0;
   cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_comp[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
   uint64_t launches = 0;
+  uint64_t reruns = 0;  // phase-major auctions run again step-major because a draw was rejected
   std::string err;
+  // draw-stream configuration mirrored in the device constant pa_rng_config (pa_ctx_set_entropy, pa_debug_set)
+  pa_rng_cfg rng_cfg = {};
+  // TEST HOOK (pa_debug_set): flip one byte of one published record between proving and verifying
+  struct Corrupt { int section = 0; size_t step = 0, bidder = 0, offset = 0; } corrupt;
+  // peer exchange window of the bidder-sharded auction (pa_xchg_*)
+  struct Xchg {
+    unsigned char *local = nullptr;      // this rank's window (cudaMalloc, exported by IPC handle)
+    unsigned char **d_peers = nullptr;   // device array [world] of every rank's window as mapped here
+    std::vector<unsigned char *> peers;  // host copy; peers[rank] == local
+    int world = 0, rank = -1;
+    uint32_t epoch = 0;                  // one per sharded run, the same on every rank
+    int *d_err = nullptr;                // set by a kernel whose wait for a peer timed out
+  } xchg;
   // optional per-kernel CUDA-event timing (pa_profile_begin / pa_profile_end)
   bool profiling = false;
   struct Span { int kid; cudaEvent_t e0, e1; };
@@ -103,10 +117,29 @@ static std::string g_create_err;
     }                                                                                           \
   } while (0)
 
+// Every exported function runs on the context's device whatever the caller's current device is
+// (torch may have changed it; a process may hold contexts on several GPUs) and restores it on return.
+struct pa_dev_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit pa_dev_guard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~pa_dev_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define PA_ENTER(ctx)              \
+  if (!(ctx)) return PA_EINVAL;    \
+  pa_dev_guard dev_guard_((ctx)->device)
+
 static int pa_fail(pa_ctx *ctx, int code, const char *msg) {
   if (ctx) ctx->err = msg;
   return code;
 }
+
+#define PA_ARGCHECK(ctx, cond) \
+  if (!(cond)) return pa_fail(ctx, PA_EINVAL, "invalid argument: " #cond)
 
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + PA_BLOCK - 1) / PA_BLOCK); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -125,7 +158,7 @@ static int ensure(pa_ctx *ctx, unsigned char **buf, size_t *cap, size_t need) {
 
 extern "C" {
 
-int pa_abi_version(void) { return 2; }  // 2: pa_seal_job.schedule / xchg_bytes, pa_ccs22_job.schedule
+int pa_abi_version(void) { return 3; }  // 3: pa_seal_job.use_xchg / ok_all, peer window, entropy key, verifiers validate points
 size_t pa_abi_sizeof(int which) {
   return which == 0 ? sizeof(pa_seal_job) : which == 1 ? sizeof(pa_ccs22_job) : which == 2 ? sizeof(pa_kernel_stat) : 0;
 }
@@ -153,29 +186,38 @@ int pa_ctx_create(pa_ctx **out, int device) {
   }
   pa_ctx *ctx = new pa_ctx();
   ctx->device = device;
+  pa_dev_guard guard(device);
+  u32 *d_bases = nullptr;
   auto fail = [&](const char *what, cudaError_t ce) {
     g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_bases);
+    cudaFree(ctx->d_comb);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PA_ECUDA;
   };
-  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  int cur = -1;
+  if ((e = cudaGetDevice(&cur)) != cudaSuccess || cur != device) return fail("cudaSetDevice", e != cudaSuccess ? e : cudaErrorInvalidDevice);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaMalloc((void **)&ctx->d_comb, PA_COMB_WORDS * sizeof(u32))) != cudaSuccess) return fail("cudaMalloc(comb)", e);
-  u32 *d_bases = nullptr;
   if ((e = cudaMalloc((void **)&d_bases, PA_COMB_WINDOWS * 16 * sizeof(u32))) != cudaSuccess) return fail("cudaMalloc(bases)", e);
   k_comb_base<<<1, 32, 0, ctx->stream>>>(d_bases);
   k_comb_entries<<<PA_COMB_WINDOWS * PA_COMB_ENTRIES / PA_BLOCK, PA_BLOCK, 0, ctx->stream>>>(d_bases, ctx->d_comb);
   ctx->launches += 2;
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("comb table build", e);
   cudaFree(d_bases);
+  d_bases = nullptr;
+  // the draw stream starts as the seeded test stream (pa_ctx_set_entropy installs a key)
+  if ((e = cudaMemcpyToSymbol(pa_rng_config, &ctx->rng_cfg, sizeof ctx->rng_cfg)) != cudaSuccess) return fail("rng config", e);
   *out = ctx;
   return PA_OK;
 }
 
 int pa_ctx_destroy(pa_ctx *ctx) {
-  if (!ctx) return PA_EINVAL;
-  cudaSetDevice(ctx->device);
+  PA_ENTER(ctx);
   cudaStreamSynchronize(ctx->stream);
+  pa_xchg_close(ctx);
   cudaFree(ctx->d_comb);
   cudaFree(ctx->d_work);
   cudaFree(ctx->d_stage);
@@ -202,6 +244,7 @@ int pa_ctx_destroy(pa_ctx *ctx) {
 }
 
 int pa_sync(pa_ctx *ctx) {
+  PA_ENTER(ctx);
   if (!ctx) return PA_EINVAL;
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PA_OK;
@@ -211,26 +254,121 @@ void *pa_ctx_stream(pa_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t pa_ctx_launches(pa_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int pa_dev_alloc(pa_ctx *ctx, void **dptr, size_t bytes) {
+  PA_ENTER(ctx);
   if (!ctx || !dptr) return PA_EINVAL;
-  PA_CUDA(ctx, cudaSetDevice(ctx->device));
   PA_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
   return PA_OK;
 }
 int pa_dev_free(pa_ctx *ctx, void *dptr) {
+  PA_ENTER(ctx);
   if (!ctx) return PA_EINVAL;
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   PA_CUDA(ctx, cudaFree(dptr));
   return PA_OK;
 }
 int pa_dev_upload(pa_ctx *ctx, void *dptr, const void *host, size_t bytes) {
+  PA_ENTER(ctx);
   if (!ctx) return PA_EINVAL;
   PA_CUDA(ctx, cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return PA_OK;
 }
 int pa_dev_download(pa_ctx *ctx, void *host, const void *dptr, size_t bytes) {
+  PA_ENTER(ctx);
   if (!ctx) return PA_EINVAL;
   PA_CUDA(ctx, cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PA_OK;
+}
+
+// ---- draw stream configuration, test hooks ----------------------------------------------------------
+static int rng_cfg_push(pa_ctx *ctx) {
+  PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PA_CUDA(ctx, cudaMemcpyToSymbol(pa_rng_config, &ctx->rng_cfg, sizeof ctx->rng_cfg));
+  return PA_OK;
+}
+int pa_ctx_set_entropy(pa_ctx *ctx, const uint8_t *key32) {
+  PA_ENTER(ctx);
+  ctx->rng_cfg.keyed = key32 ? 1u : 0u;
+  for (int w = 0; w < 8; ++w)
+    ctx->rng_cfg.key[w] = key32 ? ((u32)key32[4 * w] << 24) | ((u32)key32[4 * w + 1] << 16) | ((u32)key32[4 * w + 2] << 8) | key32[4 * w + 3] : 0u;
+  return rng_cfg_push(ctx);
+}
+int pa_debug_set(pa_ctx *ctx, int what, uint64_t a, uint64_t b, uint64_t c) {
+  PA_ENTER(ctx);
+  if (what == PA_DBG_REJECT_BITS) {
+    if (a > 16) return pa_fail(ctx, PA_EINVAL, "pa_debug_set: reject bits must be 0..16");
+    ctx->rng_cfg.reject_bits = (u32)a;
+    return rng_cfg_push(ctx);
+  }
+  if (what == PA_DBG_CORRUPT) {
+    if (a > 3) return pa_fail(ctx, PA_EINVAL, "pa_debug_set: section must be 0 (off), 1 (commitment), 2 (round one) or 3 (round two)");
+    ctx->corrupt.section = (int)a;
+    ctx->corrupt.step = (size_t)(b >> 32);
+    ctx->corrupt.bidder = (size_t)(b & 0xFFFFFFFFu);
+    ctx->corrupt.offset = (size_t)c;
+    return PA_OK;
+  }
+  return pa_fail(ctx, PA_EINVAL, "pa_debug_set: unknown hook");
+}
+
+// ---- peer exchange window ---------------------------------------------------------------------------
+// One auction sharded by bidder slice exchanges, per step, each rank's sum of cryptograms (and once per
+// pass each rank's sum of public keys).  With a window the ranks' kernels write those 96-byte values
+// straight into each other's HBM over NVLink and wait on tags there: no host round trip, no collective
+// call per step.  Layout and protocol: pa_seal.cuh, "peer exchange".
+int pa_xchg_create(pa_ctx *ctx, uint8_t *handle64) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, handle64 != nullptr);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ctx->xchg.local) {
+    PA_CUDA(ctx, cudaMalloc((void **)&ctx->xchg.local, PA_XCHG_BYTES));
+    PA_CUDA(ctx, cudaMemset(ctx->xchg.local, 0, PA_XCHG_BYTES));
+    PA_CUDA(ctx, cudaMalloc((void **)&ctx->xchg.d_err, sizeof(int)));
+    PA_CUDA(ctx, cudaMemset(ctx->xchg.d_err, 0, sizeof(int)));
+    PA_CUDA(ctx, cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  PA_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->xchg.local));
+  memcpy(handle64, &h, 64);
+  return PA_OK;
+}
+int pa_xchg_connect(pa_ctx *ctx, const uint8_t *handles, int world, int rank) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, handles && world >= 1 && world <= PA_XCHG_MAX_WORLD && rank >= 0 && rank < world && ctx->xchg.local);
+  PA_ARGCHECK(ctx, ctx->xchg.world == 0);
+  std::vector<unsigned char *> peers(world, nullptr);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      peers[r] = ctx->xchg.local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    cudaError_t e = cudaIpcOpenMemHandle((void **)&peers[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q)
+        if (q != rank) cudaIpcCloseMemHandle(peers[q]);
+      ctx->err = std::string("pa_xchg_connect: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+      return PA_ECUDA;
+    }
+  }
+  PA_CUDA(ctx, cudaMalloc((void **)&ctx->xchg.d_peers, world * sizeof(unsigned char *)));
+  PA_CUDA(ctx, cudaMemcpy(ctx->xchg.d_peers, peers.data(), world * sizeof(unsigned char *), cudaMemcpyHostToDevice));
+  ctx->xchg.peers = peers;
+  ctx->xchg.world = world;
+  ctx->xchg.rank = rank;
+  ctx->xchg.epoch = 0;
+  return PA_OK;
+}
+int pa_xchg_close(pa_ctx *ctx) {
+  PA_ENTER(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < ctx->xchg.world; ++r)
+    if (r != ctx->xchg.rank && ctx->xchg.peers[r]) cudaIpcCloseMemHandle(ctx->xchg.peers[r]);
+  cudaFree(ctx->xchg.d_peers);
+  cudaFree(ctx->xchg.local);
+  cudaFree(ctx->xchg.d_err);
+  ctx->xchg = pa_ctx::Xchg();
   return PA_OK;
 }
 
@@ -244,45 +382,41 @@ static u32 *work_prefix(pa_ctx *ctx, size_t n) { return (u32 *)(ctx->d_work + n 
 
 static int normalize_to(pa_ctx *ctx, unsigned char *d_out, size_t n, int nper = 1, size_t stride = 64, int inner = 1,
                         size_t stride_in = 0) {
-  // points per thread: share the ~270-multiplication inversion among up to 16 points as soon as
-  // that still leaves >= 16 k threads (one lone warp per SM sub-partition is latency-bound anyway)
-  size_t per = n / 16384;
+  // the inversion is shared by a warp whatever happens; a thread takes several points only when that
+  // still leaves every SM a few blocks (the chain of a thread's points is sequential)
+  size_t per = n / 65536;
   if (per < 1) per = 1;
-  if (per > 16) per = 16;
+  if (per > 8) per = 8;
   size_t T = (n + per - 1) / per;
-  PA_LAUNCH(ctx, PA_K_NORMALIZE, k_normalize<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(work_jac(ctx), work_prefix(ctx, n), d_out, (int)n, (int)T, nper, stride, inner, stride_in));
+  PA_LAUNCH(ctx, PA_K_NORMALIZE, k_normalize<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(work_jac(ctx), work_prefix(ctx, n), pa_outlay{d_out, nper, stride, inner, stride_in}, (int)n, (int)T));
   return PA_OK;
 }
 
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
-#define PA_ARGCHECK(ctx, cond) \
-  if (!(cond)) return pa_fail(ctx, PA_EINVAL, "invalid argument: " #cond)
-
 extern "C" {
 
 int pa_fixed_base_mul_dev(pa_ctx *ctx, const uint8_t *d_scalars, uint8_t *d_out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (d_scalars && d_out)) && n < (1u << 30));
   PA_ARGCHECK(ctx, aligned16(d_scalars) && aligned16(d_out));
   if (n == 0) return PA_OK;
-  int rc = work_reserve(ctx, n);
-  if (rc) return rc;
-  PA_LAUNCH(ctx, PA_K_FIXED, k_fixed_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_scalars, ctx->d_comb, work_jac(ctx), (int)n));
-  return normalize_to(ctx, d_out, n);
+  PA_LAUNCH(ctx, PA_K_FIXED, k_fixed_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_scalars, ctx->d_comb, pa_out_plain(d_out), (int)n));
+  return PA_OK;
 }
 
 int pa_var_base_mul_dev(pa_ctx *ctx, const uint8_t *d_points, const uint8_t *d_scalars, uint8_t *d_out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (d_points && d_scalars && d_out)) && n < (1u << 30));
   PA_ARGCHECK(ctx, aligned16(d_points) && aligned16(d_scalars) && aligned16(d_out));
   if (n == 0) return PA_OK;
-  int rc = work_reserve(ctx, n);
-  if (rc) return rc;
-  PA_LAUNCH(ctx, PA_K_VAR, k_var_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_points, d_scalars, work_jac(ctx), (int)n));
-  return normalize_to(ctx, d_out, n);
+  PA_LAUNCH(ctx, PA_K_VAR, k_var_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_points, d_scalars, pa_out_plain(d_out), (int)n));
+  return PA_OK;
 }
 
 int pa_double_mul_dev(pa_ctx *ctx, const uint8_t *d_a, const uint8_t *d_points, const uint8_t *d_b, uint8_t *d_out,
                       size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (d_a && d_points && d_b && d_out)) && n < (1u << 30));
   PA_ARGCHECK(ctx, aligned16(d_a) && aligned16(d_points) && aligned16(d_b) && aligned16(d_out));
   if (n == 0) return PA_OK;
@@ -294,6 +428,7 @@ int pa_double_mul_dev(pa_ctx *ctx, const uint8_t *d_a, const uint8_t *d_points, 
 
 int pa_lincomb2_dev(pa_ctx *ctx, const uint8_t *d_p, const uint8_t *d_a, const uint8_t *d_q, const uint8_t *d_b,
                     uint8_t *d_out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (d_p && d_a && d_q && d_b && d_out)) && n < (1u << 30));
   PA_ARGCHECK(ctx, aligned16(d_p) && aligned16(d_a) && aligned16(d_q) && aligned16(d_b) && aligned16(d_out));
   if (n == 0) return PA_OK;
@@ -356,6 +491,17 @@ int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
       PA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
     }
   }
+  // whatever happens below, no copy into or out of the caller's buffers is left in flight
+  struct Drain {
+    pa_ctx *c;
+    cudaStream_t main;
+    ~Drain() {
+      cudaStreamSynchronize(c->s_in);
+      cudaStreamSynchronize(c->s_alt);
+      cudaStreamSynchronize(main);
+      cudaStreamSynchronize(c->s_out);
+    }
+  } drain{ctx, ctx->stream};
   const size_t CH = n < PA_PIPE_CHUNK ? n : PA_PIPE_CHUNK;
   size_t slot_bytes = 1024;
   for (int i = 0; i < nargs; ++i) slot_bytes += align_up(args[i].per * CH, 256);
@@ -421,6 +567,7 @@ int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
 extern "C" {
 
 int pa_fixed_base_mul(pa_ctx *ctx, const uint8_t *scalars, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (scalars && out)));
   if (n == 0) return PA_OK;
   PArg a[] = {{scalars, 0, 32}, {0, out, 64}};
@@ -428,6 +575,7 @@ int pa_fixed_base_mul(pa_ctx *ctx, const uint8_t *scalars, uint8_t *out, size_t 
 }
 
 int pa_var_base_mul(pa_ctx *ctx, const uint8_t *points, const uint8_t *scalars, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (points && scalars && out)));
   if (n == 0) return PA_OK;
   PArg a[] = {{points, 0, 64}, {scalars, 0, 32}, {0, out, 64}};
@@ -435,6 +583,7 @@ int pa_var_base_mul(pa_ctx *ctx, const uint8_t *points, const uint8_t *scalars, 
 }
 
 int pa_double_mul(pa_ctx *ctx, const uint8_t *a, const uint8_t *points, const uint8_t *b, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (a && points && b && out)));
   if (n == 0) return PA_OK;
   PArg g[] = {{a, 0, 32}, {points, 0, 64}, {b, 0, 32}, {0, out, 64}};
@@ -443,6 +592,7 @@ int pa_double_mul(pa_ctx *ctx, const uint8_t *a, const uint8_t *points, const ui
 
 int pa_lincomb2(pa_ctx *ctx, const uint8_t *p, const uint8_t *a, const uint8_t *q, const uint8_t *b, uint8_t *out,
                 size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (p && a && q && b && out)));
   if (n == 0) return PA_OK;
   PArg g[] = {{p, 0, 64}, {a, 0, 32}, {q, 0, 64}, {b, 0, 32}, {0, out, 64}};
@@ -450,6 +600,7 @@ int pa_lincomb2(pa_ctx *ctx, const uint8_t *p, const uint8_t *a, const uint8_t *
 }
 
 int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, int sub) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (p && q && out)) && n < (1u << 30));
   if (n == 0) return PA_OK;
   int rc = stage_reserve(ctx, n * 192 + 1024);
@@ -467,6 +618,7 @@ int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, 
 }
 
 int pa_point_on_curve(pa_ctx *ctx, const uint8_t *points, size_t n, uint8_t *ok) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (points && ok)) && n < (1u << 30));
   if (n == 0) return PA_OK;
   int rc = stage_reserve(ctx, n * 65 + 1024);
@@ -482,6 +634,7 @@ int pa_point_on_curve(pa_ctx *ctx, const uint8_t *points, size_t n, uint8_t *ok)
 
 int pa_point_encode(pa_ctx *ctx, const uint8_t *points, size_t n, int compressed, uint8_t *out, size_t stride,
                     uint32_t *lens) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (points && out && lens)) && n < (1u << 30));
   PA_ARGCHECK(ctx, stride >= (compressed ? 33u : 65u));
   if (n == 0) return PA_OK;
@@ -498,12 +651,14 @@ int pa_point_encode(pa_ctx *ctx, const uint8_t *points, size_t n, int compressed
 }
 
 int pa_profile_begin(pa_ctx *ctx) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx);
   ctx->profiling = true;
   return PA_OK;
 }
 
 int pa_profile_end(pa_ctx *ctx, pa_kernel_stat *out, size_t cap, size_t *count) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && count && (out || cap == 0));
   ctx->profiling = false;
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -534,6 +689,7 @@ int pa_profile_end(pa_ctx *ctx, pa_kernel_stat *out, size_t cap, size_t *count) 
 }
 
 int pa_measure_int_peak(pa_ctx *ctx, double out[4]) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && out);
   int rc = stage_reserve(ctx, 4096);
   if (rc) return rc;
@@ -609,14 +765,15 @@ template <int KIND, int NCHK>
 int verify_dev(pa_ctx *ctx, const unsigned char *proofs, const unsigned char *stmts, const u64 *ids,
                unsigned char *verdict, size_t n, pa_lay L = pa_lay_packed<KIND>()) {
   if (n == 0) return PA_OK;
-  size_t need = n * 32 + n * NCHK + 512;
+  size_t need = n * 32 + n * NCHK + n + 1024;
   int rc = ensure(ctx, &ctx->d_work, &ctx->work_bytes, need);
   if (rc) return rc;
   u32 *derived = (u32 *)ctx->d_work;
   unsigned char *chk = ctx->d_work + align_up(n * 32, 256);
-  PA_LAUNCH(ctx, PA_K_VDERIVE + KIND, (k_verify_derive<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, derived, (int)n, L)));
+  unsigned char *valid = chk + align_up(n * NCHK, 256);
+  PA_LAUNCH(ctx, PA_K_VDERIVE + KIND, (k_verify_derive<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, derived, valid, (int)n, L)));
   PA_LAUNCH(ctx, PA_K_VCHECKS + KIND, (k_verify_checks<KIND, NCHK><<<grid_for(n * NCHK), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, derived, ctx->d_comb, chk, (int)n, L)));
-  PA_LAUNCH(ctx, PA_K_VERDICT, (k_verdict<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(chk, NCHK, (int)n, verdict)));
+  PA_LAUNCH(ctx, PA_K_VERDICT, (k_verdict<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(chk, valid, NCHK, (int)n, verdict)));
   return PA_OK;
 }
 
@@ -627,10 +784,8 @@ int prove_dev(pa_ctx *ctx, const unsigned char *stmts, const unsigned char *secr
   typedef proof_kind<KIND> K;
   if (n == 0) return PA_OK;
   size_t m = n * K::NEPS;
-  int rc = work_reserve(ctx, m);
-  if (rc) return rc;
-  PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n, L)));
-  if ((rc = normalize_to(ctx, proofs, m, K::NEPS, L.proof, L.inner, L.proof_in))) return rc;
+  // every operation's thread writes its eps straight into the proof record (one inversion per warp)
+  PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, pa_outlay{proofs, K::NEPS, L.proof, L.inner, L.proof_in}, (int)n, L)));
   PA_LAUNCH(ctx, PA_K_PRESPOND + KIND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, secrets, rnd, b0, b1, (int)n, L)));
   return PA_OK;
 }
@@ -641,39 +796,48 @@ extern "C" {
 
 // ---- device-pointer entry points -------------------------------------------------------
 int pa_pokdlog_prove_dev(pa_ctx *ctx, const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (X && x && ids && rnd && proofs)) && n < (1u << 26));
   return prove_dev<PA_POK>(ctx, X, x, nullptr, nullptr, (const u64 *)ids, rnd, proofs, n);
 }
 int pa_pokdlog_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *X, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && X && ids && verdict)) && n < (1u << 26));
   return verify_dev<PA_POK, 1>(ctx, proofs, X, (const u64 *)ids, verdict, n);
 }
 int pa_powfcom_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *alpha, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && alpha && bits && ids && rnd && proofs)) && n < (1u << 26));
   return prove_dev<PA_COM>(ctx, stmt, alpha, bits, nullptr, (const u64 *)ids, rnd, proofs, n);
 }
 int pa_powfcom_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
   return verify_dev<PA_COM, 4>(ctx, proofs, stmt, (const u64 *)ids, verdict, n);
 }
 int pa_stage1_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)) && n < (1u << 26));
   return prove_dev<PA_S1>(ctx, stmt, secrets, bits, nullptr, (const u64 *)ids, rnd, proofs, n);
 }
 int pa_stage1_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
   return verify_dev<PA_S1, 8>(ctx, proofs, stmt, (const u64 *)ids, verdict, n);
 }
 int pa_stage2_prove_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bi && bj && ids && rnd && proofs)) && n < (1u << 26));
   return prove_dev<PA_S2>(ctx, stmt, secrets, bi, bj, (const u64 *)ids, rnd, proofs, n);
 }
 int pa_stage2_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
   return verify_dev<PA_S2, 16>(ctx, proofs, stmt, (const u64 *)ids, verdict, n);
 }
 
 int pa_commit_points_dev(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (alpha && beta && bits && out)) && n < (1u << 26));
   if (n == 0) return PA_OK;
   int rc = work_reserve(ctx, 3 * n);
@@ -683,6 +847,7 @@ int pa_commit_points_dev(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta,
 }
 
 int pa_y_scan_dev(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, const uint32_t *offsets, size_t nseg, size_t npoints) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (npoints == 0 || (X && Y)) && npoints < (1u << 28) && nseg >= 1);
   if (npoints == 0) return PA_OK;
   int rc = work_reserve(ctx, npoints);
@@ -692,12 +857,14 @@ int pa_y_scan_dev(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, const uint32_t *off
 }
 
 int pa_point_sum_is_inf_dev(pa_ctx *ctx, const uint8_t *B, const uint32_t *offsets, size_t nseg, size_t npoints, int32_t *flags) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && flags && (npoints == 0 || B) && nseg >= 1);
   PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<(unsigned)nseg, PA_SCAN_T, 0, ctx->stream>>>(B, 64, offsets, (int)npoints, flags)));
   return PA_OK;
 }
 
 int pa_challenge_dev(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_t *ids, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && k <= 32 && (n == 0 || (ids && out && (points || k == 0))));
   if (n == 0) return PA_OK;
   PA_LAUNCH(ctx, PA_K_CHALLENGE, (k_challenge<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(points, (int)k, (const u64 *)ids, out, (int)n)));
@@ -705,6 +872,7 @@ int pa_challenge_dev(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_
 }
 
 int pa_rng_fill256_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
   if (n == 0 || per_item == 0) return PA_OK;
   PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(seed, (const u64 *)streams, (u64 *)counters, nullptr, (int)per_item, out, (int)n, 1)));
@@ -712,6 +880,7 @@ int pa_rng_fill256_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint
 }
 
 int pa_ccs22_setup_hash_dev(pa_ctx *ctx, const uint8_t *scalars, size_t k, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (scalars && out)) && k < (1u << 24));
   if (n == 0) return PA_OK;
   PA_LAUNCH(ctx, PA_K_CHALLENGE, (k_ccs22_setup_hash<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(scalars, (int)k, out, (int)n)));
@@ -719,6 +888,7 @@ int pa_ccs22_setup_hash_dev(pa_ctx *ctx, const uint8_t *scalars, size_t k, uint8
 }
 
 int pa_rng_fill_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
   if (n == 0 || per_item == 0) return PA_OK;
   PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(seed, (const u64 *)streams, (u64 *)counters, nullptr, (int)per_item, out, (int)n)));
@@ -727,36 +897,43 @@ int pa_rng_fill_dev(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_
 
 // ---- host-buffer entry points ---------------------------------------------------------------
 int pa_pokdlog_prove(pa_ctx *ctx, const uint8_t *X, const uint8_t *x, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (X && x && ids && rnd && proofs)));
   HArg a[] = {{X, 0, n * 64}, {x, 0, n * 32}, {ids, 0, n * 8}, {rnd, 0, n * 32}, {0, proofs, n * 96}};
   return staged(ctx, a, 5, [&](unsigned char **d) { return pa_pokdlog_prove_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], d[4], n); });
 }
 int pa_pokdlog_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *X, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && X && ids && verdict)));
   HArg a[] = {{proofs, 0, n * 96}, {X, 0, n * 64}, {ids, 0, n * 8}, {0, verdict, n}};
   return staged(ctx, a, 4, [&](unsigned char **d) { return pa_pokdlog_verify_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], n); });
 }
 int pa_powfcom_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *alpha, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && alpha && bits && ids && rnd && proofs)));
   HArg a[] = {{stmt, 0, n * 192}, {alpha, 0, n * 32}, {bits, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 96}, {0, proofs, n * 352}};
   return staged(ctx, a, 6, [&](unsigned char **d) { return pa_powfcom_prove_dev(ctx, d[0], d[1], d[2], (const uint64_t *)d[3], d[4], d[5], n); });
 }
 int pa_powfcom_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)));
   HArg a[] = {{proofs, 0, n * 352}, {stmt, 0, n * 192}, {ids, 0, n * 8}, {0, verdict, n}};
   return staged(ctx, a, 4, [&](unsigned char **d) { return pa_powfcom_verify_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], n); });
 }
 int pa_stage1_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)));
   HArg a[] = {{stmt, 0, n * 448}, {secrets, 0, n * 64}, {bits, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 160}, {0, proofs, n * 672}};
   return staged(ctx, a, 6, [&](unsigned char **d) { return pa_stage1_prove_dev(ctx, d[0], d[1], d[2], (const uint64_t *)d[3], d[4], d[5], n); });
 }
 int pa_stage1_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)));
   HArg a[] = {{proofs, 0, n * 672}, {stmt, 0, n * 448}, {ids, 0, n * 8}, {0, verdict, n}};
   return staged(ctx, a, 4, [&](unsigned char **d) { return pa_stage1_verify_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], n); });
 }
 int pa_stage2_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bi && bj && ids && rnd && proofs)));
   for (size_t i = 0; i < n; ++i)
     if (bi[i] && !bj[i]) return pa_fail(ctx, PA_EINVAL, "stage 2: bi == 1 requires bj == 1 (assert at SEAL/bidder.cpp:604)");
@@ -764,22 +941,26 @@ int pa_stage2_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, co
   return staged(ctx, a, 7, [&](unsigned char **d) { return pa_stage2_prove_dev(ctx, d[0], d[1], d[2], d[3], (const uint64_t *)d[4], d[5], d[6], n); });
 }
 int pa_stage2_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)));
   HArg a[] = {{proofs, 0, n * 1344}, {stmt, 0, n * 704}, {ids, 0, n * 8}, {0, verdict, n}};
   return staged(ctx, a, 4, [&](unsigned char **d) { return pa_stage2_verify_dev(ctx, d[0], d[1], (const uint64_t *)d[2], d[3], n); });
 }
 int pa_commit_points(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (alpha && beta && bits && out)));
   HArg a[] = {{alpha, 0, n * 32}, {beta, 0, n * 32}, {bits, 0, n}, {0, out, n * 192}};
   return staged(ctx, a, 4, [&](unsigned char **d) { return pa_commit_points_dev(ctx, d[0], d[1], d[2], d[3], n); });
 }
 int pa_y_scan(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (X && Y)));
   if (n == 0) return PA_OK;
   HArg a[] = {{X, 0, n * 64}, {0, Y, n * 64}};
   return staged(ctx, a, 2, [&](unsigned char **d) { return pa_y_scan_dev(ctx, d[0], d[1], nullptr, 1, n); });
 }
 int pa_y_scan_batch(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, const uint32_t *offsets, size_t nseg) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && offsets && nseg >= 1);
   size_t n = offsets[nseg];
   PA_ARGCHECK(ctx, n == 0 || (X && Y));
@@ -788,6 +969,7 @@ int pa_y_scan_batch(pa_ctx *ctx, const uint8_t *X, uint8_t *Y, const uint32_t *o
   return staged(ctx, a, 3, [&](unsigned char **d) { return pa_y_scan_dev(ctx, d[0], d[1], (const uint32_t *)d[2], nseg, n); });
 }
 int pa_point_sum_is_inf(pa_ctx *ctx, const uint8_t *B, size_t n, int *is_inf) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && is_inf && (n == 0 || B));
   int32_t flag = 0;
   HArg a[] = {{B, 0, n * 64}, {0, &flag, 4}};
@@ -796,29 +978,34 @@ int pa_point_sum_is_inf(pa_ctx *ctx, const uint8_t *B, size_t n, int *is_inf) {
   return rc;
 }
 int pa_point_sum_is_inf_batch(pa_ctx *ctx, const uint8_t *B, const uint32_t *offsets, size_t nseg, int32_t *flags) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && offsets && flags && nseg >= 1);
   size_t n = offsets[nseg];
   HArg a[] = {{B, 0, n * 64}, {offsets, 0, (nseg + 1) * 4}, {0, flags, nseg * 4}};
   return staged(ctx, a, 3, [&](unsigned char **d) { return pa_point_sum_is_inf_dev(ctx, d[0], (const uint32_t *)d[1], nseg, n, (int32_t *)d[2]); });
 }
 int pa_challenge(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_t *ids, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && k <= 32 && (n == 0 || (ids && out)));
   HArg a[] = {{points, 0, n * k * 64}, {ids, 0, n * 8}, {0, out, n * 32}};
   return staged(ctx, a, 3, [&](unsigned char **d) { return pa_challenge_dev(ctx, d[0], k, (const uint64_t *)d[1], d[2], n); });
 }
 int pa_rng_fill256(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
   HArg a[] = {{streams, 0, n * 8}, {counters, counters, n * 8}, {0, out, n * per_item * 32}};
   return staged(ctx, a, 3, [&](unsigned char **d) { return pa_rng_fill256_dev(ctx, seed, (const uint64_t *)d[0], (uint64_t *)d[1], per_item, d[2], n); });
 }
 
 int pa_ccs22_setup_hash(pa_ctx *ctx, const uint8_t *scalars, size_t k, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (scalars && out)));
   HArg a[] = {{scalars, 0, n * k * 32}, {0, out, n * 32}};
   return staged(ctx, a, 2, [&](unsigned char **d) { return pa_ccs22_setup_hash_dev(ctx, d[0], k, d[1], n); });
 }
 
 int pa_rng_fill(pa_ctx *ctx, uint64_t seed, const uint64_t *streams, uint64_t *counters, size_t per_item, uint8_t *out, size_t n) {
+  PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (streams && counters && out)));
   HArg a[] = {{streams, 0, n * 8}, {counters, counters, n * 8}, {0, out, n * per_item * 32}};
   return staged(ctx, a, 3, [&](unsigned char **d) { return pa_rng_fill_dev(ctx, seed, (const uint64_t *)d[0], (uint64_t *)d[1], per_item, d[2], n); });

@@ -87,6 +87,124 @@ PA_D void ld_jac(jac &r, const u32 *src) {
   ld_fe(r.Z, src + 16);
 }
 
+// ---- Jacobian -> 64-byte affine: one field inversion per WARP ---------------------------------
+// Montgomery's trick across the 32 lanes: inclusive prefix and suffix products of the lanes' values by
+// shuffles (5 + 5 multiplications), ONE inversion of the warp's total (the ~270-multiplication chain is
+// the same instructions whether one lane or 32 need it), then
+//   1 / a_lane = (1 / total) * prefix_(lane-1) * suffix_(lane+1).
+// The reference pays a full inversion per point inside EC_POINT_point2oct (25 us each).
+PA_D void fe_shfl_up(fe &r, const fe &a, int d) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
+}
+PA_D void fe_shfl_down(fe &r, const fe &a, int d) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
+}
+PA_D void fe_shfl(fe &r, const fe &a, int src) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+}
+PA_D void fe_select(fe &r, bool c, const fe &a, const fe &b) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = c ? a.v[i] : b.v[i];
+}
+// r = 1 / a in every lane; a != 0 in every lane (lanes with nothing to invert pass 1).
+// Collective: all 32 lanes of the warp must call it.
+PA_D void warp_inverse(fe &r, const fe &a) {
+  const int lane = threadIdx.x & 31;
+  fe one, pre = a, suf = a, t;
+  fe_set_one(one);
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    fe_shfl_up(t, pre, d);
+    fe_select(t, lane >= d, t, one);
+    fe_mul(pre, pre, t);
+    fe_shfl_down(t, suf, d);
+    fe_select(t, lane + d < 32, t, one);
+    fe_mul(suf, suf, t);
+  }
+  fe total, inv;
+  fe_shfl(total, pre, 31);
+  fe_inv(inv, total);
+  fe_shfl_up(t, pre, 1);
+  fe_select(t, lane >= 1, t, one);
+  fe_mul(inv, inv, t);
+  fe_shfl_down(t, suf, 1);
+  fe_select(t, lane + 1 < 32, t, one);
+  fe_mul(r, inv, t);
+}
+// Where point `idx` of a kernel's output goes: out + (item / inner) * stride + (item % inner) * stride_in
+// + (idx % nper) * 64 with item = idx / nper, so the same code writes plain arrays (nper = 1, stride = 64)
+// and the eps fields of proof records (nper = eps per proof, stride = record size, `inner` proofs per record).
+struct pa_outlay {
+  unsigned char *out;
+  int nper;
+  size_t stride;
+  int inner;
+  size_t stride_in;
+  PA_HD unsigned char *at(size_t idx) const {
+    size_t item = idx / (size_t)nper;
+    return out + (item / (size_t)inner) * stride + (item % (size_t)inner) * stride_in + (idx % (size_t)nper) * 64;
+  }
+};
+inline pa_outlay pa_out_plain(unsigned char *out) { return pa_outlay{out, 1, 64, 1, 0}; }
+// The producing kernels finish with this instead of writing a Jacobian triple for a separate pass:
+// every lane brings its result (has = false: none), the warp shares one inversion, each lane stores its
+// 64-byte affine point.  Collective.
+PA_D void warp_emit_point(const pa_outlay &o, size_t idx, const jac &p, bool has) {
+  const bool real = has && !jac_is_inf(p);
+  fe z, zi;
+  fe_set_one(z);
+  if (real) z = p.Z;
+  warp_inverse(zi, z);
+  if (!has) return;
+  aff a;
+  if (real) jac_to_aff_with_zinv(a, p, zi); else aff_set_inf(a);
+  st_aff(o.at(idx), a);
+}
+
+// The separate pass, for producers that emit several points per thread (scans): thread t owns points
+// t, t + T, t + 2T, ... (coalesced across the warp), multiplies their Z together (prefix products kept in
+// `prefix`), the warp inverts the lanes' products together, and the thread unwinds its own chain.
+__global__ void __launch_bounds__(PA_BLOCK)
+k_normalize(const u32 *jin, u32 *prefix, pa_outlay o, int n, int T) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  fe acc, z;
+  fe_set_one(acc);
+  int last = -1;
+  if (t < T) {
+    for (int idx = t; idx < n; idx += T) {
+      ld_fe(z, jin + 24 * (size_t)idx + 16);
+      if (!fe_is_zero(z)) fe_mul(acc, acc, z);
+      st_fe(prefix + 8 * (size_t)idx, acc);
+      last = idx;
+    }
+  }
+  fe inv;
+  warp_inverse(inv, acc);
+  for (int idx = last; idx >= 0; idx -= T) {
+    jac p;
+    ld_jac(p, jin + 24 * (size_t)idx);
+    aff a;
+    if (fe_is_zero(p.Z)) {
+      aff_set_inf(a);
+    } else {
+      fe zi;
+      if (idx - T >= 0) {
+        fe prev;
+        ld_fe(prev, prefix + 8 * (size_t)(idx - T));
+        fe_mul(zi, inv, prev);
+      } else {
+        zi = inv;
+      }
+      fe_mul(inv, inv, p.Z);
+      jac_to_aff_with_zinv(a, p, zi);
+    }
+    st_aff(o.at((size_t)idx), a);
+  }
+}
+
 // ---- comb table -------------------------------------------------------------
 __global__ void k_comb_base(u32 *bases) {  // one thread per window: B_w = 2^(PA_COMB_BITS w) G
   int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,26 +233,33 @@ __global__ void k_comb_entries(const u32 *bases, u32 *tab) {  // one thread per 
 #define PA_FIX_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(PA_BLOCK, PA_FIX_MINBLOCKS)
-k_fixed_base(const unsigned char *scalars, const u32 *__restrict__ tab, u32 *jout, int n) {
+k_fixed_base(const unsigned char *scalars, const u32 *__restrict__ tab, pa_outlay o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  sc k;
-  ld_sc(k, scalars + 32 * (size_t)i);
+  const bool has = i < n;
   jac r;
-  fixed_base_mul(r, k, tab);
-  st_jac(jout + 24 * (size_t)i, r);
+  jac_set_inf(r);
+  if (has) {
+    sc k;
+    ld_sc(k, scalars + 32 * (size_t)i);
+    fixed_base_mul(r, k, tab);
+  }
+  warp_emit_point(o, (size_t)i, r, has);
 }
 
 __global__ void __launch_bounds__(PA_BLOCK, PA_VAR_MINBLOCKS)
-k_var_base(const unsigned char *points, const unsigned char *scalars, u32 *jout, int n) {
+k_var_base(const unsigned char *points, const unsigned char *scalars, pa_outlay o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  jac P, r;
-  sc k;
-  ld_point_jac(P, points + 64 * (size_t)i);
-  ld_sc(k, scalars + 32 * (size_t)i);
-  var_base_mul(r, P, k);
-  st_jac(jout + 24 * (size_t)i, r);
+  const bool has = i < n;
+  jac r;
+  jac_set_inf(r);
+  if (has) {
+    jac P;
+    sc k;
+    ld_point_jac(P, points + 64 * (size_t)i);
+    ld_sc(k, scalars + 32 * (size_t)i);
+    var_base_mul(r, P, k);
+  }
+  warp_emit_point(o, (size_t)i, r, has);
 }
 
 __global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
@@ -179,51 +304,6 @@ k_point_add(const unsigned char *p, const unsigned char *q, u32 *jout, int n, in
   if (sub) aff_neg(Q, Q);
   jac_madd(P, P, Q);
   st_jac(jout + 24 * (size_t)i, P);
-}
-
-// ---- Jacobian -> 64-byte affine, one inversion per thread ------------------------
-// Thread t owns points t, t + T, t + 2T, ... (coalesced across the warp).
-// Output slot of point idx: out + (idx / nper) * stride + (idx % nper) * 64, so the
-// same kernel writes plain arrays (nper = 1, stride = 64) and the eps fields of
-// proof records (nper = eps per proof, stride = record size).
-__global__ void __launch_bounds__(PA_BLOCK)
-k_normalize(const u32 *jin, u32 *prefix, unsigned char *out, int n, int T, int nper, size_t stride, int inner = 1,
-            size_t stride_in = 0) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  fe acc, z;
-  fe_set_one(acc);
-  int last = -1;
-  for (int idx = t; idx < n; idx += T) {
-    ld_fe(z, jin + 24 * (size_t)idx + 16);
-    if (!fe_is_zero(z)) fe_mul(acc, acc, z);
-    st_fe(prefix + 8 * (size_t)idx, acc);
-    last = idx;
-  }
-  if (last < 0) return;
-  fe inv;
-  fe_inv(inv, acc);
-  for (int idx = last; idx >= 0; idx -= T) {
-    jac p;
-    ld_jac(p, jin + 24 * (size_t)idx);
-    aff a;
-    if (fe_is_zero(p.Z)) {
-      aff_set_inf(a);
-    } else {
-      fe zi;
-      if (idx - T >= 0) {
-        fe prev;
-        ld_fe(prev, prefix + 8 * (size_t)(idx - T));
-        fe_mul(zi, inv, prev);
-      } else {
-        zi = inv;
-      }
-      fe_mul(inv, inv, p.Z);
-      jac_to_aff_with_zinv(a, p, zi);
-    }
-    int item = idx / nper;
-    st_aff(out + (size_t)(item / inner) * stride + (size_t)(item % inner) * stride_in + (size_t)(idx % nper) * 64, a);
-  }
 }
 
 // ---- is the wire point on the curve (coordinates < p, y^2 = x^3 + 7; infinity counts)? ---------
@@ -281,16 +361,26 @@ __global__ void k_peak_imad(u32 *sink, int iters, u32 a, u32 b) {
   u32 s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
   if (s == 0x12345u) sink[0] = s;
 }
+// 32 x 32 + 64 -> 64 multiply-add, the instruction the field arithmetic is made of: eight independent
+// accumulator chains per thread, multiplicands in registers, nothing else in the loop (SASS: 64 IMAD.WIDE.U32
+// per iteration plus the loop counter), so the figure is the multiplier pipe's own rate for this instruction.
 __global__ void k_peak_imad_wide(u64 *sink, int iters, u32 a) {
   u64 x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  u32 b = threadIdx.x * 2654435761u + 12345u;
+#define PA_WIDE8                                                                  \
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x0) : "r"(a), "r"(b));      \
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x1) : "r"(a), "r"(b));      \
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x2) : "r"(a), "r"(b));      \
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x3) : "r"(a), "r"(b));      \
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x4) : "r"(a), "r"(b));      \
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x5) : "r"(a), "r"(b));      \
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x6) : "r"(a), "r"(b));      \
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x7) : "r"(a), "r"(b));
 #pragma unroll 1
   for (int i = 0; i < iters; ++i) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      x0 = (u64)(u32)x0 * a + x0; x1 = (u64)(u32)x1 * a + x1; x2 = (u64)(u32)x2 * a + x2; x3 = (u64)(u32)x3 * a + x3;
-      x4 = (u64)(u32)x4 * a + x4; x5 = (u64)(u32)x5 * a + x5; x6 = (u64)(u32)x6 * a + x6; x7 = (u64)(u32)x7 * a + x7;
-    }
+    PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8
   }
+#undef PA_WIDE8
   u64 s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
   if (s == 0x12345u) sink[0] = s;
 }
@@ -339,13 +429,16 @@ template <int KIND> inline pa_lay pa_lay_packed() {
 // verifier step 1: challenge + unpublished challenge share, one thread per proof
 template <int KIND>
 __global__ void __launch_bounds__(PA_BLOCK)
-k_verify_derive(const unsigned char *proofs, const unsigned char *stmts, const u64 *ids, u32 *derived, int n, pa_lay L) {
+k_verify_derive(const unsigned char *proofs, const unsigned char *stmts, const u64 *ids, u32 *derived, unsigned char *valid,
+                int n, pa_lay L) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   sc ch1;
   verify_derive<KIND>(ch1, proofs + L.P(i), stmts + L.S(i), ids[i / L.inner]);
 #pragma unroll
   for (int k = 0; k < 8; ++k) derived[8 * (size_t)i + k] = ch1.v[k];
+  // received points must be canonical and on the curve (or infinity); otherwise the verdict is 0
+  valid[i] = proof_points_valid<KIND>(proofs + L.P(i), stmts + L.S(i)) ? 1 : 0;
 }
 // verifier step 2: thread t owns check j = t / n of proof i = t % n (check-major: a warp
 // runs the same check, hence the same shape, for 32 proofs)
@@ -363,10 +456,10 @@ k_verify_checks(const unsigned char *proofs, const unsigned char *stmts, const u
   chk[t] = ok ? 1 : 0;
 }
 // verifier step 3: verdict = AND of all checks (no early exit, as SEAL/bidder.cpp:244-298)
-__global__ void k_verdict(const unsigned char *chk, int nchk, int n, unsigned char *verdict) {
+__global__ void k_verdict(const unsigned char *chk, const unsigned char *valid, int nchk, int n, unsigned char *verdict) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned v = 1;
+  unsigned v = valid[i];
   for (int j = 0; j < nchk; ++j) v &= chk[(size_t)j * n + i];
   verdict[i] = (unsigned char)v;
 }
@@ -380,14 +473,15 @@ PA_D int proof_branch(int kind, const unsigned char *b0, const unsigned char *b1
 template <int KIND>
 __global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
 k_prove_ops(const unsigned char *stmts, const unsigned char *rnd, const unsigned char *b0, const unsigned char *b1,
-            const u32 *__restrict__ comb, u32 *jout, int n, pa_lay L) {
+            const u32 *__restrict__ comb, pa_outlay o, int n, pa_lay L) {
   typedef proof_kind<KIND> K;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * K::NEPS) return;
-  int j = t / n, i = t % n;
+  const bool has = t < n * K::NEPS;
+  int j = t / n, i = t % n, e = 0;
   jac r;
-  int e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + L.S(i), rnd + L.R(i), comb);
-  st_jac(jout + 24 * ((size_t)i * K::NEPS + e), r);
+  jac_set_inf(r);
+  if (has) e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + L.S(i), rnd + L.R(i), comb);
+  warp_emit_point(o, (size_t)i * K::NEPS + e, r, has);  // eps e of proof i, straight into the record
 }
 // prover step 3 (after k_normalize wrote the eps points): challenge and responses
 template <int KIND>

@@ -353,6 +353,32 @@ PA_HD void proof_challenge(sc &ch, const unsigned char *proof, const unsigned ch
   challenge_hash(ch, pts, K::NHASH, id);
 }
 
+// Is a 64-byte wire encoding acceptable?  Either the point at infinity (64 zero bytes) or canonical
+// coordinates (both < p) satisfying y^2 = x^3 + 7: what EC_POINT_set_affine_coordinates enforces when a
+// point enters libcrypto in the reference.  The a = 0 group formulas never use the constant 7, so an
+// off-curve point would silently be processed on another curve, and a coordinate >= p would hash
+// differently from its reduced twin: both are refused here, before any check runs.
+PA_HD bool wire_point_valid(const unsigned char *p) {
+  aff a, c;
+  load_wire_point(a, p);
+  if (aff_is_inf(a)) return true;
+  fe_canon(c.x, a.x);
+  fe_canon(c.y, a.y);
+  bool canonical = true;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) canonical &= c.x.v[k] == a.x.v[k] && c.y.v[k] == a.y.v[k];
+  return canonical && aff_on_curve(a);
+}
+// every point a verifier receives: the eps of the proof and the statement
+template <int KIND>
+PA_HD bool proof_points_valid(const unsigned char *proof, const unsigned char *stmt) {
+  typedef proof_kind<KIND> K;
+  bool ok = true;
+  for (int i = 0; i < K::NEPS; ++i) ok &= wire_point_valid(proof + 64 * i);
+  for (int i = 0; i < K::NSTMT; ++i) ok &= wire_point_valid(stmt + 64 * i);
+  return ok;
+}
+
 // verifier: the challenge share that is not published.  ch1 = ch - ch2 (- ch3)
 // (SEAL/bidder.cpp:253, 485, 934-935); for POK it is h itself (:125).
 template <int KIND>

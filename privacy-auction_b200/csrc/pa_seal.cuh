@@ -26,57 +26,67 @@
 // commitment points straight from the draw array: slot s has draws
 //   alpha, beta, v_A, v_B, r1, d1, d2   (7 x 32 B)
 __global__ void __launch_bounds__(PA_BLOCK)
-k_seal_commit_points(const unsigned char *rndc, const unsigned char *bits, const u32 *__restrict__ comb, u32 *jout, int n) {
+k_seal_commit_points(const unsigned char *rndc, const unsigned char *bits, const u32 *__restrict__ comb, pa_outlay o, int n) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 3 * n) return;
+  const bool has = t < 3 * n;
   int which = t / n, i = t % n;
-  sc a, b, k;
-  ld_sc(a, rndc + 224 * (size_t)i);
-  ld_sc(b, rndc + 224 * (size_t)i + 32);
-  if (which == 0) {
-    sc bit;
-    sc_set_zero(bit);
-    bit.v[0] = bits[i] ? 1u : 0u;
-    sc_mul(k, a, b);
-    sc_add(k, k, bit);
-  } else {
-    k = which == 1 ? a : b;
-  }
   jac r;
-  fixed_base_mul(r, k, comb);
-  st_jac(jout + 24 * ((size_t)i * 3 + which), r);
+  jac_set_inf(r);
+  if (has) {
+    sc a, b, k;
+    ld_sc(a, rndc + 224 * (size_t)i);
+    ld_sc(b, rndc + 224 * (size_t)i + 32);
+    if (which == 0) {
+      sc bit;
+      sc_set_zero(bit);
+      bit.v[0] = bits[i] ? 1u : 0u;
+      sc_mul(k, a, b);
+      sc_add(k, k, bit);
+    } else {
+      k = which == 1 ? a : b;
+    }
+    fixed_base_mul(r, k, comb);
+  }
+  warp_emit_point(o, (size_t)i * 3 + which, r, has);
 }
 
 // X = g^x, R = g^r from the round-one draws x, r, v_X, v_R (4 x 32 B per bidder)
 __global__ void __launch_bounds__(PA_BLOCK)
-k_seal_r1_points(const unsigned char *rnd1, const u32 *__restrict__ comb, u32 *jout, int n) {
+k_seal_r1_points(const unsigned char *rnd1, const u32 *__restrict__ comb, pa_outlay o, int n) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 2 * n) return;
+  const bool has = t < 2 * n;
   int which = t / n, i = t % n;
-  sc k;
-  ld_sc(k, rnd1 + 128 * (size_t)i + 32 * which);
   jac r;
-  fixed_base_mul(r, k, comb);
-  st_jac(jout + 24 * ((size_t)i * 2 + which), r);
+  jac_set_inf(r);
+  if (has) {
+    sc k;
+    ld_sc(k, rnd1 + 128 * (size_t)i + 32 * which);
+    fixed_base_mul(r, k, comb);
+  }
+  warp_emit_point(o, (size_t)i * 2 + which, r, has);
 }
 
 // the cryptogram: b = R^x if the bidder vetoes, Y^x otherwise           SEAL/bidder.cpp:1301-1309
 __global__ void __launch_bounds__(PA_BLOCK)
 k_seal_encode(const u32 *act, const u32 *pauc, const unsigned char *bits, const u32 *boff, int step,
               const unsigned char *junc, const unsigned char *prevbit, const unsigned char *r1, const unsigned char *Y,
-              const unsigned char *rnd1, unsigned char *ebit, u32 *jout, int n) {
+              const unsigned char *rnd1, unsigned char *ebit, pa_outlay o, int n) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  u32 slot = act[p];
-  int bit = bits[boff[slot] + step];
-  int veto = bit && (!junc[pauc[p]] || prevbit[slot]);
-  ebit[p] = (unsigned char)veto;
-  jac P, r;
-  sc x;
-  ld_point_jac(P, veto ? r1 + 320 * (size_t)p + 64 : Y + 64 * (size_t)p);
-  ld_sc(x, rnd1 + 128 * (size_t)p);
-  var_base_mul(r, P, x);
-  st_jac(jout + 24 * (size_t)p, r);
+  const bool has = p < n;
+  jac r;
+  jac_set_inf(r);
+  if (has) {
+    u32 slot = act[p];
+    int bit = bits[boff[slot] + step];
+    int veto = bit && (!junc[pauc[p]] || prevbit[slot]);
+    ebit[p] = (unsigned char)veto;
+    jac P;
+    sc x;
+    ld_point_jac(P, veto ? r1 + 320 * (size_t)p + 64 : Y + 64 * (size_t)p);
+    ld_sc(x, rnd1 + 128 * (size_t)p);
+    var_base_mul(r, P, x);
+  }
+  warp_emit_point(o, (size_t)p, r, has);
 }
 
 PA_D void cp64(unsigned char *d, const unsigned char *s) {
@@ -164,16 +174,20 @@ __global__ void k_seal_scatter_u8(const u32 *g, const unsigned char *src, unsign
 
 // both candidates of every item: cand[2i] = Y^x (no veto), cand[2i+1] = R^x (veto)    SEAL/bidder.cpp:1301-1309
 __global__ void __launch_bounds__(PA_BLOCK, PA_VAR_MINBLOCKS)
-k_seal_candidates(const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1, u32 *jout, int n) {
+k_seal_candidates(const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1, pa_outlay o, int n) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 2 * n) return;
+  const bool has = t < 2 * n;
   int which = t / n, i = t % n;
-  jac P, r;
-  sc x;
-  ld_point_jac(P, which ? r1 + 320 * (size_t)i + 64 : Y + 64 * (size_t)i);
-  ld_sc(x, rnd1 + 128 * (size_t)i);
-  var_base_mul(r, P, x);
-  st_jac(jout + 24 * ((size_t)i * 2 + which), r);
+  jac r;
+  jac_set_inf(r);
+  if (has) {
+    jac P;
+    sc x;
+    ld_point_jac(P, which ? r1 + 320 * (size_t)i + 64 : Y + 64 * (size_t)i);
+    ld_sc(x, rnd1 + 128 * (size_t)i);
+    var_base_mul(r, P, x);
+  }
+  warp_emit_point(o, (size_t)i * 2 + which, r, has);
 }
 
 // state[0] = junction flag, state[1] = previous deciding step (-1: none), state[2] = next step to run,
@@ -363,6 +377,271 @@ k_seal_decide_shard(int s, int m, int limit, int world, const unsigned char *bit
   if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
 }
 
+// ---- peer exchange: the ranks' kernels talk through each other's HBM ---------------------------------
+// Every rank owns a window (pa_xchg_create) that all ranks have mapped (pa_xchg_connect, CUDA IPC over
+// NVLink).  A value is PUT into the same slot of every rank's window: 24 payload words, a system-scope
+// fence, then a tag word; readers poll the tag in their OWN memory and then read the payload.  No host
+// round trip and no collective call: the step walk of a sharded auction is one kernel per pass.
+//   slot (kind, parity, step, rank): 128 bytes = 24 payload words + tag at word 24
+//     kind 0  a rank's sum of public keys of a step     (Y reconstruction, SEAL/bidder.cpp:1286-1299)
+//     kind 1  a rank's sum of cryptograms of a step     (round three, SEAL/bidder.cpp:1393-1397)
+//     kind 2  end of run: (draws clean, verdict, max bid)
+//   tag = epoch << 8 | pass: epoch counts sharded runs (the same on every rank, parity = epoch & 1 picks one of
+//   two slot sets), pass counts the passes of a run, so a slot written twice in a run (a step redone after
+//   the junction) is never mistaken for its first value.
+//   bulk area: two buffers for a plain all-gather of up to PA_XCHG_BULK bytes (the step-major schedule's X
+//   and b), tagged with a sequence number per (buffer, rank).
+#define PA_XCHG_STEPS 64
+#define PA_XCHG_SLOTS (3 * 2 * PA_XCHG_STEPS * PA_XCHG_MAX_WORLD)
+#define PA_XCHG_BULK_OFF ((size_t)PA_XCHG_SLOTS * 128 + 4096)
+#define PA_XCHG_BULK ((PA_XCHG_BYTES - PA_XCHG_BULK_OFF) / 2)
+#define PA_XCHG_TIMEOUT_NS 10000000000ull  // a peer that does not show up in 10 s is an error, not a hang
+
+PA_D unsigned char *xchg_slot(unsigned char *win, int kind, int par, int step, int rank) {
+  return win + 128 * (size_t)((((kind * 2 + par) * PA_XCHG_STEPS) + step) * PA_XCHG_MAX_WORLD + rank);
+}
+PA_D unsigned long long pa_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// block-cooperative: put val[0..24) into `slot` of every rank's window (warp w serves ranks w, w + nwarps, ...)
+PA_D void xchg_put(unsigned char *const *peers, int world, int kind, int par, int step, int rank, const u32 *val, u32 tag) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = warp; r < world; r += nw) {
+    volatile u32 *dst = (volatile u32 *)xchg_slot(peers[r], kind, par, step, rank);
+    if (lane < 24) dst[lane] = val[lane];
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) dst[24] = tag;
+  }
+}
+// block-cooperative: wait until every rank's value for `slot` has arrived in THIS rank's window, copy the
+// payloads to shared memory.  Returns false (for the whole block) when a peer timed out; *err is set.
+PA_D bool xchg_get(unsigned char *win, int world, int kind, int par, int step, u32 tag, u32 (*dst)[24], int *err) {
+  const int t = threadIdx.x;
+  int bad = 0;
+  if (t < world) {
+    volatile u32 *src = (volatile u32 *)xchg_slot(win, kind, par, step, t);
+    const unsigned long long t0 = pa_globaltimer();
+    while (src[24] != tag) {
+      if (pa_globaltimer() - t0 > PA_XCHG_TIMEOUT_NS) {
+        bad = 1;
+        atomicExch(err, 1);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  if (__syncthreads_or(bad)) return false;
+  __threadfence_system();
+  for (int k = t; k < world * 24; k += blockDim.x)
+    dst[k / 24][k % 24] = ((volatile u32 *)xchg_slot(win, kind, par, step, k / 24))[k % 24];
+  __syncthreads();
+  return true;
+}
+
+// Plain all-gather through the windows: every rank's `bytes` at send go to offset rank * bytes of bulk
+// buffer `buf` in every window.  Grid = world blocks: block r copies to rank r, then block 0 waits for all tags.
+__global__ void k_xchg_allgather(const unsigned char *send, size_t bytes, unsigned char *const *peers, int world, int rank,
+                                 int buf, u32 seq, int *err) {
+  const int r = blockIdx.x;
+  unsigned char *bulk = peers[r] + PA_XCHG_BULK_OFF + (size_t)buf * PA_XCHG_BULK;
+  const uint4 *src = reinterpret_cast<const uint4 *>(send);
+  uint4 *dst = reinterpret_cast<uint4 *>(bulk + (size_t)rank * bytes);
+  for (size_t k = threadIdx.x; k < bytes / 16; k += blockDim.x) dst[k] = src[k];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *(volatile u32 *)(peers[r] + (size_t)PA_XCHG_SLOTS * 128 + 4 * (buf * PA_XCHG_MAX_WORLD + rank)) = seq;
+  if (r != rank) return;
+  // the block addressed to ourselves also waits until everybody's part has landed here
+  if ((int)threadIdx.x < world) {
+    volatile u32 *tagp = (volatile u32 *)(peers[rank] + (size_t)PA_XCHG_SLOTS * 128 + 4 * (buf * PA_XCHG_MAX_WORLD + threadIdx.x));
+    const unsigned long long t0 = pa_globaltimer();
+    while (*tagp != seq) {
+      if (pa_globaltimer() - t0 > PA_XCHG_TIMEOUT_NS) {
+        atomicExch(err, 1);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __threadfence_system();
+}
+
+// Y reconstruction of steps [s0, s0 + gridDim.x) when every rank holds a slice of the bidders: block b scans
+// this rank's m public keys of step s0 + b, PUTS their sum, GETS every rank's sum, and finishes
+// Y_id = E_id + P_id - T with E_id = (sum of the ranks before this one) + (local exclusive prefix).
+// Nobody needs anybody else's X: 96 bytes per rank and step cross the link instead of 64 bytes per bidder.
+__global__ void __launch_bounds__(PA_SCAN_T)
+k_y_scan_shard(const unsigned char *X, size_t xstride, int m, int s0, unsigned char *const *peers, int world, int rank, int par,
+               u32 tag, int *err, u32 *jout) {
+  __shared__ __align__(16) u32 part[2][PA_SCAN_T][24];
+  __shared__ __align__(16) u32 tot[PA_XCHG_MAX_WORLD][24];
+  __shared__ __align__(16) u32 bt[2][24];  // base = sum of the ranks before this one; minus the total
+  const int b = blockIdx.x, s = s0 + b, lo = b * m, t = threadIdx.x;
+  int chunk = (m + PA_SCAN_T - 1) / PA_SCAN_T;
+  int c0 = min(m, t * chunk), c1 = min(m, c0 + chunk);
+  jac acc;
+  jac_set_inf(acc);
+  for (int id = c0; id < c1; ++id) {
+    aff x;
+    ld_aff(x, X + xstride * (size_t)(lo + id));
+    jac_madd(acc, acc, x);
+  }
+  st_jac(part[0][t], acc);
+  __syncthreads();
+  int cur = 0;
+  for (int d = 1; d < PA_SCAN_T; d <<= 1) {  // Hillis-Steele inclusive scan of the chunk sums
+    jac a;
+    ld_jac(a, part[cur][t]);
+    if (t >= d) {
+      jac c;
+      ld_jac(c, part[cur][t - d]);
+      jac_add(a, a, c);
+    }
+    st_jac(part[cur ^ 1][t], a);
+    __syncthreads();
+    cur ^= 1;
+  }
+  xchg_put(peers, world, 0, par, s, rank, part[cur][PA_SCAN_T - 1], tag);
+  if (!xchg_get(peers[rank], world, 0, par, s, tag, tot, err)) return;
+  if (t == 0) {
+    jac all, base, v;
+    jac_set_inf(all);
+    jac_set_inf(base);
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) base = all;
+      ld_jac(v, tot[r]);
+      jac_add(all, all, v);
+    }
+    jac_neg(all, all);
+    st_jac(bt[0], base);
+    st_jac(bt[1], all);
+  }
+  __syncthreads();
+  jac total, e, base;
+  ld_jac(base, bt[0]);
+  ld_jac(total, bt[1]);
+  if (t == 0) jac_set_inf(e); else ld_jac(e, part[cur][t - 1]);
+  jac_add(e, e, base);
+  for (int id = c0; id < c1; ++id) {
+    aff x;
+    ld_aff(x, X + xstride * (size_t)(lo + id));
+    jac p, y;
+    jac_madd(p, e, x);     // inclusive prefix
+    jac_add(y, e, p);      // E + P
+    jac_add(y, y, total);  // - T
+    st_jac(jout + 24 * (size_t)(lo + id), y);
+    e = p;
+  }
+}
+
+// k_seal_decide for a rank that holds a slice: one block walks steps [state[2], limit); per step it selects
+// and sums its own cryptograms, PUTS the sum, GETS every rank's sum, folds them and takes the decision all
+// ranks take alike.  The exchange happens inside the kernel, once per step.   SEAL/bidder.cpp:1301-1309, 1386-1421
+__global__ void __launch_bounds__(PA_SCAN_T)
+k_seal_walk_shard(int m, int limit, int speculative, const unsigned char *bits, const u32 *boff, const unsigned char *cand,
+                  unsigned char *prevbit, int *state, unsigned char *ebit, unsigned char *bj, unsigned char *b, int *stage,
+                  int *prevstep, int *r3, unsigned char *const *peers, int world, int rank, int par, u32 tag, int *err) {
+  __shared__ __align__(16) u32 part[PA_SCAN_T][24];
+  __shared__ __align__(16) u32 tot[PA_XCHG_MAX_WORLD][24];
+  __shared__ int s_junc, s_last, s_deciding;
+  int t = threadIdx.x;
+  if (t == 0) s_junc = state[0], s_last = state[1];
+  __syncthreads();
+  int s = state[2];
+  for (; s < limit; ++s) {
+    int junc = s_junc;
+    jac acc;
+    jac_set_inf(acc);
+    for (int p = t; p < m; p += PA_SCAN_T) {
+      size_t i = (size_t)s * m + p;
+      int bit = bits[boff[p] + s];
+      int pb = prevbit[p];
+      int veto = bit && (!junc || pb);
+      ebit[i] = (unsigned char)veto;
+      bj[i] = (unsigned char)pb;
+      const unsigned char *src = cand + 64 * (2 * i + veto);
+      cp64(b + 64 * i, src);
+      aff x;
+      ld_aff(x, src);
+      jac_madd(acc, acc, x);
+    }
+    st_jac(part[t], acc);
+    __syncthreads();
+    for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
+      if (t < d) {
+        jac a, c;
+        ld_jac(a, part[t]);
+        ld_jac(c, part[t + d]);
+        jac_add(a, a, c);
+        st_jac(part[t], a);
+      }
+      __syncthreads();
+    }
+    xchg_put(peers, world, 1, par, s, rank, part[0], tag);
+    if (!xchg_get(peers[rank], world, 1, par, s, tag, tot, err)) {
+      if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
+      return;
+    }
+    for (int d = PA_XCHG_MAX_WORLD / 2; d > 0; d >>= 1) {  // fold the ranks' sums
+      if (t < d && t + d < world) {
+        jac a, c;
+        ld_jac(a, tot[t]);
+        ld_jac(c, tot[t + d]);
+        jac_add(a, a, c);
+        st_jac(tot[t], a);
+      }
+      __syncthreads();
+    }
+    if (t == 0) {
+      jac a;
+      ld_jac(a, tot[0]);
+      s_deciding = jac_is_inf(a) ? 0 : 1;
+      stage[s] = junc ? 2 : 1;
+      prevstep[s] = s_last;
+      r3[s] = s_deciding;
+    }
+    __syncthreads();
+    bool stop = false;
+    if (s_deciding) {
+      for (int p = t; p < m; p += PA_SCAN_T) prevbit[p] &= bits[boff[p] + s];
+      if (speculative && !junc) stop = true;  // first deciding step: one more step is still valid
+      __syncthreads();
+      if (t == 0) {
+        if (!junc) state[3] = s;  // the junction
+        s_junc = 1, s_last = s;
+      }
+    }
+    __syncthreads();
+    if (stop && limit > s + 2) limit = s + 2;
+  }
+  if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
+}
+
+// end of a sharded run: every rank PUTS (draws clean, verdict, max bid) and reads everybody's; out = the AND
+// of the first two and the OR of the max bids, so that all ranks take the same decision about a rerun.
+__global__ void k_xchg_final(u32 clean, u32 ok, u64 maxbid, unsigned char *const *peers, int world, int rank, int par, u32 tag,
+                             int *err, u64 *out) {
+  __shared__ __align__(16) u32 val[24];
+  __shared__ __align__(16) u32 tot[PA_XCHG_MAX_WORLD][24];
+  if (threadIdx.x < 24) val[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) val[0] = clean, val[1] = ok, val[2] = (u32)maxbid, val[3] = (u32)(maxbid >> 32);
+  __syncthreads();
+  xchg_put(peers, world, 2, par, 0, rank, val, tag);
+  if (!xchg_get(peers[rank], world, 2, par, 0, tag, tot, err)) return;
+  if (threadIdx.x == 0) {
+    u64 c = 1, o = 1, mb = 0;
+    for (int r = 0; r < world; ++r) c &= tot[r][0], o &= tot[r][1], mb |= (u64)tot[r][2] | ((u64)tot[r][3] << 32);
+    out[0] = c, out[1] = o, out[2] = mb;
+  }
+}
+
+// TEST HOOK (pa_debug_set PA_DBG_CORRUPT): flip one byte of a published record
+__global__ void k_dbg_flip(unsigned char *p) { *p ^= 0x01; }
+
 // ---- host side ------------------------------------------------------------------------------------
 // repeat a verification launch `vreps` times (see pa_seal_job.verify)
 #define PA_VREP(...)                           \
@@ -435,11 +714,71 @@ struct StepBufs {  // per-step device buffers; two sets, used alternately
 
 }  // namespace
 
+static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_major);
+
+// The phase-major schedule computes draw counters arithmetically, which is exact unless a draw is rejected
+// (probability 2^-128 per draw).  When that happens (all ranks of a sharded auction learn it together) the
+// auction is simply run again step-major, where every counter is carried sequentially.
 extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
+  PA_ENTER(ctx);
+  bool rerun = false;
+  int rc = seal_run_impl(ctx, job, &rerun);
+  if (rc == PA_OK && rerun) {
+    pa_seal_job again = *job;
+    again.schedule = PA_SEAL_STEP_MAJOR;
+    ctx->reruns++;
+    rc = seal_run_impl(ctx, &again, &rerun);
+  }
+  return rc;
+}
+extern "C" uint64_t pa_ctx_reruns(pa_ctx *ctx) { return ctx ? ctx->reruns : 0; }
+extern "C" int pa_xchg_skip(pa_ctx *ctx) {  // a rank that owns no bidder of a sharded auction: keep the run counter in step
+  PA_ENTER(ctx);
+  ctx->xchg.epoch++;
+  return PA_OK;
+}
+
+static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_major) {
   PA_ARGCHECK(ctx, ctx && job && job->n_auctions >= 1 && job->n && job->c && job->bids);
   const size_t A = job->n_auctions;
-  const bool sharded = job->allgather != nullptr;
-  PA_ARGCHECK(ctx, !sharded || (A == 1 && job->hi > job->lo && job->hi <= job->n[0] && job->d_send && job->d_recv && job->slice >= job->hi - job->lo));
+  const bool p2p = job->use_xchg != 0;  // exchanges go through the peer window, inside kernels
+  const bool sharded = job->allgather != nullptr || p2p;
+  PA_ARGCHECK(ctx, !sharded || (A == 1 && job->hi > job->lo && job->hi <= job->n[0] && job->slice >= job->hi - job->lo));
+  PA_ARGCHECK(ctx, !sharded || p2p || (job->d_send && job->d_recv));
+  const int xworld = sharded ? (int)((job->n[0] + job->slice - 1) / job->slice) : 1;  // ranks that own bidders
+  const int xrank = sharded ? (int)(job->lo / job->slice) : 0;
+  PA_ARGCHECK(ctx, !p2p || (ctx->xchg.world >= xworld && ctx->xchg.rank == xrank && job->lo == (uint32_t)xrank * job->slice &&
+                            (size_t)job->slice * 64 * xworld <= PA_XCHG_BULK));
+  u32 xpass = 0, xseq = 0;  // passes / plain all-gathers of this run
+  if (p2p) ctx->xchg.epoch++;
+  const u32 xepoch = ctx->xchg.epoch;
+  const int xpar = (int)(xepoch & 1u);
+  unsigned char *const *xpeers = ctx->xchg.d_peers;
+  int *xerr = ctx->xchg.d_err;
+  bool draws_clean = true;
+  // stream-ordered all-gather of `bytes` per rank through the windows; *recv = where the concatenation lands
+  auto xchg_allgather = [&](const unsigned char *send, size_t bytes, const unsigned char **recv) -> int {
+    const int buf = (int)(xseq & 1u);
+    const u32 seq = (xepoch << 12) | (++xseq);
+    PA_LAUNCH(ctx, PA_K_ENCODE, (k_xchg_allgather<<<xworld, 256, 0, ctx->stream>>>(send, bytes, xpeers, xworld, xrank, buf, seq, xerr)));
+    *recv = ctx->xchg.local + PA_XCHG_BULK_OFF + (size_t)buf * PA_XCHG_BULK;
+    return PA_OK;
+  };
+  auto xchg_check = [&]() -> int {  // after a host sync: did a wait on a peer time out?
+    int e = 0;
+    PA_CUDA(ctx, cudaMemcpyAsync(&e, xerr, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e) {
+      cudaMemsetAsync(xerr, 0, sizeof(int), ctx->stream);
+      return pa_fail(ctx, PA_ECUDA, "pa_seal_run: a peer did not reach the exchange within 10 s (peer exchange window)");
+    }
+    return PA_OK;
+  };
+  // TEST HOOK: flip one byte of a published record between proving and verifying
+  auto dbg_corrupt = [&](int section, unsigned char *rec) -> int {
+    if (ctx->corrupt.section == section) PA_LAUNCH(ctx, PA_K_VERDICT, (k_dbg_flip<<<1, 1, 0, ctx->stream>>>(rec + ctx->corrupt.offset)));
+    return PA_OK;
+  };
   const bool verify = job->verify != 0;
   // verify = k > 1: every proof is verified k times (k = n - 1 is the work of the reference, where each of the n
   // bidders repeats the same deterministic checks on everybody else); the verdicts do not change
@@ -447,7 +786,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   // one unsharded auction: phase-major schedule unless the caller asks for the step-major one
   // (sharded: the exchange buffers must hold the X of all steps, and a Jacobian partial sum)
   bool phased = A == 1 && job->c[0] >= 1 && job->schedule != PA_SEAL_STEP_MAJOR &&
-                (!sharded || (job->xchg_bytes >= (size_t)job->c[0] * job->slice * 64 && job->xchg_bytes >= 128));
+                (!sharded || p2p || (job->xchg_bytes >= (size_t)job->c[0] * job->slice * 64 && job->xchg_bytes >= 128));
   PA_ARGCHECK(ctx, job->schedule != PA_SEAL_PHASE_MAJOR || phased);
   const bool want_r1 = job->out_r1 != nullptr, want_b = job->out_r2_b != nullptr, want_proof = job->out_r2_proof != nullptr;
   int rc;
@@ -495,6 +834,8 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     unsigned char *Xall, *Yall, *part;  // sharded: every bidder's X / Y of every step; the ranks' partial sums of a step
     u32 *gidx, *lidx, *soffN;
   } PH{};
+  unsigned char *d_xsend = nullptr;  // peer window: staging of this rank's part of a plain all-gather
+  u64 *d_xfinal = nullptr;
   const size_t nall = job->n[0];
   const size_t T = phased ? cmax * m : 0;
   const size_t nY = sharded ? nall : m;
@@ -511,11 +852,15 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PH.bi = pool.alloc<unsigned char>(T + 256); PH.bjp = pool.alloc<unsigned char>(T + 256);
       PH.rnd2 = pool.alloc<unsigned char>(T * 352 + 256); PH.proof = pool.alloc<unsigned char>(T * 1344 + 256);
       PH.r2ok = pool.alloc<unsigned char>(T + 256);
-      if (sharded) {
+      if (sharded && !p2p) {
         PH.Xall = pool.alloc<unsigned char>(cmax * nall * 64); PH.Yall = pool.alloc<unsigned char>(cmax * nall * 64);
         PH.gidx = pool.alloc<u32>(cmax * nall); PH.lidx = pool.alloc<u32>(T); PH.soffN = pool.alloc<u32>(cmax + 1);
         PH.part = pool.alloc<unsigned char>(((nall + job->slice - 1) / job->slice) * 128);
       }
+    }
+    if (p2p) {
+      d_xsend = pool.alloc<unsigned char>((size_t)job->slice * 64);
+      d_xfinal = pool.alloc<u64>(4);
     }
     d_bits = pool.alloc<unsigned char>(Mb);
     d_boff = pool.alloc<u32>(m + 1);
@@ -616,7 +961,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       bool clean = true;
       for (u32 k = boff[s]; k < boff[s + 1]; ++k) clean &= after[k] == sctr[k] + 7;
       u64 cnt = 7ull * (boff[s + 1] - boff[s]);
-      if (!clean) phased = false;  // a rejected draw (probability 2^-128): counters are no longer arithmetic
+      if (!clean) draws_clean = false;  // a rejected draw (probability 2^-128): counters are no longer arithmetic
       if (!clean) {
         u64 zero = 0;
         PA_CUDA(ctx, cudaMemcpyAsync(d_ctr + s, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -629,12 +974,13 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     // and the verification of all of it
     auto commit_work = [&]() -> int {
       int rc2;
-      if ((rc2 = work_reserve(ctx, 3 * Mb))) return rc2;
-      PA_LAUNCH(ctx, PA_K_COMMIT, (k_seal_commit_points<<<grid_for(3 * Mb), PA_BLOCK, 0, ctx->stream>>>(d_rndc, d_bits, ctx->d_comb, work_jac(ctx), (int)Mb)));
-      if ((rc2 = normalize_to(ctx, d_crec, 3 * Mb, 3, 736))) return rc2;
+      PA_LAUNCH(ctx, PA_K_COMMIT, (k_seal_commit_points<<<grid_for(3 * Mb), PA_BLOCK, 0, ctx->stream>>>(d_rndc, d_bits, ctx->d_comb, pa_outlay{d_crec, 3, 736, 1, 0}, (int)Mb)));
       PA_CUDA(ctx, cudaEventRecord(ev_enc[1], ctx->stream));  // phi, A, B are in the records
       if ((rc2 = prove_dev<PA_POK>(ctx, d_crec + 64, d_rndc, nullptr, nullptr, d_cid, d_rndc + 64, d_crec + 192, 2 * Mb, LC2))) return rc2;
       if ((rc2 = prove_dev<PA_COM>(ctx, d_crec, d_rndc, d_bits, nullptr, d_cid, d_rndc + 128, d_crec + 384, Mb, LC))) return rc2;
+      if (ctx->corrupt.bidder < m && ctx->corrupt.step < boff[ctx->corrupt.bidder + 1] - boff[ctx->corrupt.bidder] &&
+          (rc2 = dbg_corrupt(1, d_crec + 736 * ((size_t)boff[ctx->corrupt.bidder] + ctx->corrupt.step))))
+        return rc2;
       if (!verify) {
         PA_CUDA(ctx, cudaMemsetAsync(d_cv + 3 * Mb, 1, Mb, ctx->stream));
         return PA_OK;
@@ -683,6 +1029,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     auto pok_all = [&]() -> int {
       int rc2;
       if ((rc2 = prove_dev<PA_POK>(ctx, PH.r1, PH.rnd1, nullptr, nullptr, PH.pid, PH.rnd1 + 64, PH.r1 + 128, 2 * T, LR2))) return rc2;
+      if (ctx->corrupt.step < c && ctx->corrupt.bidder < m && (rc2 = dbg_corrupt(2, PH.r1 + 320 * (ctx->corrupt.step * m + ctx->corrupt.bidder)))) return rc2;
       if (verify) {
         PA_VREP(verify_dev<PA_POK, 1>(ctx, PH.r1 + 128, PH.r1, PH.pid, PH.pokv, 2 * T, LR2));
         PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(PH.pokv, nullptr, PH.r1ok, (int)T)));
@@ -701,9 +1048,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream + i0, PH.ictr + i0, nullptr, 4, PH.rnd1 + 128 * i0, (int)cnt)));
       PA_CUDA(ctx, cudaMemcpyAsync(after.data() + i0, PH.ictr + i0, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
       int rc2;
-      if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
-      PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
-      if ((rc2 = normalize_to(ctx, PH.r1 + 320 * i0, 2 * cnt, 2, 320))) return rc2;
+      PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, pa_outlay{PH.r1 + 320 * i0, 2, 320, 1, 0}, (int)cnt)));
       if (!speculative && s1 == c && !pok_on_lane) {
         // these are the last keys: every X and R is final, so their proofs can run beside the rest of this pass
         // (they write the proof fields of the round-one records, the pass reads the point fields)
@@ -715,7 +1060,14 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
         pok_on_lane = true;
       }
       if (!sharded) {
+        if ((rc2 = work_reserve(ctx, cnt))) return rc2;
         PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(s1 - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
+        if ((rc2 = normalize_to(ctx, PH.Y + 64 * i0, cnt))) return rc2;
+      } else if (p2p) {
+        // every rank scans its own slice; only the ranks' sums of public keys (96 bytes per rank and step) are exchanged,
+        // kernel to kernel through the peer windows
+        if ((rc2 = work_reserve(ctx, cnt))) return rc2;
+        PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan_shard<<<(unsigned)(s1 - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, (int)m, (int)s0, xpeers, xworld, xrank, xpar, (xepoch << 8) | xpass, xerr, work_jac(ctx))));
         if ((rc2 = normalize_to(ctx, PH.Y + 64 * i0, cnt))) return rc2;
       } else {
         // one exchange for the X of all remaining steps: rank r's block is [step][position in slice]
@@ -730,26 +1082,28 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
         if ((rc2 = normalize_to(ctx, PH.Yall + 64 * s0 * nall, cn))) return rc2;
         PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_gather64<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(PH.Y + 64 * i0, PH.Yall, PH.lidx + i0, (int)cnt)));
       }
-      if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
-      PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1 + 320 * i0, PH.Y + 64 * i0, PH.rnd1 + 128 * i0, work_jac(ctx), (int)cnt)));
-      if ((rc2 = normalize_to(ctx, PH.cand + 128 * i0, 2 * cnt))) return rc2;
+      PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1 + 320 * i0, PH.Y + 64 * i0, PH.rnd1 + 128 * i0, pa_out_plain(PH.cand + 128 * i0), (int)cnt)));
       if (!sharded)
         PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
+      else if (p2p)  // the walk and the per-step exchange of the ranks' cryptogram sums are one kernel
+        PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_walk_shard<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3, xpeers, xworld, xrank, xpar, (xepoch << 8) | xpass, xerr)));
       return PA_OK;
     };
     int st[4];
     bool clean = true;
     long J = -1;
-    if (!sharded) {
+    if (!sharded || p2p) {
       // Until the first deciding step the keys are speculative, so they are computed for a short window of
       // steps that doubles while no junction shows up (with random bids it is step 0 or 1; only an auction
       // of all-zero bids goes through every window); after it, one pass takes all remaining steps.
       size_t done = 0, win = 2;
       while (done < c) {
         const size_t s1 = J < 0 ? (done + win < c ? done + win : c) : c;
+        ++xpass;
         if ((rc = run_steps(done, s1, J, J < 0 ? 1 : 0))) return rc;
         PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (p2p && (rc = xchg_check())) return rc;
         for (size_t i = done * m; i < s1 * m; ++i) clean &= after[i] == ictr[i] + 4;
         if (J < 0 && st[0]) J = st[3];
         done = (size_t)st[2];
@@ -814,19 +1168,23 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     if (!verify) PA_CUDA(ctx, cudaMemsetAsync(PH.r2ok, 1, T, ctx->stream));
     // the two groups are independent: the (small, latency-bound) stage-1 group runs on a lane beside stage 2
     const bool s1_on_lane = n1 && n2;
+    const size_t cor_item = ctx->corrupt.bidder < m ? ctx->corrupt.step * m + ctx->corrupt.bidder : T;
     if (s1_on_lane) {
       PA_CUDA(ctx, cudaEventRecord(ev_enc[0], ctx->stream));
       LaneScope ls(ctx, L_prove);
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[0], 0));
       if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
+      if (cor_item < n1 && (rc = dbg_corrupt(3, PH.proof + 672 * cor_item))) return rc;
       if (verify) PA_VREP(verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1));
       PA_CUDA(ctx, cudaEventRecord(ev_proved[0], ctx->stream));
     } else if (n1) {
       if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
+      if (cor_item < n1 && (rc = dbg_corrupt(3, PH.proof + 672 * cor_item))) return rc;
       if (verify) PA_VREP(verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1));
     }
     if (n2) {
       if ((rc = prove_dev<PA_S2>(ctx, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.pid + n1, PH.rnd2 + o_rnd, PH.proof + o_proof, n2))) return rc;
+      if (cor_item >= n1 && cor_item < T && (rc = dbg_corrupt(3, PH.proof + o_proof + 1344 * (cor_item - n1)))) return rc;
       if (verify) PA_VREP(verify_dev<PA_S2, 16>(ctx, PH.proof + o_proof, PH.stmt + o_stmt, PH.pid + n1, PH.r2ok + n1, n2));
     }
     if (s1_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_proved[0], 0));
@@ -844,14 +1202,39 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     }
     PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < T; ++i) clean &= after[i] == ictr[i] + (i < n1 ? 5 : 11);
-    if (!clean) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: a draw was rejected (probability 2^-128); rerun with schedule = PA_SEAL_STEP_MAJOR");
+    clean &= draws_clean;
     for (size_t i = 0; i < T; ++i) okv[0] &= r1ok[i] & r2ok[i];
+    for (size_t s2 = 0; s2 < c; ++s2)
+      if (r3[s2]) maxbid[0] |= (u64)1 << (c - s2 - 1);  // SEAL/bidder.cpp:1403, 64-bit shift (SURVEY.md Q2)
+    if (sharded) {
+      // all ranks must agree on whether a draw was rejected somewhere (then everybody runs the auction again step-major)
+      if (p2p) {
+        PA_LAUNCH(ctx, PA_K_VERDICT, (k_xchg_final<<<1, 32, 0, ctx->stream>>>(clean ? 1u : 0u, okv[0] ? 1u : 0u, maxbid[0], xpeers, xworld, xrank, xpar, (xepoch << 8) | 255u, xerr, d_xfinal)));
+        u64 fin[3] = {0, 0, 0};
+        PA_CUDA(ctx, cudaMemcpyAsync(fin, d_xfinal, sizeof fin, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = xchg_check())) return rc;
+        clean = fin[0] != 0;
+        if (job->ok_all) *job->ok_all = fin[1] != 0 ? 1 : 0;
+      } else {
+        u32 flag[32] = {clean ? 1u : 0u};
+        PA_CUDA(ctx, cudaMemcpyAsync(job->d_send, flag, sizeof flag, cudaMemcpyHostToDevice, ctx->stream));
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (job->allgather(job->user, 3) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (draw flags)");
+        std::vector<u32> all((size_t)xworld * 32);
+        PA_CUDA(ctx, cudaMemcpyAsync(all.data(), job->d_recv, all.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < xworld; ++r) clean &= all[(size_t)r * 32] != 0;
+      }
+    }
+    if (!clean) {
+      *rerun_step_major = true;
+      return PA_OK;
+    }
     if (job->out_r1_ok) memcpy(job->out_r1_ok, r1ok.data(), T);
     if (job->out_r2_ok) memcpy(job->out_r2_ok, r2ok.data(), T);
     for (size_t s2 = 0; s2 < c; ++s2) {
       if (job->out_r2_tag) memset(job->out_r2_tag + s2 * m, stage[s2], m);
       if (job->out_r3) job->out_r3[s2] = r3[s2] ? 1 : 0;
-      if (r3[s2]) maxbid[0] |= (u64)1 << (c - s2 - 1);  // SEAL/bidder.cpp:1403, 64-bit shift (SURVEY.md Q2)
     }
     if (job->max_bid) job->max_bid[0] = maxbid[0];
     if (job->ok) job->ok[0] = okv[0];
@@ -898,9 +1281,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
 
     // ---- main lane: x, r, X = g^x, R = g^r ------------------------------------------------
     PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.act, 4, B.rnd1, (int)ma)));
-    if ((rc = work_reserve(ctx, 2 * ma))) return rc;
-    PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * ma), PA_BLOCK, 0, ctx->stream>>>(B.rnd1, ctx->d_comb, work_jac(ctx), (int)ma)));
-    if ((rc = normalize_to(ctx, B.r1, 2 * ma, 2, 320))) return rc;
+    PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * ma), PA_BLOCK, 0, ctx->stream>>>(B.rnd1, ctx->d_comb, pa_outlay{B.r1, 2, 320, 1, 0}, (int)ma)));
     PA_CUDA(ctx, cudaEventRecord(ev_r1[par], ctx->stream));
 
     // ---- lane 1: the Schnorr proofs of X (x, v_X) and R (r, v_R) and their verification -------
@@ -908,6 +1289,7 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       LaneScope ls(ctx, L_pok);
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[par], 0));
       if ((rc = prove_dev<PA_POK>(ctx, B.r1, B.rnd1, nullptr, nullptr, B.pid, B.rnd1 + 64, B.r1 + 128, 2 * ma, LR2))) return rc;
+      if (A == 1 && ctx->corrupt.step == step && ctx->corrupt.bidder < ma && (rc = dbg_corrupt(2, B.r1 + 320 * ctx->corrupt.bidder))) return rc;
       if (verify) {
         PA_VREP(verify_dev<PA_POK, 1>(ctx, B.r1 + 128, B.r1, B.pid, B.pokv, 2 * ma, LR2));
         PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.pokv, nullptr, d_r1ok + step * m, (int)ma)));
@@ -925,20 +1307,24 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     } else {
       // all-gather the X_i of every slice, then every rank scans the whole auction
       const size_t nall = job->n[0];
-      PA_CUDA(ctx, cudaMemsetAsync(job->d_send, 0, (size_t)job->slice * 64, ctx->stream));
-      PA_CUDA(ctx, cudaMemcpy2DAsync(job->d_send, 64, B.r1, 320, 64, ma, cudaMemcpyDeviceToDevice, ctx->stream));
-      PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      if (job->allgather(job->user, 0) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (X)");
+      const unsigned char *gathered = job->d_recv;
+      unsigned char *send = p2p ? d_xsend : job->d_send;
+      PA_CUDA(ctx, cudaMemsetAsync(send, 0, (size_t)job->slice * 64, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpy2DAsync(send, 64, B.r1, 320, 64, ma, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (p2p) {
+        if ((rc = xchg_allgather(send, (size_t)job->slice * 64, &gathered))) return rc;
+      } else {
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (job->allgather(job->user, 0) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (X)");
+      }
       if ((rc = work_reserve(ctx, nall))) return rc;
-      PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<1, PA_SCAN_T, 0, ctx->stream>>>(job->d_recv, 64, nullptr, (int)nall, work_jac(ctx))));
+      PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<1, PA_SCAN_T, 0, ctx->stream>>>(gathered, 64, nullptr, (int)nall, work_jac(ctx))));
       if ((rc = normalize_to(ctx, B.Y, nall))) return rc;
       Yloc = B.Y + 64 * (size_t)job->lo;
     }
 
     // ---- main lane: cryptogram b, statements and draws of the OR proofs --------------------------
-    if ((rc = work_reserve(ctx, ma))) return rc;
-    PA_LAUNCH(ctx, PA_K_VAR, (k_seal_encode<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.act, B.pauc, d_bits, d_boff, (int)step, d_junc, d_prevbit, B.r1, Yloc, B.rnd1, B.ebit, work_jac(ctx), (int)ma)));
-    if ((rc = normalize_to(ctx, B.b, ma))) return rc;
+    PA_LAUNCH(ctx, PA_K_VAR, (k_seal_encode<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.act, B.pauc, d_bits, d_boff, (int)step, d_junc, d_prevbit, B.r1, Yloc, B.rnd1, B.ebit, pa_out_plain(B.b), (int)ma)));
     if (n1) {
       PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(1, B.g, B.act, d_boff, (int)step, B.b, B.r1, Yloc, B.rnd1, d_crec, d_rndc, d_prevpts, d_prevx, B.ebit, d_prevbit, B.stmt, B.sec, B.bi, B.bj, (int)n1)));
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.gslot, 5, B.rnd2, (int)n1)));
@@ -956,6 +1342,10 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[par], 0));
       if (n1 && (rc = prove_dev<PA_S1>(ctx, B.stmt, B.sec, B.bi, nullptr, B.gid, B.rnd2, B.proof, n1))) return rc;
       if (n2 && (rc = prove_dev<PA_S2>(ctx, B.stmt + o_stmt, B.sec + o_sec, B.bi + o_b, B.bj + o_b, B.gid + n1, B.rnd2 + o_rnd, B.proof + o_proof, n2))) return rc;
+      if (A == 1 && ctx->corrupt.step == step && ctx->corrupt.bidder < ma) {  // one auction: position = bidder, one group per step
+        unsigned char *rec = n1 ? B.proof + 672 * ctx->corrupt.bidder : B.proof + o_proof + 1344 * ctx->corrupt.bidder;
+        if ((rc = dbg_corrupt(3, rec))) return rc;
+      }
       if (want_proof) {  // group-compact: stage-1 members first, then stage-2 members
         if (n1) PA_CUDA(ctx, cudaMemcpyAsync(h_stage + off_pf + step * m * 1344, B.proof, n1 * 672, cudaMemcpyDeviceToHost, ctx->stream));
         if (n2) PA_CUDA(ctx, cudaMemcpyAsync(h_stage + off_pf + step * m * 1344 + o_proof, B.proof + o_proof, n2 * 1344, cudaMemcpyDeviceToHost, ctx->stream));
@@ -983,11 +1373,17 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
     if (!sharded) {
       PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<(unsigned)na, PA_SCAN_T, 0, ctx->stream>>>(B.b, 64, B.soff, (int)ma, B.isinf)));
     } else {
-      PA_CUDA(ctx, cudaMemsetAsync(job->d_send, 0, (size_t)job->slice * 64, ctx->stream));
-      PA_CUDA(ctx, cudaMemcpyAsync(job->d_send, B.b, ma * 64, cudaMemcpyDeviceToDevice, ctx->stream));
-      PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      if (job->allgather(job->user, 1) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (b)");
-      PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<1, PA_SCAN_T, 0, ctx->stream>>>(job->d_recv, 64, nullptr, (int)job->n[0], B.isinf)));
+      const unsigned char *gathered = job->d_recv;
+      unsigned char *send = p2p ? d_xsend : job->d_send;
+      PA_CUDA(ctx, cudaMemsetAsync(send, 0, (size_t)job->slice * 64, ctx->stream));
+      PA_CUDA(ctx, cudaMemcpyAsync(send, B.b, ma * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (p2p) {
+        if ((rc = xchg_allgather(send, (size_t)job->slice * 64, &gathered))) return rc;
+      } else {
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (job->allgather(job->user, 1) != 0) return pa_fail(ctx, PA_EINVAL, "pa_seal_run: all-gather callback failed (b)");
+      }
+      PA_LAUNCH(ctx, PA_K_SUMINF, (k_point_sum_is_inf<<<1, PA_SCAN_T, 0, ctx->stream>>>(gathered, 64, nullptr, (int)job->n[0], B.isinf)));
     }
     PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_update<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.act, B.pseg, B.pauc, B.isinf, d_bits, d_boff, (int)step, B.r1, Yloc, B.b, B.rnd1, d_prevpts, d_prevx, d_prevbit, d_junc, (int)ma)));
     std::vector<int> isinf(na);
@@ -1032,6 +1428,13 @@ extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   for (size_t a = 0; a < A; ++a) {
     if (job->max_bid) job->max_bid[a] = maxbid[a];
     if (job->ok) job->ok[a] = okv[a];
+  }
+  if (p2p) {  // the verdict of all ranks
+    PA_LAUNCH(ctx, PA_K_VERDICT, (k_xchg_final<<<1, 32, 0, ctx->stream>>>(1u, okv[0] ? 1u : 0u, maxbid[0], xpeers, xworld, xrank, xpar, (xepoch << 8) | 254u, xerr, d_xfinal)));
+    u64 fin[3] = {0, 0, 0};
+    PA_CUDA(ctx, cudaMemcpyAsync(fin, d_xfinal, sizeof fin, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = xchg_check())) return rc;
+    if (job->ok_all) *job->ok_all = fin[1] != 0 ? 1 : 0;
   }
   return PA_OK;
 }

@@ -144,10 +144,34 @@ PA_HD void challenge_hash(sc &h, const unsigned char *const *pts, int k, u64 id)
 
 // PA deterministic draw stream (include/pa_engine.h, "seeded randomness"):
 //   draw(seed, stream, ctr) = SHA-256("PAv1" || LE64 seed || LE64 stream || LE64 ctr)
+// With a 32-byte entropy key installed (pa_ctx_set_entropy: what a deployment uses, the seeded
+// form is for tests and benchmarks) the draw is
+//   SHA-256("PAv2" || key[32] || LE64 seed || LE64 stream || LE64 ctr)
+// so that nothing derivable from a published transcript reproduces a party's secrets.
+struct pa_rng_cfg {
+  u32 keyed;        // 1: key[] is mixed into every draw
+  u32 reject_bits;  // TEST HOOK: a draw whose top `reject_bits` bits are all ones is redrawn, as if it were >= the
+                    // group order (probability 2^-reject_bits instead of 2^-128), to exercise the redraw paths
+  u32 key[8];
+};
+#if defined(__CUDACC__)
+__constant__ pa_rng_cfg pa_rng_config;  // zero: the seeded test stream
+#endif
+
 PA_HD void pa_stream_draw(u32 digest[8], u64 seed, u64 stream, u64 ctr) {
   sha256_state s;
   sha256_init(s);
-  sha256_put(s, 'P'); sha256_put(s, 'A'); sha256_put(s, 'v'); sha256_put(s, '1');
+  sha256_put(s, 'P'); sha256_put(s, 'A'); sha256_put(s, 'v');
+#if defined(__CUDA_ARCH__)
+  if (pa_rng_config.keyed) {
+    sha256_put(s, '2');
+    for (int w = 0; w < 8; ++w)
+      for (int b = 3; b >= 0; --b) sha256_put(s, (pa_rng_config.key[w] >> (8 * b)) & 0xFFu);
+  } else
+#endif
+  {
+    sha256_put(s, '1');
+  }
   for (int i = 0; i < 8; ++i) sha256_put(s, (u32)(seed >> (8 * i)) & 0xFFu);
   for (int i = 0; i < 8; ++i) sha256_put(s, (u32)(stream >> (8 * i)) & 0xFFu);
   for (int i = 0; i < 8; ++i) sha256_put(s, (u32)(ctr >> (8 * i)) & 0xFFu);
@@ -160,6 +184,11 @@ PA_HD void pa_stream_rand_range(sc &r, u64 seed, u64 stream, u64 &ctr) {
     pa_stream_draw(d, seed, stream, ctr++);
 #pragma unroll
     for (int i = 0; i < 8; ++i) r.v[i] = d[7 - i];
-    if (!sc_ge_n(r.v)) return;
+    bool reject = sc_ge_n(r.v);
+#if defined(__CUDA_ARCH__)
+    const u32 rb = pa_rng_config.reject_bits;
+    if (rb) reject |= (r.v[7] >> (32 - rb)) == ((1u << rb) - 1u);
+#endif
+    if (!reject) return;
   }
 }

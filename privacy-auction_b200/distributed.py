@@ -13,19 +13,50 @@ import torch
 import torch.distributed as dist
 
 
-def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False):
+def connect_peer_windows(engine):
+    """Create this rank's peer exchange window and map everybody else's (CUDA IPC over NVLink): after this the
+    kernels of a sharded auction exchange their per-step sums by writing into each other's HBM.  The 64-byte
+    handles travel through torch.distributed once; nothing else does afterwards."""
+    if engine.xchg_world:
+        return
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = engine.xchg_create()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    engine.xchg_connect(handles, rank)
+    dist.barrier()
+
+
+def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False, transport="auto", schedule=0):
     """Run ONE SEAL auction of n bidders sharded over the ranks of the default process group.
     Every rank passes the same (seed, n, c, bids_all).  Returns the engine's result dict for
-    the local slice plus 'ok_all' (MIN over ranks) and 'slice' = (lo, hi)."""
+    the local slice plus 'ok_all' (AND over ranks), 'max_bid_all' and 'slice' = (lo, hi).
+    transport: "xchg" = kernels exchange through the peer windows (connect_peer_windows), no host round
+    trip per step; "nccl" = an NCCL all-gather called back from the engine per exchange; "auto" = xchg when
+    the windows are connected."""
     rank, world = dist.get_rank(), dist.get_world_size()
     slice_ = (n + world - 1) // world
     lo, hi = min(n, rank * slice_), min(n, (rank + 1) * slice_)
     dev = torch.device("cuda", torch.cuda.current_device())
+    if transport == "auto":
+        transport = "xchg" if engine.xchg_world == world else "nccl"
+    if transport == "xchg":
+        assert engine.xchg_world == world, "connect_peer_windows(engine) first"
+        if hi > lo:
+            res = engine.seal_run(seed, [n], [c], list(bids_all[lo:hi]), verify=verify, sections=sections, schedule=schedule,
+                                  shard=dict(lo=lo, hi=hi, slice=slice_, use_xchg=True))
+            res["max_bid_all"] = res["max_bid"][0]   # every rank derives it from the same all-rank sums
+        else:   # more ranks than bidders: this rank owns nobody and stays out of the exchanges
+            engine.xchg_skip()
+            res = {"max_bid": [0], "ok": [True], "ok_all": None, "max_bid_all": None}
+        res["slice"] = (lo, hi)
+        res["transport"] = "xchg"
+        return res
     cap = max(c * slice_ * 64, 128)
     send = torch.zeros(cap, dtype=torch.uint8, device=dev)
     recv = torch.empty(world * cap, dtype=torch.uint8, device=dev)
     # the phase-major schedule needs every rank to own bidders (all ranks take the same decisions)
-    phase_major = (world - 1) * slice_ < n
+    phase_major = (world - 1) * slice_ < n and schedule != 1
     sizes = {0: slice_ * 64, 1: slice_ * 64, 2: c * slice_ * 64, 3: 128}
 
     def allgather(which):
@@ -37,7 +68,7 @@ def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False):
         return 0
 
     if hi > lo:
-        res = engine.seal_run(seed, [n], [c], list(bids_all[lo:hi]), verify=verify, sections=sections,
+        res = engine.seal_run(seed, [n], [c], list(bids_all[lo:hi]), verify=verify, sections=sections, schedule=1 if not phase_major else schedule,
                               shard=dict(lo=lo, hi=hi, slice=slice_, d_send=send.data_ptr(), d_recv=recv.data_ptr(), allgather=allgather,
                                          xchg_bytes=cap if phase_major else 0))
     else:  # more ranks than bidders: still take part in the exchanges
@@ -51,4 +82,5 @@ def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False):
     res["ok_all"] = bool(ok.item())
     res["max_bid_all"] = int(mb.item())
     res["slice"] = (lo, hi)
+    res["transport"] = "nccl"
     return res

@@ -90,6 +90,13 @@ SIGNATURES = {
     "pa_rng_fill256_dev": (ctypes.c_int, [_ctx, ctypes.c_uint64, _vp, _vp, _sz, _vp, _sz]),
     "pa_ccs22_setup_hash": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _sz]),
     "pa_ccs22_setup_hash_dev": (ctypes.c_int, [_ctx, _vp, _sz, _vp, _sz]),
+    "pa_ctx_set_entropy": (ctypes.c_int, [_ctx, _vp]),
+    "pa_debug_set": (ctypes.c_int, [_ctx, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]),
+    "pa_ctx_reruns": (ctypes.c_uint64, [_ctx]),
+    "pa_xchg_create": (ctypes.c_int, [_ctx, _vp]),
+    "pa_xchg_connect": (ctypes.c_int, [_ctx, _vp, ctypes.c_int, ctypes.c_int]),
+    "pa_xchg_skip": (ctypes.c_int, [_ctx]),
+    "pa_xchg_close": (ctypes.c_int, [_ctx]),
     "pa_profile_begin": (ctypes.c_int, [_ctx]),
     "pa_profile_end": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.POINTER(_sz)]),
 }
@@ -114,6 +121,7 @@ class SealJob(ctypes.Structure):
         ("out_r1_ok", ctypes.c_void_p), ("out_r2_tag", ctypes.c_void_p), ("out_r2_b", ctypes.c_void_p),
         ("out_r2_proof", ctypes.c_void_p), ("out_r2_ok", ctypes.c_void_p), ("out_r3", ctypes.c_void_p),
         ("schedule", ctypes.c_int), ("xchg_bytes", ctypes.c_size_t),
+        ("use_xchg", ctypes.c_int), ("ok_all", ctypes.c_void_p),
     ]
 
 
@@ -159,14 +167,53 @@ def _buf(b):
 class Engine:
     """One engine context on one GPU (pa_ctx)."""
 
-    def __init__(self, device=0, lib=None):
+    def __init__(self, device=0, lib=None, entropy=None):
+        """entropy: None = the seeded draw stream (tests, benchmarks: reproducible); "os" = a fresh 32-byte key
+        from the operating system mixed into every draw (what a deployment uses); or 32 bytes."""
         self.lib = lib or load_library()
         self.ctx = _ctx()
+        self.xchg_world = 0
         rc = self.lib.pa_ctx_create(ctypes.byref(self.ctx), device)
         if rc != PA_OK:
             msg = self.lib.pa_last_error(None)
             self.ctx = None
             raise EngineError(f"pa_ctx_create failed ({rc}): {msg.decode() if msg else ''}")
+        if entropy is not None:
+            self.set_entropy(os.urandom(32) if entropy == "os" else entropy)
+
+    def set_entropy(self, key32):
+        """pa_ctx_set_entropy: 32 secret bytes mixed into every draw; None = back to the seeded test stream."""
+        if key32 is None:
+            self._check(self.lib.pa_ctx_set_entropy(self.ctx, None))
+            return
+        assert len(key32) == 32
+        p, keep = _buf(bytes(key32))
+        self._check(self.lib.pa_ctx_set_entropy(self.ctx, p))
+
+    def debug_set(self, what, a=0, b=0, c=0):
+        """pa_debug_set (test hooks): what = 1 reject bits (a), 2 corrupt (a = section, b = step << 32 | bidder, c = offset)."""
+        self._check(self.lib.pa_debug_set(self.ctx, what, a, b, c))
+
+    @property
+    def reruns(self):
+        return self.lib.pa_ctx_reruns(self.ctx)
+
+    # -- peer exchange window (one process per GPU) -----------------------------------
+    def xchg_create(self):
+        """pa_xchg_create: allocate this rank's window, return its 64-byte IPC handle."""
+        h = (ctypes.c_uint8 * 64)()
+        self._check(self.lib.pa_xchg_create(self.ctx, ctypes.addressof(h)))
+        return bytes(h)
+
+    def xchg_connect(self, handles, rank):
+        """pa_xchg_connect: handles = every rank's handle in rank order."""
+        blob = b"".join(handles)
+        p, keep = _buf(blob)
+        self._check(self.lib.pa_xchg_connect(self.ctx, p, len(handles), rank))
+        self.xchg_world, self.xchg_rank = len(handles), rank
+
+    def xchg_skip(self):
+        self._check(self.lib.pa_xchg_skip(self.ctx))
 
     def close(self):
         if self.ctx:
@@ -406,13 +453,18 @@ class Engine:
         job.schedule = schedule   # 0 auto, 1 step-major, 2 phase-major (one unsharded auction)
         job.max_bid, job.ok = ctypes.addressof(max_bid), ctypes.addressof(ok)
         cb = None
+        ok_all = ctypes.c_uint8(1)
         if shard is not None:
-            fn = shard["allgather"]
-            cb = ALLGATHER_FN(lambda user, which: int(fn(which) or 0))
             job.lo, job.hi, job.slice = shard["lo"], shard["hi"], shard["slice"]
-            job.allgather = cb
-            job.d_send, job.d_recv = shard["d_send"], shard["d_recv"]
-            job.xchg_bytes = shard.get("xchg_bytes", 0)
+            if shard.get("use_xchg"):   # kernels exchange through the peer window: no callback, no buffers
+                job.use_xchg = 1
+                job.ok_all = ctypes.addressof(ok_all)
+            else:
+                fn = shard["allgather"]
+                cb = ALLGATHER_FN(lambda user, which: int(fn(which) or 0))
+                job.allgather = cb
+                job.d_send, job.d_recv = shard["d_send"], shard["d_recv"]
+                job.xchg_bytes = shard.get("xchg_bytes", 0)
         out = {}
         if sections:
             cmax = max(c)
@@ -430,6 +482,8 @@ class Engine:
                 out[name] = buf
         self._check(self.lib.pa_seal_run(self.ctx, ctypes.byref(job)))
         res = {"max_bid": list(max_bid), "ok": [bool(v) for v in ok]}
+        if shard is not None and shard.get("use_xchg"):
+            res["ok_all"] = bool(ok_all.value)
         for name, buf in out.items():
             res[name[4:]] = bytes(buf)
         return res

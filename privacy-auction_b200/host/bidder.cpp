@@ -18,8 +18,7 @@ Bidder::Bidder(size_t id, size_t n, size_t c) : id_(id), c_(c), n_(n) {
   assert(c <= C_MAX);
   // uniform c-bit bid; 64-bit arithmetic, so c = 32 does not degenerate to 0 as the
   // reference's `(1 << c) - 1` on int does
-  std::mt19937_64 gen(config().seed * 0x9E3779B97F4A7C15ull + id + 1);
-  init((size_t)(gen() & ((c >= 64 ? ~0ull : (1ull << c)) - 1)));
+  init((size_t)(bid_entropy(id + 1) & ((c >= 64 ? ~0ull : (1ull << c)) - 1)));
 }
 
 Bidder::Bidder(size_t id, size_t n, size_t c, size_t bid) : id_(id), c_(c), n_(n) {

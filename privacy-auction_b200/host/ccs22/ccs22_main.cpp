@@ -30,7 +30,7 @@ int main(int argc, char *argv[]) {
   long evArg = -1;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
-    if (a == "--seed" && i + 1 < argc) pa_host::config().seed = std::stoull(argv[++i]);
+    if (a == "--seed" && i + 1 < argc) pa_host::config().seed = std::stoull(argv[++i]), pa_host::config().seeded = true;
     else if (a == "--bids" && i + 1 < argc) bidarg = argv[++i];
     else if (a == "--evaluator" && i + 1 < argc) evArg = std::stol(argv[++i]);
     else if (a == "--transcript" && i + 1 < argc) transcript = argv[++i];
@@ -57,8 +57,7 @@ int main(int argc, char *argv[]) {
 
   BulletinBoard bb(n, c);
   // =============== Initialization phase ============
-  std::mt19937_64 gen(pa_host::config().seed ^ 0xE7A1ull);
-  size_t evaluatorId = evArg >= 0 ? (size_t)evArg : (size_t)(gen() % n);
+  size_t evaluatorId = evArg >= 0 ? (size_t)evArg : (size_t)(pa_host::bid_entropy(0xE7A1ull) % n);
   auto pos = [evaluatorId](size_t i) {
     assert(i != evaluatorId);
     return i < evaluatorId ? i : i - 1;
@@ -82,7 +81,7 @@ int main(int argc, char *argv[]) {
   PRINT_MESSAGE("Finished initialization.\nMax bid: " << maxBid << ", Max bid (in binary): "
                                                       << std::bitset<C_MAX>(maxBid).to_string().substr(C_MAX - c));
   put("PACCS22T", 8);
-  put_u64(n), put_u64(c), put_u64(pa_host::config().seed), put_u64(evaluatorId);
+  put_u64(n), put_u64(c), put_u64(pa_host::config().seeded ? pa_host::config().seed : 0), put_u64(evaluatorId);
   for (size_t b : bids) put_u64(b);
   put(&bb.getPubParams().g1, 64);
   put(&bb.getPubParams().h, 64);

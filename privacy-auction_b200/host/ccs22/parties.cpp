@@ -121,8 +121,7 @@ size_t BulletinBoard::getd() const {
 
 // ---------------------------------------------------------------- Bidder
 Bidder::Bidder(size_t id, size_t n, size_t c, const PubParams &p) : id_(id), c_(c), n_(n), pp(p) {
-  std::mt19937_64 gen(config().seed * 0x9E3779B97F4A7C15ull + id + 1);
-  init((size_t)(gen() & ((1ull << c) - 1)));
+  init((size_t)(bid_entropy(id + 1) & ((1ull << c) - 1)));
 }
 Bidder::Bidder(size_t id, size_t n, size_t c, const PubParams &p, size_t bid) : id_(id), c_(c), n_(n), pp(p) { init(bid); }
 

@@ -2,6 +2,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <random>
+#include <sys/random.h>
 
 namespace pa_host {
 
@@ -18,8 +20,26 @@ pa_ctx *engine() {
       fprintf(stderr, "pa_ctx_create failed (%d): %s\n", rc, pa_last_error(nullptr));
       exit(1);
     }
+    if (!config().seeded) {  // a deployment: key the draw stream from the OS entropy pool; never written anywhere
+      uint8_t key[32];
+      if (getrandom(key, sizeof key, 0) != (ssize_t)sizeof key) {
+        fprintf(stderr, "getrandom failed: refusing to run with predictable randomness (use --seed for a test run)\n");
+        exit(1);
+      }
+      check(pa_ctx_set_entropy(ctx, key), "pa_ctx_set_entropy");
+      for (auto &b : key) b = 0;
+    }
   }
   return ctx;
+}
+
+uint64_t bid_entropy(uint64_t salt) {
+  if (config().seeded) {
+    std::mt19937_64 gen(config().seed * 0x9E3779B97F4A7C15ull + salt);
+    return gen();
+  }
+  std::random_device rd;  // SEAL/bidder.cpp:27
+  return ((uint64_t)rd() << 32) | rd();
 }
 
 void check(int rc, const char *what) {

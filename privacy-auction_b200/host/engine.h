@@ -15,9 +15,17 @@
 namespace pa_host {
 
 struct Config {
-  uint64_t seed = 1;  // seed of the PA stream; bidder j draws from stream (seed, j)
+  // seeded = false (the default): every draw is keyed with 32 bytes from the operating system's entropy pool
+  // (pa_ctx_set_entropy) and bids come from std::random_device, as the reference draws from OpenSSL's DRBG and
+  // std::random_device (SEAL/bidder.cpp:27, :97) - nothing in a transcript reproduces a secret.
+  // seeded = true (--seed S on the command lines; tests, benchmarks): bidder j draws from PA stream (seed, j),
+  // reproducible and therefore NOT private.
+  bool seeded = false;
+  uint64_t seed = 1;
   int device = 0;
 };
+// a 64-bit value for the parties' bids / the evaluator's id: from the seed when seeded, else std::random_device
+uint64_t bid_entropy(uint64_t salt);
 Config &config();
 
 pa_ctx *engine();  // created on first use

@@ -4,7 +4,7 @@
 // phases run in the same order, the same summary block, exit code 0 when every
 // verification held and every bidder computed the true maximum bid, 1 otherwise.
 // Options added here (the reference is unseeded and never serialises anything):
-//   --seed S          seed of the PA draw stream (default 1)
+//   --seed S          TEST RUN: seeded, reproducible PA draw stream (default: a 32-byte key from getrandom(2), never published)
 //   --bids a,b,...    explicit bids instead of pseudo-random ones
 //   --transcript F    write the PASEALT1 transcript of everything published
 //   --no-verify       skip the verify* calls (ENABLE_VERIFICATION off)
@@ -41,7 +41,7 @@ int main(int argc, char *argv[]) {
   bool verify = true, profile = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
-    if (a == "--seed" && i + 1 < argc) pa_host::config().seed = std::stoull(argv[++i]);
+    if (a == "--seed" && i + 1 < argc) pa_host::config().seed = std::stoull(argv[++i]), pa_host::config().seeded = true;
     else if (a == "--bids" && i + 1 < argc) bidarg = argv[++i];
     else if (a == "--transcript" && i + 1 < argc) transcript = argv[++i];
     else if (a == "--device" && i + 1 < argc) pa_host::config().device = std::stoi(argv[++i]);
@@ -81,7 +81,7 @@ int main(int argc, char *argv[]) {
   PRINT_MESSAGE("Finished initialization.\nMax bid: " << maxBid << ", Max bid (in binary): "
                                                       << std::bitset<C_MAX>(maxBid).to_string().substr(C_MAX - c));
   put("PASEALT1", 8);
-  put_u64(n), put_u64(c), put_u64(pa_host::config().seed);
+  put_u64(n), put_u64(c), put_u64(pa_host::config().seeded ? pa_host::config().seed : 0);  // the seed only exists in a test run
   for (size_t b : bids) put_u64(b);
 
   if (profile) pa_profile_begin(pa_host::engine());

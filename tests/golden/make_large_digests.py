@@ -109,9 +109,22 @@ def run_config4(name, spec, world, port):
     # section digests, to localise a mismatch: the bytes of each step as they appear in the transcript
     t = seal_flow.parse_transcript(out)
     d["commit_sha256"] = hashlib.sha256(b"".join(b"".join(row) for row in t["commit"])).hexdigest()
+    # per bidder: everything that bidder published, in transcript order - lets the ranks of a sharded run check
+    # their own slices (bench.py) without moving 78 MB of records to one place
+    d["bidder_sha256"] = [bidder_digest(t, j) for j in range(n)]
     d["step_sha256"] = [hashlib.sha256(b"".join(s["r1"]) + b"".join(int(tag).to_bytes(4, "little") + b + pr for tag, b, pr in s["r2"])).hexdigest()
                         for s in t["steps"]]
     return d
+
+
+def bidder_digest(t, j):
+    """SHA-256 of what bidder j published: its c commitment records, then per step its round-one record,
+    LE32 stage tag, cryptogram and proof (t = seal_flow.parse_transcript(...))."""
+    h = hashlib.sha256(b"".join(t["commit"][j]))
+    for s in t["steps"]:
+        tag, b, pr = s["r2"][j]
+        h.update(s["r1"][j] + int(tag).to_bytes(4, "little") + b + pr)
+    return h.hexdigest()
 
 
 def _one5(args):

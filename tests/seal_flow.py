@@ -176,6 +176,16 @@ class SealFlow:
         return out
 
 
+def _per_verifier(okl):
+    """verifier j's byte = AND of the once-computed verdicts of every prover i != j"""
+    bad = [i for i, v in enumerate(okl) if not v]
+    if not bad:
+        return bytes([1] * len(okl))
+    if len(bad) == 1:   # only the failing prover itself still sees everybody else pass
+        return bytes(1 if j == bad[0] else 0 for j in range(len(okl)))
+    return bytes(len(okl))
+
+
 def assemble_transcript(n, c, seed, bids, section_list):
     """PASEALT1 from the sections of one or several processes (each holding a subset of the bidders)."""
     def merged(key, step=None):
@@ -187,7 +197,7 @@ def assemble_transcript(n, c, seed, bids, section_list):
     def per_verifier(ok):
         # reference: verifier j checks every i != j (SEAL/bidder.cpp:1178-1190); verifier j's answer is
         # the AND over i != j of the once-computed verdicts
-        return bytes(1 if all(ok[i] for i in range(n) if i != j) else 0 for j in range(n))
+        return _per_verifier([ok[i] for i in range(n)])
 
     out = bytearray(b"PASEALT1" + struct.pack("<QQQ", n, c, seed))
     for bid in bids:
@@ -265,8 +275,7 @@ def sections_to_transcripts(seed, n, c, bids, res):
         for _ in range(n[a]):
             boff.append(boff[-1] + c[a])
 
-    def per_verifier(okl):
-        return bytes(1 if all(okl[i] for i in range(len(okl)) if i != j) else 0 for j in range(len(okl)))
+    per_verifier = _per_verifier
 
     outs = []
     for a in range(A):

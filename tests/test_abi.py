@@ -73,4 +73,4 @@ def test_struct_layouts_match_the_binding(pa):
     assert lib.pa_abi_sizeof(0) == ctypes.sizeof(eng.SealJob)
     assert lib.pa_abi_sizeof(1) == ctypes.sizeof(eng.Ccs22Job)
     assert lib.pa_abi_sizeof(2) == ctypes.sizeof(eng.KernelStat)
-    assert lib.pa_abi_sizeof(9) == 0 and lib.pa_abi_version() == 2
+    assert lib.pa_abi_sizeof(9) == 0 and lib.pa_abi_version() == 3

@@ -75,3 +75,20 @@ def test_ccs22_cli_config2_and_sweep():
         n, c = rnd.randint(1, 10), rnd.randint(1, 16)
         r = subprocess.run([CCS22, str(n), str(c), "--seed", str(rnd.randrange(1 << 30)), "--quiet"], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, (n, c, r.stderr[-1500:])
+
+
+def test_cli_without_seed_uses_os_entropy(tmp_path):
+    """No --seed: the draw stream is keyed from getrandom(2) and bids come from std::random_device, like the
+    reference (SEAL/bidder.cpp:27, :97): two runs publish different records, both verify, and the transcript
+    header carries no seed."""
+    outs = []
+    for k in range(2):
+        out = tmp_path / f"t{k}.bin"
+        r = subprocess.run([SEAL, "3", "4", "--bids", "11,6,13", "--transcript", str(out), "--quiet"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(out.read_bytes())
+    t0, t1 = (seal_flow.parse_transcript(o) for o in outs)
+    assert t0["seed"] == 0 and t1["seed"] == 0
+    assert t0["max_bid"] == t1["max_bid"] == [13, 13, 13]
+    assert t0["commit"] != t1["commit"]
+    assert seal_flow.transcript_ok(outs[0]) and seal_flow.transcript_ok(outs[1])
