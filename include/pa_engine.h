@@ -395,11 +395,16 @@ int pa_profile_begin(pa_ctx *ctx);
 int pa_profile_end(pa_ctx *ctx, pa_kernel_stat *out, size_t cap, size_t *count);
 
 /*
- * Register-only integer-pipe microbenchmark (SURVEY.md §8d asks for the IMAD
- * peak to be measured on the box).  out[0] = 32-bit IMAD / s, out[1] = 32x32+64
- * IMAD.WIDE / s, out[2] = field multiplications / s, out[3] = field squarings / s,
- * all whole-GPU, timed with CUDA events on the context's stream. */
-int pa_measure_int_peak(pa_ctx *ctx, double out[4]);
+ * Register-only integer-pipe microbenchmarks (SURVEY.md section 8d asks for the IMAD peak to be measured on
+ * the box), whole-GPU rates timed with CUDA events on the context's stream:
+ *   out[0]  32-bit IMAD / s
+ *   out[1]  32 x 32 + 64 multiply-adds / s in the shape of the field multiplier: chains of four linked by
+ *           the carry flag (mad.lo.cc / madc.hi.cc -> IMAD.WIDE.U32.X), nothing else in the loop
+ *   out[2]  field multiplications / s      out[3]  field squarings / s
+ *   out[4]  32 x 32 + 64 multiply-adds / s without carry links (mad.wide.u32; ptxas turns each into an
+ *           IMAD.WIDE.U32 with a zero addend plus a 64-bit addition on the other pipe)
+ *   out[5]  reserved (0) */
+int pa_measure_int_peak(pa_ctx *ctx, double out[6]);
 
 #ifdef __cplusplus
 }

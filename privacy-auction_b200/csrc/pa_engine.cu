@@ -382,11 +382,11 @@ static u32 *work_prefix(pa_ctx *ctx, size_t n) { return (u32 *)(ctx->d_work + n 
 
 static int normalize_to(pa_ctx *ctx, unsigned char *d_out, size_t n, int nper = 1, size_t stride = 64, int inner = 1,
                         size_t stride_in = 0) {
-  // the inversion is shared by a warp whatever happens; a thread takes several points only when that
-  // still leaves every SM a few blocks (the chain of a thread's points is sequential)
-  size_t per = n / 65536;
+  // points per thread: share the ~270-multiplication inversion among up to 16 points as soon as
+  // that still leaves >= 16 k threads (one lone warp per SM sub-partition is latency-bound anyway)
+  size_t per = n / 16384;
   if (per < 1) per = 1;
-  if (per > 8) per = 8;
+  if (per > 16) per = 16;
   size_t T = (n + per - 1) / per;
   PA_LAUNCH(ctx, PA_K_NORMALIZE, k_normalize<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>(work_jac(ctx), work_prefix(ctx, n), pa_outlay{d_out, nper, stride, inner, stride_in}, (int)n, (int)T));
   return PA_OK;
@@ -401,8 +401,10 @@ int pa_fixed_base_mul_dev(pa_ctx *ctx, const uint8_t *d_scalars, uint8_t *d_out,
   PA_ARGCHECK(ctx, ctx && (n == 0 || (d_scalars && d_out)) && n < (1u << 30));
   PA_ARGCHECK(ctx, aligned16(d_scalars) && aligned16(d_out));
   if (n == 0) return PA_OK;
-  PA_LAUNCH(ctx, PA_K_FIXED, k_fixed_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_scalars, ctx->d_comb, pa_out_plain(d_out), (int)n));
-  return PA_OK;
+  int rc = work_reserve(ctx, n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_FIXED, k_fixed_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_scalars, ctx->d_comb, work_jac(ctx), (int)n));
+  return normalize_to(ctx, d_out, n);
 }
 
 int pa_var_base_mul_dev(pa_ctx *ctx, const uint8_t *d_points, const uint8_t *d_scalars, uint8_t *d_out, size_t n) {
@@ -410,8 +412,10 @@ int pa_var_base_mul_dev(pa_ctx *ctx, const uint8_t *d_points, const uint8_t *d_s
   PA_ARGCHECK(ctx, ctx && (n == 0 || (d_points && d_scalars && d_out)) && n < (1u << 30));
   PA_ARGCHECK(ctx, aligned16(d_points) && aligned16(d_scalars) && aligned16(d_out));
   if (n == 0) return PA_OK;
-  PA_LAUNCH(ctx, PA_K_VAR, k_var_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_points, d_scalars, pa_out_plain(d_out), (int)n));
-  return PA_OK;
+  int rc = work_reserve(ctx, n);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_VAR, k_var_base<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(d_points, d_scalars, work_jac(ctx), (int)n));
+  return normalize_to(ctx, d_out, n);
 }
 
 int pa_double_mul_dev(pa_ctx *ctx, const uint8_t *d_a, const uint8_t *d_points, const uint8_t *d_b, uint8_t *d_out,
@@ -688,7 +692,7 @@ int pa_profile_end(pa_ctx *ctx, pa_kernel_stat *out, size_t cap, size_t *count) 
   return PA_OK;
 }
 
-int pa_measure_int_peak(pa_ctx *ctx, double out[4]) {
+int pa_measure_int_peak(pa_ctx *ctx, double out[6]) {
   PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && out);
   int rc = stage_reserve(ctx, 4096);
@@ -697,13 +701,15 @@ int pa_measure_int_peak(pa_ctx *ctx, double out[4]) {
   PA_CUDA(ctx, cudaEventCreate(&e0));
   PA_CUDA(ctx, cudaEventCreate(&e1));
   const int blocks = 148 * 8, threads = 256;
-  for (int which = 0; which < 4; ++which) {
-    int iters = which < 2 ? 4096 : 2048;
+  out[5] = 0;
+  for (int which = 0; which < 5; ++which) {
+    int iters = which < 2 || which == 4 ? 4096 : 2048;
     double best = 0;
     for (int rep = 0; rep < 4; ++rep) {
       PA_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
       if (which == 0) k_peak_imad<<<blocks, threads, 0, ctx->stream>>>((u32 *)ctx->d_stage, iters, 3u + rep, 7u);
-      if (which == 1) k_peak_imad_wide<<<blocks, threads, 0, ctx->stream>>>((u64 *)ctx->d_stage, iters, 3u + rep);
+      if (which == 1) k_peak_imad_wide<<<blocks, threads, 0, ctx->stream>>>((u64 *)ctx->d_stage, iters, 3u + rep, 1);
+      if (which == 4) k_peak_imad_wide<<<blocks, threads, 0, ctx->stream>>>((u64 *)ctx->d_stage, iters, 3u + rep, 0);
       if (which == 2) k_peak_fe<<<blocks, threads, 0, ctx->stream>>>((u32 *)ctx->d_stage, iters, 0);
       if (which == 3) k_peak_fe<<<blocks, threads, 0, ctx->stream>>>((u32 *)ctx->d_stage, iters, 1);
       ctx->launches++;
@@ -712,7 +718,7 @@ int pa_measure_int_peak(pa_ctx *ctx, double out[4]) {
       PA_CUDA(ctx, cudaEventSynchronize(e1));
       float ms = 0;
       PA_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
-      double ops = (double)blocks * threads * iters * (which < 2 ? 64.0 : 2.0);
+      double ops = (double)blocks * threads * iters * (which < 2 || which == 4 ? 64.0 : 2.0);
       double rate = ops / (ms * 1e-3);
       if (rep > 0 && rate > best) best = rate;  // first repetition is warm-up
     }
@@ -784,8 +790,10 @@ int prove_dev(pa_ctx *ctx, const unsigned char *stmts, const unsigned char *secr
   typedef proof_kind<KIND> K;
   if (n == 0) return PA_OK;
   size_t m = n * K::NEPS;
-  // every operation's thread writes its eps straight into the proof record (one inversion per warp)
-  PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, pa_outlay{proofs, K::NEPS, L.proof, L.inner, L.proof_in}, (int)n, L)));
+  int rc = work_reserve(ctx, m);
+  if (rc) return rc;
+  PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n, L)));
+  if ((rc = normalize_to(ctx, proofs, m, K::NEPS, L.proof, L.inner, L.proof_in))) return rc;
   PA_LAUNCH(ctx, PA_K_PRESPOND + KIND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, secrets, rnd, b0, b1, (int)n, L)));
   return PA_OK;
 }

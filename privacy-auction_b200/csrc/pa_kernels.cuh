@@ -87,56 +87,15 @@ PA_D void ld_jac(jac &r, const u32 *src) {
   ld_fe(r.Z, src + 16);
 }
 
-// ---- Jacobian -> 64-byte affine: one field inversion per WARP ---------------------------------
-// Montgomery's trick across the 32 lanes: inclusive prefix and suffix products of the lanes' values by
-// shuffles (5 + 5 multiplications), ONE inversion of the warp's total (the ~270-multiplication chain is
-// the same instructions whether one lane or 32 need it), then
-//   1 / a_lane = (1 / total) * prefix_(lane-1) * suffix_(lane+1).
-// The reference pays a full inversion per point inside EC_POINT_point2oct (25 us each).
-PA_D void fe_shfl_up(fe &r, const fe &a, int d) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
-}
-PA_D void fe_shfl_down(fe &r, const fe &a, int d) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
-}
-PA_D void fe_shfl(fe &r, const fe &a, int src) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
-}
-PA_D void fe_select(fe &r, bool c, const fe &a, const fe &b) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r.v[i] = c ? a.v[i] : b.v[i];
-}
-// r = 1 / a in every lane; a != 0 in every lane (lanes with nothing to invert pass 1).
-// Collective: all 32 lanes of the warp must call it.
-PA_D void warp_inverse(fe &r, const fe &a) {
-  const int lane = threadIdx.x & 31;
-  fe one, pre = a, suf = a, t;
-  fe_set_one(one);
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    fe_shfl_up(t, pre, d);
-    fe_select(t, lane >= d, t, one);
-    fe_mul(pre, pre, t);
-    fe_shfl_down(t, suf, d);
-    fe_select(t, lane + d < 32, t, one);
-    fe_mul(suf, suf, t);
-  }
-  fe total, inv;
-  fe_shfl(total, pre, 31);
-  fe_inv(inv, total);
-  fe_shfl_up(t, pre, 1);
-  fe_select(t, lane >= 1, t, one);
-  fe_mul(inv, inv, t);
-  fe_shfl_down(t, suf, 1);
-  fe_select(t, lane + 1 < 32, t, one);
-  fe_mul(r, inv, t);
-}
-// Where point `idx` of a kernel's output goes: out + (item / inner) * stride + (item % inner) * stride_in
-// + (idx % nper) * 64 with item = idx / nper, so the same code writes plain arrays (nper = 1, stride = 64)
-// and the eps fields of proof records (nper = eps per proof, stride = record size, `inner` proofs per record).
+// ---- Jacobian -> 64-byte affine, one inversion per thread ------------------------
+// Thread t owns points t, t + T, t + 2T, ... (coalesced across the warp) and shares ONE field inversion
+// among them (Montgomery's trick along the thread's chain).  Sharing the inversion across the LANES of a
+// warp instead was built and measured in r02 (prefix / suffix products by shuffles, then fused into the
+// producing kernels): it saves nothing, because a warp executes the ~270-multiplication inversion chain
+// whether one lane or 32 need it - 2^20 fixed-base mults went from 1.90 + 0.5 ms to 3.93 ms.
+// Where point `idx` goes: out + (item / inner) * stride + (item % inner) * stride_in + (idx % nper) * 64 with
+// item = idx / nper, so the same kernel writes plain arrays (nper = 1, stride = 64) and the eps fields of
+// proof records (nper = eps per proof, stride = record size, `inner` proofs per record).
 struct pa_outlay {
   unsigned char *out;
   int nper;
@@ -148,41 +107,22 @@ struct pa_outlay {
     return out + (item / (size_t)inner) * stride + (item % (size_t)inner) * stride_in + (idx % (size_t)nper) * 64;
   }
 };
-inline pa_outlay pa_out_plain(unsigned char *out) { return pa_outlay{out, 1, 64, 1, 0}; }
-// The producing kernels finish with this instead of writing a Jacobian triple for a separate pass:
-// every lane brings its result (has = false: none), the warp shares one inversion, each lane stores its
-// 64-byte affine point.  Collective.
-PA_D void warp_emit_point(const pa_outlay &o, size_t idx, const jac &p, bool has) {
-  const bool real = has && !jac_is_inf(p);
-  fe z, zi;
-  fe_set_one(z);
-  if (real) z = p.Z;
-  warp_inverse(zi, z);
-  if (!has) return;
-  aff a;
-  if (real) jac_to_aff_with_zinv(a, p, zi); else aff_set_inf(a);
-  st_aff(o.at(idx), a);
-}
-
-// The separate pass, for producers that emit several points per thread (scans): thread t owns points
-// t, t + T, t + 2T, ... (coalesced across the warp), multiplies their Z together (prefix products kept in
-// `prefix`), the warp inverts the lanes' products together, and the thread unwinds its own chain.
 __global__ void __launch_bounds__(PA_BLOCK)
 k_normalize(const u32 *jin, u32 *prefix, pa_outlay o, int n, int T) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
   fe acc, z;
   fe_set_one(acc);
   int last = -1;
-  if (t < T) {
-    for (int idx = t; idx < n; idx += T) {
-      ld_fe(z, jin + 24 * (size_t)idx + 16);
-      if (!fe_is_zero(z)) fe_mul(acc, acc, z);
-      st_fe(prefix + 8 * (size_t)idx, acc);
-      last = idx;
-    }
+  for (int idx = t; idx < n; idx += T) {
+    ld_fe(z, jin + 24 * (size_t)idx + 16);
+    if (!fe_is_zero(z)) fe_mul(acc, acc, z);
+    st_fe(prefix + 8 * (size_t)idx, acc);
+    last = idx;
   }
+  if (last < 0) return;
   fe inv;
-  warp_inverse(inv, acc);
+  fe_inv(inv, acc);
   for (int idx = last; idx >= 0; idx -= T) {
     jac p;
     ld_jac(p, jin + 24 * (size_t)idx);
@@ -233,33 +173,26 @@ __global__ void k_comb_entries(const u32 *bases, u32 *tab) {  // one thread per 
 #define PA_FIX_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(PA_BLOCK, PA_FIX_MINBLOCKS)
-k_fixed_base(const unsigned char *scalars, const u32 *__restrict__ tab, pa_outlay o, int n) {
+k_fixed_base(const unsigned char *scalars, const u32 *__restrict__ tab, u32 *jout, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool has = i < n;
+  if (i >= n) return;
+  sc k;
+  ld_sc(k, scalars + 32 * (size_t)i);
   jac r;
-  jac_set_inf(r);
-  if (has) {
-    sc k;
-    ld_sc(k, scalars + 32 * (size_t)i);
-    fixed_base_mul(r, k, tab);
-  }
-  warp_emit_point(o, (size_t)i, r, has);
+  fixed_base_mul(r, k, tab);
+  st_jac(jout + 24 * (size_t)i, r);
 }
 
 __global__ void __launch_bounds__(PA_BLOCK, PA_VAR_MINBLOCKS)
-k_var_base(const unsigned char *points, const unsigned char *scalars, pa_outlay o, int n) {
+k_var_base(const unsigned char *points, const unsigned char *scalars, u32 *jout, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool has = i < n;
-  jac r;
-  jac_set_inf(r);
-  if (has) {
-    jac P;
-    sc k;
-    ld_point_jac(P, points + 64 * (size_t)i);
-    ld_sc(k, scalars + 32 * (size_t)i);
-    var_base_mul(r, P, k);
-  }
-  warp_emit_point(o, (size_t)i, r, has);
+  if (i >= n) return;
+  jac P, r;
+  sc k;
+  ld_point_jac(P, points + 64 * (size_t)i);
+  ld_sc(k, scalars + 32 * (size_t)i);
+  var_base_mul(r, P, k);
+  st_jac(jout + 24 * (size_t)i, r);
 }
 
 __global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
@@ -361,27 +294,39 @@ __global__ void k_peak_imad(u32 *sink, int iters, u32 a, u32 b) {
   u32 s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
   if (s == 0x12345u) sink[0] = s;
 }
-// 32 x 32 + 64 -> 64 multiply-add, the instruction the field arithmetic is made of: eight independent
-// accumulator chains per thread, multiplicands in registers, nothing else in the loop (SASS: 64 IMAD.WIDE.U32
-// per iteration plus the loop counter), so the figure is the multiplier pipe's own rate for this instruction.
-__global__ void k_peak_imad_wide(u64 *sink, int iters, u32 a) {
-  u64 x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-  u32 b = threadIdx.x * 2654435761u + 12345u;
-#define PA_WIDE8                                                                  \
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x0) : "r"(a), "r"(b));      \
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x1) : "r"(a), "r"(b));      \
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x2) : "r"(a), "r"(b));      \
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x3) : "r"(a), "r"(b));      \
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x4) : "r"(a), "r"(b));      \
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x5) : "r"(a), "r"(b));      \
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x6) : "r"(a), "r"(b));      \
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x7) : "r"(a), "r"(b));
+// 32 x 32 + 64 -> 64 multiply-add, the instruction the field arithmetic is made of.  Eight 64-bit accumulators
+// per thread; each takes the LOW WORD OF ITS NEIGHBOUR as multiplicand, so every product is new (ptxas folds a
+// loop-invariant product into additions) and there is no other instruction in the loop body: SASS = 64
+// IMAD.WIDE.U32 per iteration plus the loop counter.  chained = 0: independent accumulations (mad.wide.u32);
+// chained = 1: the shape of a row of the field multiplier, four multiply-adds linked by the carry flag
+// (mad.lo.cc / madc.hi.cc pairs, fused by ptxas into IMAD.WIDE.U32.X).
+__global__ void k_peak_imad_wide(u64 *sink, int iters, u32 b, int chained) {
+  u32 l0 = threadIdx.x * 2654435761u + 1u, l1 = l0 * 3u + 1u, l2 = l1 * 3u + 1u, l3 = l2 * 3u + 1u, l4 = l3 * 3u + 1u,
+      l5 = l4 * 3u + 1u, l6 = l5 * 3u + 1u, l7 = l6 * 3u + 1u;
+  u32 h0 = 0, h1 = 1, h2 = 2, h3 = 3, h4 = 4, h5 = 5, h6 = 6, h7 = 7;
+  b |= 0x80000001u;
+#define PA_W(lo, hi, m) asm volatile("{ .reg .b64 t; mov.b64 t, {%0, %1}; mad.wide.u32 t, %2, %3, t; mov.b64 {%0, %1}, t; }" : "+r"(lo), "+r"(hi) : "r"(m), "r"(b));
+#define PA_WIDE8 PA_W(l0, h0, l1) PA_W(l1, h1, l2) PA_W(l2, h2, l3) PA_W(l3, h3, l4) PA_W(l4, h4, l5) PA_W(l5, h5, l6) PA_W(l6, h6, l7) PA_W(l7, h7, l0)
+#define PA_PKA(lo, hi, m) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(m), "r"(b));
+#define PA_PKB(lo, hi, m) asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(m), "r"(b));
+#define PA_CHAIN8 PA_PKA(l0, h0, l1) PA_PKB(l2, h2, l3) PA_PKB(l4, h4, l5) PA_PKB(l6, h6, l7) PA_PKA(l1, h1, l2) PA_PKB(l3, h3, l4) PA_PKB(l5, h5, l6) PA_PKB(l7, h7, l0)
+  if (!chained) {
 #pragma unroll 1
-  for (int i = 0; i < iters; ++i) {
-    PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8
+    for (int i = 0; i < iters; ++i) {
+      PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8 PA_WIDE8
+    }
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+      PA_CHAIN8 PA_CHAIN8 PA_CHAIN8 PA_CHAIN8 PA_CHAIN8 PA_CHAIN8 PA_CHAIN8 PA_CHAIN8
+    }
   }
+#undef PA_W
 #undef PA_WIDE8
-  u64 s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+#undef PA_PKA
+#undef PA_PKB
+#undef PA_CHAIN8
+  u32 s = l0 ^ l1 ^ l2 ^ l3 ^ l4 ^ l5 ^ l6 ^ l7 ^ h0 ^ h1 ^ h2 ^ h3 ^ h4 ^ h5 ^ h6 ^ h7;
   if (s == 0x12345u) sink[0] = s;
 }
 __global__ void k_peak_fe(u32 *sink, int iters, int sqr) {
@@ -473,15 +418,14 @@ PA_D int proof_branch(int kind, const unsigned char *b0, const unsigned char *b1
 template <int KIND>
 __global__ void __launch_bounds__(PA_BLOCK, PA_OP_MINBLOCKS)
 k_prove_ops(const unsigned char *stmts, const unsigned char *rnd, const unsigned char *b0, const unsigned char *b1,
-            const u32 *__restrict__ comb, pa_outlay o, int n, pa_lay L) {
+            const u32 *__restrict__ comb, u32 *jout, int n, pa_lay L) {
   typedef proof_kind<KIND> K;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool has = t < n * K::NEPS;
-  int j = t / n, i = t % n, e = 0;
+  if (t >= n * K::NEPS) return;
+  int j = t / n, i = t % n;
   jac r;
-  jac_set_inf(r);
-  if (has) e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + L.S(i), rnd + L.R(i), comb);
-  warp_emit_point(o, (size_t)i * K::NEPS + e, r, has);  // eps e of proof i, straight into the record
+  int e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + L.S(i), rnd + L.R(i), comb);
+  st_jac(jout + 24 * ((size_t)i * K::NEPS + e), r);
 }
 // prover step 3 (after k_normalize wrote the eps points): challenge and responses
 template <int KIND>

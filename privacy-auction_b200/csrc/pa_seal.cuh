@@ -26,67 +26,57 @@
 // commitment points straight from the draw array: slot s has draws
 //   alpha, beta, v_A, v_B, r1, d1, d2   (7 x 32 B)
 __global__ void __launch_bounds__(PA_BLOCK)
-k_seal_commit_points(const unsigned char *rndc, const unsigned char *bits, const u32 *__restrict__ comb, pa_outlay o, int n) {
+k_seal_commit_points(const unsigned char *rndc, const unsigned char *bits, const u32 *__restrict__ comb, u32 *jout, int n) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool has = t < 3 * n;
+  if (t >= 3 * n) return;
   int which = t / n, i = t % n;
-  jac r;
-  jac_set_inf(r);
-  if (has) {
-    sc a, b, k;
-    ld_sc(a, rndc + 224 * (size_t)i);
-    ld_sc(b, rndc + 224 * (size_t)i + 32);
-    if (which == 0) {
-      sc bit;
-      sc_set_zero(bit);
-      bit.v[0] = bits[i] ? 1u : 0u;
-      sc_mul(k, a, b);
-      sc_add(k, k, bit);
-    } else {
-      k = which == 1 ? a : b;
-    }
-    fixed_base_mul(r, k, comb);
+  sc a, b, k;
+  ld_sc(a, rndc + 224 * (size_t)i);
+  ld_sc(b, rndc + 224 * (size_t)i + 32);
+  if (which == 0) {
+    sc bit;
+    sc_set_zero(bit);
+    bit.v[0] = bits[i] ? 1u : 0u;
+    sc_mul(k, a, b);
+    sc_add(k, k, bit);
+  } else {
+    k = which == 1 ? a : b;
   }
-  warp_emit_point(o, (size_t)i * 3 + which, r, has);
+  jac r;
+  fixed_base_mul(r, k, comb);
+  st_jac(jout + 24 * ((size_t)i * 3 + which), r);
 }
 
 // X = g^x, R = g^r from the round-one draws x, r, v_X, v_R (4 x 32 B per bidder)
 __global__ void __launch_bounds__(PA_BLOCK)
-k_seal_r1_points(const unsigned char *rnd1, const u32 *__restrict__ comb, pa_outlay o, int n) {
+k_seal_r1_points(const unsigned char *rnd1, const u32 *__restrict__ comb, u32 *jout, int n) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool has = t < 2 * n;
+  if (t >= 2 * n) return;
   int which = t / n, i = t % n;
+  sc k;
+  ld_sc(k, rnd1 + 128 * (size_t)i + 32 * which);
   jac r;
-  jac_set_inf(r);
-  if (has) {
-    sc k;
-    ld_sc(k, rnd1 + 128 * (size_t)i + 32 * which);
-    fixed_base_mul(r, k, comb);
-  }
-  warp_emit_point(o, (size_t)i * 2 + which, r, has);
+  fixed_base_mul(r, k, comb);
+  st_jac(jout + 24 * ((size_t)i * 2 + which), r);
 }
 
 // the cryptogram: b = R^x if the bidder vetoes, Y^x otherwise           SEAL/bidder.cpp:1301-1309
 __global__ void __launch_bounds__(PA_BLOCK)
 k_seal_encode(const u32 *act, const u32 *pauc, const unsigned char *bits, const u32 *boff, int step,
               const unsigned char *junc, const unsigned char *prevbit, const unsigned char *r1, const unsigned char *Y,
-              const unsigned char *rnd1, unsigned char *ebit, pa_outlay o, int n) {
+              const unsigned char *rnd1, unsigned char *ebit, u32 *jout, int n) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool has = p < n;
-  jac r;
-  jac_set_inf(r);
-  if (has) {
-    u32 slot = act[p];
-    int bit = bits[boff[slot] + step];
-    int veto = bit && (!junc[pauc[p]] || prevbit[slot]);
-    ebit[p] = (unsigned char)veto;
-    jac P;
-    sc x;
-    ld_point_jac(P, veto ? r1 + 320 * (size_t)p + 64 : Y + 64 * (size_t)p);
-    ld_sc(x, rnd1 + 128 * (size_t)p);
-    var_base_mul(r, P, x);
-  }
-  warp_emit_point(o, (size_t)p, r, has);
+  if (p >= n) return;
+  u32 slot = act[p];
+  int bit = bits[boff[slot] + step];
+  int veto = bit && (!junc[pauc[p]] || prevbit[slot]);
+  ebit[p] = (unsigned char)veto;
+  jac P, r;
+  sc x;
+  ld_point_jac(P, veto ? r1 + 320 * (size_t)p + 64 : Y + 64 * (size_t)p);
+  ld_sc(x, rnd1 + 128 * (size_t)p);
+  var_base_mul(r, P, x);
+  st_jac(jout + 24 * (size_t)p, r);
 }
 
 PA_D void cp64(unsigned char *d, const unsigned char *s) {
@@ -174,20 +164,16 @@ __global__ void k_seal_scatter_u8(const u32 *g, const unsigned char *src, unsign
 
 // both candidates of every item: cand[2i] = Y^x (no veto), cand[2i+1] = R^x (veto)    SEAL/bidder.cpp:1301-1309
 __global__ void __launch_bounds__(PA_BLOCK, PA_VAR_MINBLOCKS)
-k_seal_candidates(const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1, pa_outlay o, int n) {
+k_seal_candidates(const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1, u32 *jout, int n) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool has = t < 2 * n;
+  if (t >= 2 * n) return;
   int which = t / n, i = t % n;
-  jac r;
-  jac_set_inf(r);
-  if (has) {
-    jac P;
-    sc x;
-    ld_point_jac(P, which ? r1 + 320 * (size_t)i + 64 : Y + 64 * (size_t)i);
-    ld_sc(x, rnd1 + 128 * (size_t)i);
-    var_base_mul(r, P, x);
-  }
-  warp_emit_point(o, (size_t)i * 2 + which, r, has);
+  jac P, r;
+  sc x;
+  ld_point_jac(P, which ? r1 + 320 * (size_t)i + 64 : Y + 64 * (size_t)i);
+  ld_sc(x, rnd1 + 128 * (size_t)i);
+  var_base_mul(r, P, x);
+  st_jac(jout + 24 * ((size_t)i * 2 + which), r);
 }
 
 // state[0] = junction flag, state[1] = previous deciding step (-1: none), state[2] = next step to run,
@@ -974,7 +960,9 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     // and the verification of all of it
     auto commit_work = [&]() -> int {
       int rc2;
-      PA_LAUNCH(ctx, PA_K_COMMIT, (k_seal_commit_points<<<grid_for(3 * Mb), PA_BLOCK, 0, ctx->stream>>>(d_rndc, d_bits, ctx->d_comb, pa_outlay{d_crec, 3, 736, 1, 0}, (int)Mb)));
+      if ((rc2 = work_reserve(ctx, 3 * Mb))) return rc2;
+      PA_LAUNCH(ctx, PA_K_COMMIT, (k_seal_commit_points<<<grid_for(3 * Mb), PA_BLOCK, 0, ctx->stream>>>(d_rndc, d_bits, ctx->d_comb, work_jac(ctx), (int)Mb)));
+      if ((rc2 = normalize_to(ctx, d_crec, 3 * Mb, 3, 736))) return rc2;
       PA_CUDA(ctx, cudaEventRecord(ev_enc[1], ctx->stream));  // phi, A, B are in the records
       if ((rc2 = prove_dev<PA_POK>(ctx, d_crec + 64, d_rndc, nullptr, nullptr, d_cid, d_rndc + 64, d_crec + 192, 2 * Mb, LC2))) return rc2;
       if ((rc2 = prove_dev<PA_COM>(ctx, d_crec, d_rndc, d_bits, nullptr, d_cid, d_rndc + 128, d_crec + 384, Mb, LC))) return rc2;
@@ -1048,7 +1036,9 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream + i0, PH.ictr + i0, nullptr, 4, PH.rnd1 + 128 * i0, (int)cnt)));
       PA_CUDA(ctx, cudaMemcpyAsync(after.data() + i0, PH.ictr + i0, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
       int rc2;
-      PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, pa_outlay{PH.r1 + 320 * i0, 2, 320, 1, 0}, (int)cnt)));
+      if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
+      PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
+      if ((rc2 = normalize_to(ctx, PH.r1 + 320 * i0, 2 * cnt, 2, 320))) return rc2;
       if (!speculative && s1 == c && !pok_on_lane) {
         // these are the last keys: every X and R is final, so their proofs can run beside the rest of this pass
         // (they write the proof fields of the round-one records, the pass reads the point fields)
@@ -1082,7 +1072,9 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
         if ((rc2 = normalize_to(ctx, PH.Yall + 64 * s0 * nall, cn))) return rc2;
         PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_gather64<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(PH.Y + 64 * i0, PH.Yall, PH.lidx + i0, (int)cnt)));
       }
-      PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1 + 320 * i0, PH.Y + 64 * i0, PH.rnd1 + 128 * i0, pa_out_plain(PH.cand + 128 * i0), (int)cnt)));
+      if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
+      PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1 + 320 * i0, PH.Y + 64 * i0, PH.rnd1 + 128 * i0, work_jac(ctx), (int)cnt)));
+      if ((rc2 = normalize_to(ctx, PH.cand + 128 * i0, 2 * cnt))) return rc2;
       if (!sharded)
         PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
       else if (p2p)  // the walk and the per-step exchange of the ranks' cryptogram sums are one kernel
@@ -1281,7 +1273,9 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
 
     // ---- main lane: x, r, X = g^x, R = g^r ------------------------------------------------
     PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.act, 4, B.rnd1, (int)ma)));
-    PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * ma), PA_BLOCK, 0, ctx->stream>>>(B.rnd1, ctx->d_comb, pa_outlay{B.r1, 2, 320, 1, 0}, (int)ma)));
+    if ((rc = work_reserve(ctx, 2 * ma))) return rc;
+    PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * ma), PA_BLOCK, 0, ctx->stream>>>(B.rnd1, ctx->d_comb, work_jac(ctx), (int)ma)));
+    if ((rc = normalize_to(ctx, B.r1, 2 * ma, 2, 320))) return rc;
     PA_CUDA(ctx, cudaEventRecord(ev_r1[par], ctx->stream));
 
     // ---- lane 1: the Schnorr proofs of X (x, v_X) and R (r, v_R) and their verification -------
@@ -1324,7 +1318,9 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     }
 
     // ---- main lane: cryptogram b, statements and draws of the OR proofs --------------------------
-    PA_LAUNCH(ctx, PA_K_VAR, (k_seal_encode<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.act, B.pauc, d_bits, d_boff, (int)step, d_junc, d_prevbit, B.r1, Yloc, B.rnd1, B.ebit, pa_out_plain(B.b), (int)ma)));
+    if ((rc = work_reserve(ctx, ma))) return rc;
+    PA_LAUNCH(ctx, PA_K_VAR, (k_seal_encode<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.act, B.pauc, d_bits, d_boff, (int)step, d_junc, d_prevbit, B.r1, Yloc, B.rnd1, B.ebit, work_jac(ctx), (int)ma)));
+    if ((rc = normalize_to(ctx, B.b, ma))) return rc;
     if (n1) {
       PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(1, B.g, B.act, d_boff, (int)step, B.b, B.r1, Yloc, B.rnd1, d_crec, d_rndc, d_prevpts, d_prevx, B.ebit, d_prevbit, B.stmt, B.sec, B.bi, B.bj, (int)n1)));
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.gslot, 5, B.rnd2, (int)n1)));

@@ -559,6 +559,7 @@ class Engine:
         return bytes(out)
 
     def measure_int_peak(self):
-        out = (ctypes.c_double * 4)()
+        out = (ctypes.c_double * 6)()
         self._check(self.lib.pa_measure_int_peak(self.ctx, out))
-        return {"imad_per_s": out[0], "imad_wide_per_s": out[1], "fe_mul_per_s": out[2], "fe_sqr_per_s": out[3]}
+        return {"imad_per_s": out[0], "imad_wide_per_s": out[1], "fe_mul_per_s": out[2], "fe_sqr_per_s": out[3],
+                "imad_wide_unchained_per_s": out[4]}

@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o
 for w in $what; do
   case $w in
     tests)
-      timeout 1500 python -m pytest tests -m gpu -q -p pytest_timeout --timeout 600 > $out/${tag}_gpu_tests.log 2>&1
+      timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > $out/${tag}_gpu_tests.log 2>&1
       echo "tests rc=$?" >> $out/${tag}_gpu_tests.log; tail -15 $out/${tag}_gpu_tests.log ;;
     bench)
       timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
