@@ -783,16 +783,25 @@ int verify_dev(pa_ctx *ctx, const unsigned char *proofs, const unsigned char *st
   return PA_OK;
 }
 
+// wit: `secrets` holds the EXTENDED secrets (pa_proof.cuh, "prover with witnesses"; L.secret is their stride) and
+// cb the committed bit per proof (stage 2 only): every published point costs one fixed-base multiplication and at
+// most one variable-base multiplication.  Same bytes as the plain prover.
 template <int KIND>
 int prove_dev(pa_ctx *ctx, const unsigned char *stmts, const unsigned char *secrets, const unsigned char *b0,
               const unsigned char *b1, const u64 *ids, const unsigned char *rnd, unsigned char *proofs, size_t n,
-              pa_lay L = pa_lay_packed<KIND>()) {
+              pa_lay L = pa_lay_packed<KIND>(), bool wit = false, const unsigned char *cb = nullptr) {
   typedef proof_kind<KIND> K;
   if (n == 0) return PA_OK;
   size_t m = n * K::NEPS;
   int rc = work_reserve(ctx, m);
   if (rc) return rc;
-  PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n, L)));
+  if (wit) {
+    if constexpr (KIND != PA_POK) {
+      PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops_wit<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, secrets, b0, b1, cb, ctx->d_comb, work_jac(ctx), (int)n, L)));
+    }
+  } else {
+    PA_LAUNCH(ctx, PA_K_POPS + KIND, (k_prove_ops<KIND><<<grid_for(m), PA_BLOCK, 0, ctx->stream>>>(stmts, rnd, b0, b1, ctx->d_comb, work_jac(ctx), (int)n, L)));
+  }
   if ((rc = normalize_to(ctx, proofs, m, K::NEPS, L.proof, L.inner, L.proof_in))) return rc;
   PA_LAUNCH(ctx, PA_K_PRESPOND + KIND, (k_prove_respond<KIND><<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(proofs, stmts, ids, secrets, rnd, b0, b1, (int)n, L)));
   return PA_OK;
@@ -842,6 +851,27 @@ int pa_stage2_verify_dev(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt
   PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && (n == 0 || (proofs && stmt && ids && verdict)) && n < (1u << 26));
   return verify_dev<PA_S2, 16>(ctx, proofs, stmt, (const u64 *)ids, verdict, n);
+}
+
+// provers with witnesses (pa_proof.cuh): extended secrets, same proofs
+static pa_lay lay_w(pa_lay L, size_t secret_stride) {
+  L.secret = secret_stride;
+  return L;
+}
+int pa_powfcom_prove_w_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)) && n < (1u << 26));
+  return prove_dev<PA_COM>(ctx, stmt, secrets, bits, nullptr, (const u64 *)ids, rnd, proofs, n, lay_w(pa_lay_packed<PA_COM>(), 64), true);
+}
+int pa_stage1_prove_w_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)) && n < (1u << 26));
+  return prove_dev<PA_S1>(ctx, stmt, secrets, bits, nullptr, (const u64 *)ids, rnd, proofs, n, lay_w(pa_lay_packed<PA_S1>(), 128), true);
+}
+int pa_stage2_prove_w_dev(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint8_t *cbit, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bi && bj && cbit && ids && rnd && proofs)) && n < (1u << 26));
+  return prove_dev<PA_S2>(ctx, stmt, secrets, bi, bj, (const u64 *)ids, rnd, proofs, n, lay_w(pa_lay_packed<PA_S2>(), 192), true, cbit);
 }
 
 int pa_commit_points_dev(pa_ctx *ctx, const uint8_t *alpha, const uint8_t *beta, const uint8_t *bits, uint8_t *out, size_t n) {
@@ -947,6 +977,26 @@ int pa_stage2_prove(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, co
     if (bi[i] && !bj[i]) return pa_fail(ctx, PA_EINVAL, "stage 2: bi == 1 requires bj == 1 (assert at SEAL/bidder.cpp:604)");
   HArg a[] = {{stmt, 0, n * 704}, {secrets, 0, n * 96}, {bi, 0, n}, {bj, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 352}, {0, proofs, n * 1344}};
   return staged(ctx, a, 7, [&](unsigned char **d) { return pa_stage2_prove_dev(ctx, d[0], d[1], d[2], d[3], (const uint64_t *)d[4], d[5], d[6], n); });
+}
+int pa_powfcom_prove_w(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)));
+  HArg a[] = {{stmt, 0, n * 192}, {secrets, 0, n * 64}, {bits, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 96}, {0, proofs, n * 352}};
+  return staged(ctx, a, 6, [&](unsigned char **d) { return pa_powfcom_prove_w_dev(ctx, d[0], d[1], d[2], (const uint64_t *)d[3], d[4], d[5], n); });
+}
+int pa_stage1_prove_w(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bits, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bits && ids && rnd && proofs)));
+  HArg a[] = {{stmt, 0, n * 448}, {secrets, 0, n * 128}, {bits, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 160}, {0, proofs, n * 672}};
+  return staged(ctx, a, 6, [&](unsigned char **d) { return pa_stage1_prove_w_dev(ctx, d[0], d[1], d[2], (const uint64_t *)d[3], d[4], d[5], n); });
+}
+int pa_stage2_prove_w(pa_ctx *ctx, const uint8_t *stmt, const uint8_t *secrets, const uint8_t *bi, const uint8_t *bj, const uint8_t *cbit, const uint64_t *ids, const uint8_t *rnd, uint8_t *proofs, size_t n) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, ctx && (n == 0 || (stmt && secrets && bi && bj && cbit && ids && rnd && proofs)));
+  for (size_t i = 0; i < n; ++i)
+    if (bi[i] && !bj[i]) return pa_fail(ctx, PA_EINVAL, "stage 2: bi == 1 requires bj == 1 (assert at SEAL/bidder.cpp:604)");
+  HArg a[] = {{stmt, 0, n * 704}, {secrets, 0, n * 192}, {bi, 0, n}, {bj, 0, n}, {cbit, 0, n}, {ids, 0, n * 8}, {rnd, 0, n * 352}, {0, proofs, n * 1344}};
+  return staged(ctx, a, 8, [&](unsigned char **d) { return pa_stage2_prove_w_dev(ctx, d[0], d[1], d[2], d[3], d[4], (const uint64_t *)d[5], d[6], d[7], n); });
 }
 int pa_stage2_verify(pa_ctx *ctx, const uint8_t *proofs, const uint8_t *stmt, const uint64_t *ids, uint8_t *verdict, size_t n) {
   PA_ENTER(ctx);

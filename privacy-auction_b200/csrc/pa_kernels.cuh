@@ -427,6 +427,26 @@ k_prove_ops(const unsigned char *stmts, const unsigned char *rnd, const unsigned
   int e = prove_op_one<KIND>(r, proof_branch(KIND, b0, b1, i), j, stmts + L.S(i), rnd + L.R(i), comb);
   st_jac(jout + 24 * ((size_t)i * K::NEPS + e), r);
 }
+// prover step 1 with witnesses (pa_proof.cuh, "prover with witnesses"): the same operations, each as one
+// fixed-base multiplication plus at most one variable-base multiplication of the foreign point Y.
+// secrets: the extended secrets (L.X strides); cb: committed bit per proof (stage 2; NULL = the branch tells).
+// A warp runs operation j for 32 proofs; where their branches differ, some lanes have a foreign term and
+// some do not, and the warp pays for the longer path.
+template <int KIND>
+__global__ void __launch_bounds__(PA_BLOCK, PA_VAR_MINBLOCKS)
+k_prove_ops_wit(const unsigned char *stmts, const unsigned char *rnd, const unsigned char *secrets, const unsigned char *b0,
+                const unsigned char *b1, const unsigned char *cb, const u32 *__restrict__ comb, u32 *jout, int n, pa_lay L) {
+  typedef proof_kind<KIND> K;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * K::NEPS) return;
+  int j = t / n, i = t % n;
+  int branch = proof_branch(KIND, b0, b1, i);
+  int veto_i = b0[i] ? 1 : 0, veto_j = (KIND == PA_S2 && b1[i]) ? 1 : 0;
+  int cbit = (KIND == PA_S2) ? (cb[i] ? 1 : 0) : branch;  // COM, S1: branch 1 <=> committed bit 1
+  jac r;
+  int e = prove_op_one_wit<KIND>(r, branch, j, stmts + L.S(i), rnd + L.R(i), secrets + L.X(i), veto_i, veto_j, cbit, comb);
+  st_jac(jout + 24 * ((size_t)i * K::NEPS + e), r);
+}
 // prover step 3 (after k_normalize wrote the eps points): challenge and responses
 template <int KIND>
 __global__ void __launch_bounds__(PA_BLOCK)

@@ -341,6 +341,154 @@ PA_HD int prove_op_one(jac &r, int branch, int j, const unsigned char *stmt, con
   return op.E;
 }
 
+// ---- prover with witnesses ---------------------------------------------------------------
+// A prover knows the discrete logarithm of most points of its own statement: X = g^x, R = g^r,
+// A = g^alpha, B = g^beta, c = g^(alpha beta + bit), and its cryptogram is g^(r x) when it vetoes,
+// Y^x when it does not.  Only Y (the combination of the OTHER bidders' keys) is foreign.  So every
+// published point  a*P + b*Q  equals  kf*g + kv*Y  with two scalars computed mod n from the draws
+// and the secrets: one fixed-base multiplication and at most one variable-base multiplication
+// instead of up to two variable-base ones.  The points are the same group elements, hence the same
+// bytes (the reference calls EC_POINT_mul on the bases as given, SEAL/bidder.cpp:171-202, 355-417,
+// 657-814).  Extended secrets:
+//   COM (alpha, beta)    S1 (x, alpha, r, beta)    S2 (xi, xj, alpha, ri, rj, beta)
+// flags: veto_i / veto_j say which form the cryptograms Bi / Bj have, cbit is the committed bit.
+struct wit_term {
+  sc u;       // the point's g-part: u*g                 (valid if has_u)
+  sc v;       // the point's foreign part: v*stmt[ybase]  (valid if ybase >= 0)
+  bool has_u;
+  int ybase;
+};
+template <int KIND> struct wit_kind;
+template <> struct wit_kind<PA_COM> { static constexpr int NSECRET = 2; };
+template <> struct wit_kind<PA_S1> { static constexpr int NSECRET = 4; };
+template <> struct wit_kind<PA_S2> { static constexpr int NSECRET = 6; };
+
+// dlog of the commitment point c = phi: alpha * beta + bit  (- 1 for c / g)
+PA_HD void wit_commit_dlog(sc &u, const unsigned char *alpha, const unsigned char *beta, int cbit, bool over_g) {
+  sc a, b, one;
+  load_wire_scalar(a, alpha);
+  load_wire_scalar(b, beta);
+  sc_mul(u, a, b);
+  sc_set_zero(one);
+  one.v[0] = 1;
+  if (cbit) sc_add(u, u, one);
+  if (over_g) sc_sub(u, u, one);
+}
+PA_HD void wit_set_u(wit_term &w, const unsigned char *s) {
+  load_wire_scalar(w.u, s);
+  w.has_u = true;
+  w.ybase = -1;
+}
+PA_HD void wit_set_prod(wit_term &w, const unsigned char *s0, const unsigned char *s1) {
+  sc a, b;
+  load_wire_scalar(a, s0);
+  load_wire_scalar(b, s1);
+  sc_mul(w.u, a, b);
+  w.has_u = true;
+  w.ybase = -1;
+}
+PA_HD void wit_set_y(wit_term &w, int ybase, const unsigned char *s) {  // s == NULL: the foreign point itself
+  if (s) {
+    load_wire_scalar(w.v, s);
+  } else {
+    sc_set_zero(w.v);
+    w.v.v[0] = 1;
+  }
+  w.has_u = false;
+  w.ybase = ybase;
+}
+template <int KIND>
+PA_HD void wit_resolve(wit_term &w, int code, const unsigned char *s, int veto_i, int veto_j, int cbit);
+template <>
+PA_HD void wit_resolve<PA_COM>(wit_term &w, int code, const unsigned char *s, int, int, int cbit) {
+  // stmt phi=0 A=1 B=2; secrets alpha, beta
+  if (code == PS_CG || code == PS_STMT + 0) {
+    wit_commit_dlog(w.u, s, s + 32, cbit, code == PS_CG);
+    w.has_u = true;
+    w.ybase = -1;
+  } else {
+    wit_set_u(w, code == PS_STMT + 1 ? s : s + 32);
+  }
+}
+template <>
+PA_HD void wit_resolve<PA_S1>(wit_term &w, int code, const unsigned char *s, int veto_i, int, int cbit) {
+  // stmt b=0 X=1 Y=2 R=3 c=4 A=5 B=6; secrets x, alpha, r, beta
+  switch (code) {
+    case PS_STMT + 0: if (veto_i) wit_set_prod(w, s + 64, s); else wit_set_y(w, 2, s); break;  // b = R^x | Y^x
+    case PS_STMT + 1: wit_set_u(w, s); break;
+    case PS_STMT + 2: wit_set_y(w, 2, nullptr); break;
+    case PS_STMT + 3: wit_set_u(w, s + 64); break;
+    case PS_STMT + 5: wit_set_u(w, s + 32); break;
+    case PS_STMT + 6: wit_set_u(w, s + 96); break;
+    default:  // c, c/g
+      wit_commit_dlog(w.u, s + 32, s + 96, cbit, code == PS_CG);
+      w.has_u = true;
+      w.ybase = -1;
+  }
+}
+template <>
+PA_HD void wit_resolve<PA_S2>(wit_term &w, int code, const unsigned char *s, int veto_i, int veto_j, int cbit) {
+  // stmt Bi=0 Xi=1 Ri=2 Bj=3 Xj=4 Rj=5 Ci=6 A=7 B=8 Yi=9 Yj=10; secrets xi, xj, alpha, ri, rj, beta
+  switch (code) {
+    case PS_STMT + 0: if (veto_i) wit_set_prod(w, s + 96, s); else wit_set_y(w, 9, s); break;          // Bi = Ri^xi | Yi^xi
+    case PS_STMT + 1: wit_set_u(w, s); break;
+    case PS_STMT + 2: wit_set_u(w, s + 96); break;
+    case PS_STMT + 3: if (veto_j) wit_set_prod(w, s + 128, s + 32); else wit_set_y(w, 10, s + 32); break;  // Bj = Rj^xj | Yj^xj
+    case PS_STMT + 4: wit_set_u(w, s + 32); break;
+    case PS_STMT + 5: wit_set_u(w, s + 128); break;
+    case PS_STMT + 7: wit_set_u(w, s + 64); break;
+    case PS_STMT + 8: wit_set_u(w, s + 160); break;
+    case PS_STMT + 9: wit_set_y(w, 9, nullptr); break;
+    case PS_STMT + 10: wit_set_y(w, 10, nullptr); break;
+    default:  // Ci, Ci/g
+      wit_commit_dlog(w.u, s + 64, s + 160, cbit, code == PS_CG);
+      w.has_u = true;
+      w.ybase = -1;
+  }
+}
+
+// prover with witnesses, operation j of one proof: r = eps[E] = kf*g + kv*stmt[ybase]; returns E.
+// The two terms of an operation never involve two different foreign points (prove_op tables).
+template <int KIND>
+PA_HD int prove_op_one_wit(jac &r, int branch, int j, const unsigned char *stmt, const unsigned char *rnd,
+                           const unsigned char *secrets, int veto_i, int veto_j, int cbit, const u32 *comb) {
+  pa_op op = prove_op<KIND>(branch, j);
+  sc kf, kv, a, t;
+  sc_set_zero(kf);
+  sc_set_zero(kv);
+  int ybase = -1;
+  for (int side = 0; side < 2; ++side) {
+    int code = side ? op.Q : op.P, scode = side ? op.b : op.a;
+    if (code == PS_NONE) continue;
+    if (scode == SS_ZERO) continue;  // the term vanishes (stage-2 branch 3)
+    load_wire_scalar(a, rnd + 32 * scode);
+    if (code == PS_G) {
+      sc_add(kf, kf, a);
+      continue;
+    }
+    wit_term w;
+    wit_resolve<KIND>(w, code, secrets, veto_i, veto_j, cbit);
+    if (w.has_u) {
+      sc_mul(t, a, w.u);
+      sc_add(kf, kf, t);
+    } else {
+      sc_mul(t, a, w.v);
+      sc_add(kv, kv, t);
+      ybase = w.ybase;
+    }
+  }
+  fixed_base_mul(r, kf, comb);
+  if (ybase >= 0 && !sc_is_zero(kv)) {
+    aff y;
+    jac Y, v;
+    load_wire_point(y, stmt + 64 * ybase);
+    jac_from_aff(Y, y);
+    var_base_mul(v, Y, kv);
+    jac_add(r, r, v);
+  }
+  return op.E;
+}
+
 // ---- Fiat-Shamir challenge of one proof ------------------------------------------------
 template <int KIND>
 PA_HD void proof_challenge(sc &ch, const unsigned char *proof, const unsigned char *stmt, u64 id) {

@@ -91,13 +91,15 @@ PA_D void cp32(unsigned char *d, const unsigned char *s) {
 }
 
 // statement / witness assembly for the round-two proofs of group members g[q] (positions in
-// the active list).  Stage 1: (b, X, Y, R, c, A, B), (x, alpha).  Stage 2: (Bi, Xi, Ri, Bj, Xj,
-// Rj, Ci, A, B, Yi, Yj), (xi, xj, alpha), bi = encoded bit, bj = prevDecidingBit.
+// the active list).  Stage 1: (b, X, Y, R, c, A, B), extended secrets (x, alpha, r, beta).  Stage 2:
+// (Bi, Xi, Ri, Bj, Xj, Rj, Ci, A, B, Yi, Yj), (xi, xj, alpha, ri, rj, beta), bi = encoded bit,
+// bj = prevDecidingBit, cb = the committed bit (pa_proof.cuh, "prover with witnesses").
 __global__ void k_seal_stmt(int stage, const u32 *g, const u32 *act, const u32 *boff, int step, const unsigned char *b,
                             const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1,
                             const unsigned char *crec, const unsigned char *rndc, const unsigned char *prevpts,
                             const unsigned char *prevx, const unsigned char *ebit, const unsigned char *prevbit,
-                            unsigned char *stmt, unsigned char *sec, unsigned char *bi, unsigned char *bj, int n) {
+                            const unsigned char *bits, unsigned char *stmt, unsigned char *sec, unsigned char *bi,
+                            unsigned char *bj, unsigned char *cb, int n) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
   u32 p = g[q], slot = act[p];
@@ -107,8 +109,9 @@ __global__ void k_seal_stmt(int stage, const u32 *g, const u32 *act, const u32 *
     unsigned char *o = stmt + 448 * (size_t)q;
     cp64(o, b + 64 * (size_t)p); cp64(o + 64, X); cp64(o + 128, Y + 64 * (size_t)p); cp64(o + 192, R);
     cp64(o + 256, c); cp64(o + 320, c + 64); cp64(o + 384, c + 128);
-    cp32(sec + 64 * (size_t)q, rnd1 + 128 * (size_t)p);
-    cp32(sec + 64 * (size_t)q + 32, rndc + 224 * cs);
+    unsigned char *w = sec + 128 * (size_t)q;
+    cp32(w, rnd1 + 128 * (size_t)p); cp32(w + 32, rndc + 224 * cs);
+    cp32(w + 64, rnd1 + 128 * (size_t)p + 32); cp32(w + 96, rndc + 224 * cs + 32);
     bi[q] = ebit[p];
   } else {
     const unsigned char *pp = prevpts + 256 * (size_t)slot;  // X, R, Y, b at the previous deciding step
@@ -117,11 +120,12 @@ __global__ void k_seal_stmt(int stage, const u32 *g, const u32 *act, const u32 *
     cp64(o + 192, pp + 192); cp64(o + 256, pp); cp64(o + 320, pp + 64);
     cp64(o + 384, c); cp64(o + 448, c + 64); cp64(o + 512, c + 128);
     cp64(o + 576, Y + 64 * (size_t)p); cp64(o + 640, pp + 128);
-    cp32(sec + 96 * (size_t)q, rnd1 + 128 * (size_t)p);
-    cp32(sec + 96 * (size_t)q + 32, prevx + 32 * (size_t)slot);
-    cp32(sec + 96 * (size_t)q + 64, rndc + 224 * cs);
+    unsigned char *w = sec + 192 * (size_t)q;
+    cp32(w, rnd1 + 128 * (size_t)p); cp32(w + 32, prevx + 64 * (size_t)slot); cp32(w + 64, rndc + 224 * cs);
+    cp32(w + 96, rnd1 + 128 * (size_t)p + 32); cp32(w + 128, prevx + 64 * (size_t)slot + 32); cp32(w + 160, rndc + 224 * cs + 32);
     bi[q] = ebit[p];
     bj[q] = prevbit[slot];
+    cb[q] = bits[cs];
   }
 }
 
@@ -138,7 +142,8 @@ __global__ void k_seal_update(const u32 *act, const u32 *pseg, const u32 *pauc, 
   unsigned char *pp = prevpts + 256 * (size_t)slot;
   cp64(pp, r1 + 320 * (size_t)p); cp64(pp + 64, r1 + 320 * (size_t)p + 64);
   cp64(pp + 128, Y + 64 * (size_t)p); cp64(pp + 192, b + 64 * (size_t)p);
-  cp32(prevx + 32 * (size_t)slot, rnd1 + 128 * (size_t)p);
+  cp32(prevx + 64 * (size_t)slot, rnd1 + 128 * (size_t)p);  // x and r of the deciding step
+  cp32(prevx + 64 * (size_t)slot + 32, rnd1 + 128 * (size_t)p + 32);
   prevbit[slot] &= bits[boff[slot] + step];
   junc[pauc[p]] = 1;
 }
@@ -163,16 +168,25 @@ __global__ void k_seal_scatter_u8(const u32 *g, const unsigned char *src, unsign
 // the proofs of all steps in one batch per kind.  Item i = step * m + bidder.
 
 // both candidates of every item: cand[2i] = Y^x (no veto), cand[2i+1] = R^x (veto)    SEAL/bidder.cpp:1301-1309
+// The veto candidate is the bidder's own R = g^r raised to x, i.e. g^(r x): a fixed-base multiplication.
 __global__ void __launch_bounds__(PA_BLOCK, PA_VAR_MINBLOCKS)
-k_seal_candidates(const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1, u32 *jout, int n) {
+k_seal_candidates(const unsigned char *Y, const unsigned char *rnd1, const u32 *__restrict__ comb, u32 *jout, int n) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 2 * n) return;
   int which = t / n, i = t % n;
-  jac P, r;
+  jac r;
   sc x;
-  ld_point_jac(P, which ? r1 + 320 * (size_t)i + 64 : Y + 64 * (size_t)i);
   ld_sc(x, rnd1 + 128 * (size_t)i);
-  var_base_mul(r, P, x);
+  if (which) {
+    sc rr, k;
+    ld_sc(rr, rnd1 + 128 * (size_t)i + 32);
+    sc_mul(k, rr, x);
+    fixed_base_mul(r, k, comb);
+  } else {
+    jac P;
+    ld_point_jac(P, Y + 64 * (size_t)i);
+    var_base_mul(r, P, x);
+  }
   st_jac(jout + 24 * ((size_t)i * 2 + which), r);
 }
 
@@ -249,8 +263,9 @@ k_seal_decide(int m, int limit, int speculative, const unsigned char *bits, cons
 __global__ void k_seal_stmt_items(int m, int n1, const int *stage, const int *prevstep, const u32 *boff, const unsigned char *b,
                                   const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1,
                                   const unsigned char *crec, const unsigned char *rndc, const unsigned char *ebit,
-                                  const unsigned char *bjv, unsigned char *stmt1, unsigned char *sec1, unsigned char *bi1,
-                                  unsigned char *stmt2, unsigned char *sec2, unsigned char *bi2, unsigned char *bj2, int n) {
+                                  const unsigned char *bjv, const unsigned char *bits, unsigned char *stmt1, unsigned char *sec1,
+                                  unsigned char *bi1, unsigned char *stmt2, unsigned char *sec2, unsigned char *bi2, unsigned char *bj2,
+                                  unsigned char *cb2, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int s = i / m, p = i % m;
@@ -261,8 +276,9 @@ __global__ void k_seal_stmt_items(int m, int n1, const int *stage, const int *pr
     unsigned char *o = stmt1 + 448 * q;
     cp64(o, b + 64 * (size_t)i); cp64(o + 64, X); cp64(o + 128, Y + 64 * (size_t)i); cp64(o + 192, R);
     cp64(o + 256, c); cp64(o + 320, c + 64); cp64(o + 384, c + 128);
-    cp32(sec1 + 64 * q, rnd1 + 128 * (size_t)i);
-    cp32(sec1 + 64 * q + 32, rndc + 224 * cs);
+    unsigned char *w = sec1 + 128 * q;  // x, alpha, r, beta
+    cp32(w, rnd1 + 128 * (size_t)i); cp32(w + 32, rndc + 224 * cs);
+    cp32(w + 64, rnd1 + 128 * (size_t)i + 32); cp32(w + 96, rndc + 224 * cs + 32);
     bi1[q] = ebit[i];
   } else {
     size_t q = (size_t)i - n1, j = (size_t)prevstep[s] * m + p;  // the same bidder at the previous deciding step
@@ -271,11 +287,12 @@ __global__ void k_seal_stmt_items(int m, int n1, const int *stage, const int *pr
     cp64(o + 192, b + 64 * j); cp64(o + 256, r1 + 320 * j); cp64(o + 320, r1 + 320 * j + 64);
     cp64(o + 384, c); cp64(o + 448, c + 64); cp64(o + 512, c + 128);
     cp64(o + 576, Y + 64 * (size_t)i); cp64(o + 640, Y + 64 * j);
-    cp32(sec2 + 96 * q, rnd1 + 128 * (size_t)i);
-    cp32(sec2 + 96 * q + 32, rnd1 + 128 * j);
-    cp32(sec2 + 96 * q + 64, rndc + 224 * cs);
+    unsigned char *w = sec2 + 192 * q;  // xi, xj, alpha, ri, rj, beta
+    cp32(w, rnd1 + 128 * (size_t)i); cp32(w + 32, rnd1 + 128 * j); cp32(w + 64, rndc + 224 * cs);
+    cp32(w + 96, rnd1 + 128 * (size_t)i + 32); cp32(w + 128, rnd1 + 128 * j + 32); cp32(w + 160, rndc + 224 * cs + 32);
     bi2[q] = ebit[i];
     bj2[q] = bjv[i];
+    cb2[q] = bits[cs];
   }
 }
 
@@ -694,7 +711,7 @@ int lanes_init(pa_ctx *ctx) {
 struct StepBufs {  // per-step device buffers; two sets, used alternately
   u32 *act, *pauc, *pseg, *soff, *g, *gslot;
   u64 *pid, *gid;
-  unsigned char *rnd1, *r1, *pokv, *Y, *b, *ebit, *stmt, *sec, *bi, *bj, *rnd2, *proof, *pv;
+  unsigned char *rnd1, *r1, *pokv, *Y, *b, *ebit, *stmt, *sec, *bi, *bj, *cb, *rnd2, *proof, *pv;
   int *isinf;
 };
 
@@ -816,7 +833,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     u64 *istream, *ictr, *pid;
     u32 *soff;
     int *stage, *prevstep, *r3, *state;
-    unsigned char *rnd1, *r1, *pokv, *r1ok, *Y, *cand, *b, *ebit, *bj, *stmt, *sec, *bi, *bjp, *rnd2, *proof, *r2ok;
+    unsigned char *rnd1, *r1, *pokv, *r1ok, *Y, *cand, *b, *ebit, *bj, *stmt, *sec, *bi, *bjp, *cbp, *rnd2, *proof, *r2ok;
     unsigned char *Xall, *Yall, *part;  // sharded: every bidder's X / Y of every step; the ranks' partial sums of a step
     u32 *gidx, *lidx, *soffN;
   } PH{};
@@ -834,8 +851,8 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       PH.pokv = pool.alloc<unsigned char>(T * 2); PH.r1ok = pool.alloc<unsigned char>(T);
       PH.Y = pool.alloc<unsigned char>(T * 64); PH.cand = pool.alloc<unsigned char>(T * 128); PH.b = pool.alloc<unsigned char>(T * 64);
       PH.ebit = pool.alloc<unsigned char>(T); PH.bj = pool.alloc<unsigned char>(T);
-      PH.stmt = pool.alloc<unsigned char>(T * 704 + 256); PH.sec = pool.alloc<unsigned char>(T * 96 + 256);
-      PH.bi = pool.alloc<unsigned char>(T + 256); PH.bjp = pool.alloc<unsigned char>(T + 256);
+      PH.stmt = pool.alloc<unsigned char>(T * 704 + 256); PH.sec = pool.alloc<unsigned char>(T * 192 + 256);
+      PH.bi = pool.alloc<unsigned char>(T + 256); PH.bjp = pool.alloc<unsigned char>(T + 256); PH.cbp = pool.alloc<unsigned char>(T + 256);
       PH.rnd2 = pool.alloc<unsigned char>(T * 352 + 256); PH.proof = pool.alloc<unsigned char>(T * 1344 + 256);
       PH.r2ok = pool.alloc<unsigned char>(T + 256);
       if (sharded && !p2p) {
@@ -860,7 +877,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     d_junc = pool.alloc<unsigned char>(A, true);
     d_prevbit = pool.alloc<unsigned char>(m);
     d_prevpts = pool.alloc<unsigned char>(m * 256, true);
-    d_prevx = pool.alloc<unsigned char>(m * 32, true);
+    d_prevx = pool.alloc<unsigned char>(m * 64, true);
     d_r1ok = pool.alloc<unsigned char>(cmax * m);
     d_r2ok = pool.alloc<unsigned char>(cmax * m);
     d_sstream = pool.alloc<u64>(Mb);
@@ -873,8 +890,8 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       B.rnd1 = pool.alloc<unsigned char>(m * 128); B.r1 = pool.alloc<unsigned char>(m * 320); B.pokv = pool.alloc<unsigned char>(m * 2);
       B.Y = pool.alloc<unsigned char>(nY * 64); B.b = pool.alloc<unsigned char>(m * 64); B.ebit = pool.alloc<unsigned char>(m);
       // stage-1 members first, stage-2 members behind them (256-byte aligned)
-      B.stmt = pool.alloc<unsigned char>(m * 704 + 256); B.sec = pool.alloc<unsigned char>(m * 96 + 256);
-      B.bi = pool.alloc<unsigned char>(m + 256); B.bj = pool.alloc<unsigned char>(m + 256);
+      B.stmt = pool.alloc<unsigned char>(m * 704 + 256); B.sec = pool.alloc<unsigned char>(m * 192 + 256);
+      B.bi = pool.alloc<unsigned char>(m + 256); B.bj = pool.alloc<unsigned char>(m + 256); B.cb = pool.alloc<unsigned char>(m + 256);
       B.rnd2 = pool.alloc<unsigned char>(m * 352 + 256); B.proof = pool.alloc<unsigned char>(m * 1344 + 256);
       B.pv = pool.alloc<unsigned char>(m + 256);
       B.isinf = pool.alloc<int>(A);
@@ -917,6 +934,10 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
   // strides of the records the proofs live in; LC2 / LR2: the two Schnorr proofs of a record in one batch
   const pa_lay LC{736, 736, 224, 224, 1, 0, 0, 0, 0}, LC2{736, 736, 224, 224, 2, 96, 64, 32, 32};
   const pa_lay LR2{320, 320, 128, 128, 2, 96, 64, 32, 32};
+  // round-two proofs with witnesses: packed records, extended secrets (x, alpha, r, beta) / (xi, xj, alpha, ri, rj, beta)
+  pa_lay LW1 = pa_lay_packed<PA_S1>(), LW2 = pa_lay_packed<PA_S2>();
+  LW1.secret = 128;
+  LW2.secret = 192;
 
   // verdicts and records of the commit phase to the host (after their verification has been queued)
   auto collect_commitments = [&]() -> int {
@@ -965,7 +986,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       if ((rc2 = normalize_to(ctx, d_crec, 3 * Mb, 3, 736))) return rc2;
       PA_CUDA(ctx, cudaEventRecord(ev_enc[1], ctx->stream));  // phi, A, B are in the records
       if ((rc2 = prove_dev<PA_POK>(ctx, d_crec + 64, d_rndc, nullptr, nullptr, d_cid, d_rndc + 64, d_crec + 192, 2 * Mb, LC2))) return rc2;
-      if ((rc2 = prove_dev<PA_COM>(ctx, d_crec, d_rndc, d_bits, nullptr, d_cid, d_rndc + 128, d_crec + 384, Mb, LC))) return rc2;
+      if ((rc2 = prove_dev<PA_COM>(ctx, d_crec, d_rndc, d_bits, nullptr, d_cid, d_rndc + 128, d_crec + 384, Mb, LC, true))) return rc2;
       if (ctx->corrupt.bidder < m && ctx->corrupt.step < boff[ctx->corrupt.bidder + 1] - boff[ctx->corrupt.bidder] &&
           (rc2 = dbg_corrupt(1, d_crec + 736 * ((size_t)boff[ctx->corrupt.bidder] + ctx->corrupt.step))))
         return rc2;
@@ -1073,7 +1094,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
         PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_gather64<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(PH.Y + 64 * i0, PH.Yall, PH.lidx + i0, (int)cnt)));
       }
       if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
-      PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.r1 + 320 * i0, PH.Y + 64 * i0, PH.rnd1 + 128 * i0, work_jac(ctx), (int)cnt)));
+      PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.Y + 64 * i0, PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.cand + 128 * i0, 2 * cnt))) return rc2;
       if (!sharded)
         PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
@@ -1144,13 +1165,13 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     for (size_t s2 = 0; s2 < c; ++s2)
       if (stage[s2] == 2) { c1 = s2; break; }
     const size_t n1 = c1 * m, n2 = T - n1;
-    const size_t o_stmt = align_up(n1 * 448, 256), o_sec = align_up(n1 * 64, 256), o_b = align_up(n1, 256),
+    const size_t o_stmt = align_up(n1 * 448, 256), o_sec = align_up(n1 * 128, 256), o_b = align_up(n1, 256),
                  o_rnd = align_up(n1 * 160, 256), o_proof = align_up(n1 * 672, 256);
     if (pok_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[0], 0));
     else if ((rc = pok_all())) return rc;
     // ---- round-two proofs: statements, draws (right after the four key draws), prove, verify -----------------
     PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[1], 0));  // the commitment points (side lane)
-    PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt_items<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>((int)m, (int)n1, PH.stage, PH.prevstep, d_boff, PH.b, PH.r1, PH.Y, PH.rnd1, d_crec, d_rndc, PH.ebit, PH.bj, PH.stmt, PH.sec, PH.bi, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, (int)T)));
+    PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt_items<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>((int)m, (int)n1, PH.stage, PH.prevstep, d_boff, PH.b, PH.r1, PH.Y, PH.rnd1, d_crec, d_rndc, PH.ebit, PH.bj, d_bits, PH.stmt, PH.sec, PH.bi, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.cbp + o_b, (int)T)));
     for (size_t i = 0; i < T; ++i) ictr[i] = key_ctr(i / m, J) + 4, istream[i] = streams[i % m];
     PA_CUDA(ctx, cudaMemcpyAsync(PH.istream, istream.data(), T * 8, cudaMemcpyHostToDevice, ctx->stream));
     PA_CUDA(ctx, cudaMemcpyAsync(PH.ictr, ictr.data(), T * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1165,17 +1186,17 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       PA_CUDA(ctx, cudaEventRecord(ev_enc[0], ctx->stream));
       LaneScope ls(ctx, L_prove);
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[0], 0));
-      if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
+      if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1, LW1, true))) return rc;
       if (cor_item < n1 && (rc = dbg_corrupt(3, PH.proof + 672 * cor_item))) return rc;
       if (verify) PA_VREP(verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1));
       PA_CUDA(ctx, cudaEventRecord(ev_proved[0], ctx->stream));
     } else if (n1) {
-      if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1))) return rc;
+      if ((rc = prove_dev<PA_S1>(ctx, PH.stmt, PH.sec, PH.bi, nullptr, PH.pid, PH.rnd2, PH.proof, n1, LW1, true))) return rc;
       if (cor_item < n1 && (rc = dbg_corrupt(3, PH.proof + 672 * cor_item))) return rc;
       if (verify) PA_VREP(verify_dev<PA_S1, 8>(ctx, PH.proof, PH.stmt, PH.pid, PH.r2ok, n1));
     }
     if (n2) {
-      if ((rc = prove_dev<PA_S2>(ctx, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.pid + n1, PH.rnd2 + o_rnd, PH.proof + o_proof, n2))) return rc;
+      if ((rc = prove_dev<PA_S2>(ctx, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.pid + n1, PH.rnd2 + o_rnd, PH.proof + o_proof, n2, LW2, true, PH.cbp + o_b))) return rc;
       if (cor_item >= n1 && cor_item < T && (rc = dbg_corrupt(3, PH.proof + o_proof + 1344 * (cor_item - n1)))) return rc;
       if (verify) PA_VREP(verify_dev<PA_S2, 16>(ctx, PH.proof + o_proof, PH.stmt + o_stmt, PH.pid + n1, PH.r2ok + n1, n2));
     }
@@ -1258,7 +1279,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     for (u32 p : g1) g.push_back(p), gslot.push_back(act[p]), gid.push_back(ids[act[p]]);
     for (u32 p : g2) g.push_back(p), gslot.push_back(act[p]), gid.push_back(ids[act[p]]);
     // offsets of the stage-2 group inside the shared per-step arrays
-    const size_t o_stmt = align_up(n1 * 448, 256), o_sec = align_up(n1 * 64, 256), o_b = align_up(n1, 256),
+    const size_t o_stmt = align_up(n1 * 448, 256), o_sec = align_up(n1 * 128, 256), o_b = align_up(n1, 256),
                  o_rnd = align_up(n1 * 160, 256), o_proof = align_up(n1 * 672, 256);
 
     // this buffer set was last used two steps ago: its side lanes must have drained
@@ -1322,11 +1343,11 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     PA_LAUNCH(ctx, PA_K_VAR, (k_seal_encode<<<grid_for(ma), PA_BLOCK, 0, ctx->stream>>>(B.act, B.pauc, d_bits, d_boff, (int)step, d_junc, d_prevbit, B.r1, Yloc, B.rnd1, B.ebit, work_jac(ctx), (int)ma)));
     if ((rc = normalize_to(ctx, B.b, ma))) return rc;
     if (n1) {
-      PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(1, B.g, B.act, d_boff, (int)step, B.b, B.r1, Yloc, B.rnd1, d_crec, d_rndc, d_prevpts, d_prevx, B.ebit, d_prevbit, B.stmt, B.sec, B.bi, B.bj, (int)n1)));
+      PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(1, B.g, B.act, d_boff, (int)step, B.b, B.r1, Yloc, B.rnd1, d_crec, d_rndc, d_prevpts, d_prevx, B.ebit, d_prevbit, d_bits, B.stmt, B.sec, B.bi, B.bj, B.cb, (int)n1)));
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n1), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.gslot, 5, B.rnd2, (int)n1)));
     }
     if (n2) {
-      PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(2, B.g + n1, B.act, d_boff, (int)step, B.b, B.r1, Yloc, B.rnd1, d_crec, d_rndc, d_prevpts, d_prevx, B.ebit, d_prevbit, B.stmt + o_stmt, B.sec + o_sec, B.bi + o_b, B.bj + o_b, (int)n2)));
+      PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(2, B.g + n1, B.act, d_boff, (int)step, B.b, B.r1, Yloc, B.rnd1, d_crec, d_rndc, d_prevpts, d_prevx, B.ebit, d_prevbit, d_bits, B.stmt + o_stmt, B.sec + o_sec, B.bi + o_b, B.bj + o_b, B.cb + o_b, (int)n2)));
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(n2), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_streams, d_ctr, B.gslot + n1, 11, B.rnd2 + o_rnd, (int)n2)));
     }
     if (want_b) PA_CUDA(ctx, cudaMemcpyAsync(h_stage + off_b + step * m * 64, B.b, ma * 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1336,8 +1357,8 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     {
       LaneScope ls(ctx, L_prove);
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[par], 0));
-      if (n1 && (rc = prove_dev<PA_S1>(ctx, B.stmt, B.sec, B.bi, nullptr, B.gid, B.rnd2, B.proof, n1))) return rc;
-      if (n2 && (rc = prove_dev<PA_S2>(ctx, B.stmt + o_stmt, B.sec + o_sec, B.bi + o_b, B.bj + o_b, B.gid + n1, B.rnd2 + o_rnd, B.proof + o_proof, n2))) return rc;
+      if (n1 && (rc = prove_dev<PA_S1>(ctx, B.stmt, B.sec, B.bi, nullptr, B.gid, B.rnd2, B.proof, n1, LW1, true))) return rc;
+      if (n2 && (rc = prove_dev<PA_S2>(ctx, B.stmt + o_stmt, B.sec + o_sec, B.bi + o_b, B.bj + o_b, B.gid + n1, B.rnd2 + o_rnd, B.proof + o_proof, n2, LW2, true, B.cb + o_b))) return rc;
       if (A == 1 && ctx->corrupt.step == step && ctx->corrupt.bidder < ma) {  // one auction: position = bidder, one group per step
         unsigned char *rec = n1 ? B.proof + 672 * ctx->corrupt.bidder : B.proof + o_proof + 1344 * ctx->corrupt.bidder;
         if ((rc = dbg_corrupt(3, rec))) return rc;

@@ -63,6 +63,12 @@ SIGNATURES = {
     "pa_stage2_prove": (ctypes.c_int, [_ctx] + [_vp] * 7 + [_sz]),
     "pa_stage2_prove_dev": (ctypes.c_int, [_ctx] + [_vp] * 7 + [_sz]),
     "pa_stage2_verify": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
+    "pa_powfcom_prove_w": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_powfcom_prove_w_dev": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_stage1_prove_w": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_stage1_prove_w_dev": (ctypes.c_int, [_ctx] + [_vp] * 6 + [_sz]),
+    "pa_stage2_prove_w": (ctypes.c_int, [_ctx] + [_vp] * 8 + [_sz]),
+    "pa_stage2_prove_w_dev": (ctypes.c_int, [_ctx] + [_vp] * 8 + [_sz]),
     "pa_stage2_verify_dev": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
     "pa_commit_points": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
     "pa_commit_points_dev": (ctypes.c_int, [_ctx] + [_vp] * 4 + [_sz]),
@@ -387,6 +393,16 @@ class Engine:
 
     def stage2_verify(self, proofs, stmt, ids):
         return self._run("pa_stage2_verify", (proofs, stmt, self._ids(ids)), len(ids), len(ids))
+
+    # provers with witnesses (include/pa_engine.h): extended secrets, byte-identical proofs, 2-3 times less work
+    def powfcom_prove_w(self, stmt, secrets, bits, ids, rnd):
+        return self._run("pa_powfcom_prove_w", (stmt, secrets, bytes(bits), self._ids(ids), rnd), 352 * len(ids), len(ids))
+
+    def stage1_prove_w(self, stmt, secrets, bits, ids, rnd):
+        return self._run("pa_stage1_prove_w", (stmt, secrets, bytes(bits), self._ids(ids), rnd), 672 * len(ids), len(ids))
+
+    def stage2_prove_w(self, stmt, secrets, bi, bj, cbit, ids, rnd):
+        return self._run("pa_stage2_prove_w", (stmt, secrets, bytes(bi), bytes(bj), bytes(cbit), self._ids(ids), rnd), 1344 * len(ids), len(ids))
 
     def commit_points(self, alpha, beta, bits):
         return self._run("pa_commit_points", (alpha, beta, bytes(bits)), 192 * len(bits), len(bits))

@@ -179,7 +179,27 @@ template <int KIND> static void prove_all(unsigned char *proof, const unsigned c
   }
   prove_respond<KIND>(proof, stmt, id, secrets, rnd, branch);
 }
+// the prover with witnesses (pa_proof.cuh): extended secrets; must publish the same bytes as prove_all
+template <int KIND> static void prove_all_wit(unsigned char *proof, const unsigned char *stmt, u64 id, const unsigned char *secrets,
+                                              const unsigned char *rnd, int branch, int veto_i, int veto_j, int cbit) {
+  typedef proof_kind<KIND> K;
+  ensure_tab();
+  for (int j = 0; j < K::NEPS; ++j) {
+    jac r;
+    int e = prove_op_one_wit<KIND>(r, branch, j, stmt, rnd, secrets, veto_i, veto_j, cbit, g_tab.data());
+    out_jac(proof + 64 * e, r);
+  }
+  prove_respond<KIND>(proof, stmt, id, secrets, rnd, branch);
+}
 extern "C" {
+void hc_proof_prove_w(int kind, unsigned char *proof, const unsigned char *stmt, unsigned long long id,
+                      const unsigned char *secrets, const unsigned char *rnd, int branch, int veto_i, int veto_j, int cbit) {
+  switch (kind) {
+  case PA_COM: prove_all_wit<PA_COM>(proof, stmt, id, secrets, rnd, branch, veto_i, veto_j, cbit); break;
+  case PA_S1: prove_all_wit<PA_S1>(proof, stmt, id, secrets, rnd, branch, veto_i, veto_j, cbit); break;
+  default: prove_all_wit<PA_S2>(proof, stmt, id, secrets, rnd, branch, veto_i, veto_j, cbit);
+  }
+}
 unsigned hc_proof_verify(int kind, const unsigned char *proof, const unsigned char *stmt, unsigned long long id) {
   switch (kind) {
   case PA_POK: return verify_all<PA_POK>(proof, stmt, id, 1);

@@ -74,3 +74,25 @@ class HostcheckBackend:
 
     def stage2_verify(self, proofs, stmt, ids):
         return self._verify("stage2", proofs, stmt, ids)
+
+    # ---- provers with witnesses (pa_engine.h, pa_*_prove_w): extended secrets, same bytes --------------
+    def _prove_w(self, name, nsec, stmt, secrets, branches, veto_i, veto_j, cbit, ids, rnd):
+        kind, rec, nst, _, nrnd, _ = KIND[name]
+        out = bytearray()
+        for i, ident in enumerate(ids):
+            proof = ctypes.create_string_buffer(rec)
+            self.hc.hc_proof_prove_w(kind, proof, stmt[64 * nst * i:64 * nst * (i + 1)], ctypes.c_ulonglong(ident),
+                                     secrets[32 * nsec * i:32 * nsec * (i + 1)], rnd[32 * nrnd * i:32 * nrnd * (i + 1)],
+                                     int(branches[i]), int(veto_i[i]), int(veto_j[i]), int(cbit[i]))
+            out += proof.raw
+        return bytes(out)
+
+    def powfcom_prove_w(self, stmt, secrets, bits, ids, rnd):
+        return self._prove_w("powfcom", 2, stmt, secrets, bits, bits, [0] * len(ids), bits, ids, rnd)
+
+    def stage1_prove_w(self, stmt, secrets, bits, ids, rnd):
+        return self._prove_w("stage1", 4, stmt, secrets, bits, bits, [0] * len(ids), bits, ids, rnd)
+
+    def stage2_prove_w(self, stmt, secrets, bi, bj, cbit, ids, rnd):
+        br = [0 if a == 1 else (1 if b == 1 else 2) for a, b in zip(bi, bj)]
+        return self._prove_w("stage2", 6, stmt, secrets, br, bi, bj, cbit, ids, rnd)

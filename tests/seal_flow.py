@@ -26,9 +26,12 @@ class SealFlow:
     processes in id order (the all-gather of SURVEY.md section 8e) — used for the X of
     round one and the b of round two, the only data a bidder needs from the others."""
 
-    def __init__(self, backend, n, c, seed, bids, verify=True, auction=0, mine=None, exchange=None):
+    def __init__(self, backend, n, c, seed, bids, verify=True, auction=0, mine=None, exchange=None, witness=False):
+        """witness: prove with the backend's pa_*_prove_w entry points (extended secrets: the prover's knowledge of the
+        discrete logarithms of its own points turns variable-base into fixed-base work); same transcript."""
         assert len(bids) == n
         self.be, self.n, self.c, self.seed, self.bids, self.verify = backend, n, c, seed, list(bids), verify
+        self.witness = witness
         self.mine = list(range(n)) if mine is None else list(mine)
         self.exchange = exchange or (lambda kind, data: data)
         self.streams = {j: E.PaStream(seed, (auction << 32) | j) for j in self.mine}
@@ -68,7 +71,11 @@ class SealFlow:
         B = self._cat(pts[192 * k + 128:192 * k + 192] for k in range(m))
         pokA = be.pokdlog_prove(A, alpha, ids, self._cat(vA))
         pokB = be.pokdlog_prove(B, beta, ids, self._cat(vB))
-        com = be.powfcom_prove(pts, alpha, bytes(bits), ids, self._cat(rc))
+        if self.witness:
+            com = be.powfcom_prove_w(pts, self._cat(a + b for a, b in zip(al, bt)), bytes(bits), ids, self._cat(rc))
+        else:
+            com = be.powfcom_prove(pts, alpha, bytes(bits), ids, self._cat(rc))
+        self.beta = {j: [bt[q * c + i] for i in range(c)] for q, j in enumerate(mine)}
         self.alpha = {j: [al[q * c + i] for i in range(c)] for q, j in enumerate(mine)}
         self.cpts = {j: [pts[192 * (q * c + i):192 * (q * c + i + 1)] for i in range(c)] for q, j in enumerate(mine)}
         # Bidder::verifyCommitment (SEAL/bidder.cpp:1171-1195): every proof once
@@ -97,7 +104,7 @@ class SealFlow:
         R = be.fixed_base_mul(r_b)
         pokX = be.pokdlog_prove(X, x_b, mine, self._cat(vx))
         pokR = be.pokdlog_prove(R, r_b, mine, self._cat(vr))
-        self.x, self.X, self.R = xs, X, R
+        self.x, self.r, self.X, self.R = xs, rs, X, R
         if self.verify and self.n > 1:
             v1 = be.pokdlog_verify(pokX, X, mine)
             v2 = be.pokdlog_verify(pokR, R, mine)
@@ -126,20 +133,26 @@ class SealFlow:
         if not self.junction:
             for q, j in enumerate(mine):
                 stmt.append(pt(b, q) + pt(self.X, q) + pt(Y, q) + pt(self.R, q) + self.cpts[j][step])
-                sec.append(self.x[q] + self.alpha[j][step])
+                sec.append(self.x[q] + self.alpha[j][step] + (self.r[q] + self.beta[j][step] if self.witness else b""))
                 rnd.append(self._cat(b32(v) for v in self._draw(j, 5)))
             stmt_b = self._cat(stmt)
-            proofs = be.stage1_prove(stmt_b, self._cat(sec), bytes(ebit), mine, self._cat(rnd))
+            prove = be.stage1_prove_w if self.witness else be.stage1_prove
+            proofs = prove(stmt_b, self._cat(sec), bytes(ebit), mine, self._cat(rnd))
             rec, tag = 672, 1
         else:
             P = self.prev
             for q, j in enumerate(mine):
                 stmt.append(pt(b, q) + pt(self.X, q) + pt(self.R, q) + pt(P["b"], q) + pt(P["X"], q) + pt(P["R"], q) +
                             self.cpts[j][step] + pt(Y, q) + pt(P["Y"], q))
-                sec.append(self.x[q] + P["x"][q] + self.alpha[j][step])
+                sec.append(self.x[q] + P["x"][q] + self.alpha[j][step] +
+                           (self.r[q] + P["r"][q] + self.beta[j][step] if self.witness else b""))
                 rnd.append(self._cat(b32(v) for v in self._draw(j, 11)))
             stmt_b = self._cat(stmt)
-            proofs = be.stage2_prove(stmt_b, self._cat(sec), bytes(ebit), bytes(self.prev_bit[j] for j in mine), mine, self._cat(rnd))
+            bjs = bytes(self.prev_bit[j] for j in mine)
+            if self.witness:
+                proofs = be.stage2_prove_w(stmt_b, self._cat(sec), bytes(ebit), bjs, bytes(self.bits[j][step] for j in mine), mine, self._cat(rnd))
+            else:
+                proofs = be.stage2_prove(stmt_b, self._cat(sec), bytes(ebit), bjs, mine, self._cat(rnd))
             rec, tag = 1344, 2
         if self.verify and self.n > 1:
             v = be.stage1_verify(proofs, stmt_b, mine) if tag == 1 else be.stage2_verify(proofs, stmt_b, mine)
@@ -159,7 +172,7 @@ class SealFlow:
             for j in self.mine:
                 self.prev_bit[j] &= self.bits[j][step]                    # :1402 (true bit)
             self.max_bid |= 1 << (self.c - step - 1)                      # :1403 (64-bit shift here)
-            self.prev = {"X": self.X, "R": self.R, "Y": self.Y, "b": self.b, "x": list(self.x)}   # :1406-1411
+            self.prev = {"X": self.X, "R": self.R, "Y": self.Y, "b": self.b, "x": list(self.x), "r": list(self.r)}   # :1406-1411
         self.sec["r3"].append(1 if deciding else 0)
 
     def run_sections(self):

@@ -136,7 +136,8 @@ def _random_proofs(oracle, rnd, kind, n):
         al, be = [sc() for _ in range(n)], [sc() for _ in range(n)]
         bits = bytes(rnd.randrange(2) for _ in range(n))
         stmt = oracle.commit_points(b"".join(map(b32, al)), b"".join(map(b32, be)), bits)
-        return dict(stmt=stmt, secrets=b"".join(map(b32, al)), ids=ids, rnd=b"".join(b32(sc()) for _ in range(3 * n)), args=(bits,))
+        return dict(stmt=stmt, secrets=b"".join(map(b32, al)), ids=ids, rnd=b"".join(b32(sc()) for _ in range(3 * n)), args=(bits,),
+                    wsecrets=b"".join(b32(al[i]) + b32(be[i]) for i in range(n)), wargs=(bits,))
     # stage 1 / stage 2 statements
     x, r, al, be = ([sc() for _ in range(n)] for _ in range(4))
     bits = [rnd.randrange(2) for _ in range(n)]
@@ -150,7 +151,9 @@ def _random_proofs(oracle, rnd, kind, n):
     if kind == "stage1":
         stmt = b"".join(p(b, i) + p(X, i) + p(Y, i) + p(R, i) + cpts[192 * i:192 * i + 192] for i in range(n))
         sec = b"".join(b32(x[i]) + b32(al[i]) for i in range(n))
-        return dict(stmt=stmt, secrets=sec, ids=ids, rnd=b"".join(b32(sc()) for _ in range(5 * n)), args=(bytes(bits),))
+        wsec = b"".join(b32(x[i]) + b32(al[i]) + b32(r[i]) + b32(be[i]) for i in range(n))
+        return dict(stmt=stmt, secrets=sec, ids=ids, rnd=b"".join(b32(sc()) for _ in range(5 * n)), args=(bytes(bits),),
+                    wsecrets=wsec, wargs=(bytes(bits),))
     # stage 2: previous deciding step data; bj random, bi = bit & bj
     xj, rj = [sc() for _ in range(n)], [sc() for _ in range(n)]
     bj = [rnd.randrange(2) for _ in range(n)]
@@ -160,13 +163,16 @@ def _random_proofs(oracle, rnd, kind, n):
     Yj = oracle.fixed_base_mul(b"".join(b32(sc()) for _ in range(n)))
     basej = b"".join((Rj if bj[i] else Yj)[64 * i:64 * i + 64] for i in range(n))
     Bj = oracle.var_base_mul(basej, b"".join(map(b32, xj)))
-    cpts = oracle.commit_points(b"".join(map(b32, al)), b"".join(map(b32, be)), bytes(bi))
+    # the commitment holds the TRUE bit: equal to bi while the bidder is in the race (bj = 1), free once it is out
+    cpts = oracle.commit_points(b"".join(map(b32, al)), b"".join(map(b32, be)), bytes(bits))
     basei = b"".join((R if bi[i] else Y)[64 * i:64 * i + 64] for i in range(n))
     Bi = oracle.var_base_mul(basei, b"".join(map(b32, x)))
     stmt = b"".join(p(Bi, i) + p(X, i) + p(R, i) + p(Bj, i) + p(Xj, i) + p(Rj, i) + cpts[192 * i:192 * i + 192] + p(Y, i) + p(Yj, i)
                     for i in range(n))
     sec = b"".join(b32(x[i]) + b32(xj[i]) + b32(al[i]) for i in range(n))
-    return dict(stmt=stmt, secrets=sec, ids=ids, rnd=b"".join(b32(sc()) for _ in range(11 * n)), args=(bytes(bi), bytes(bj)))
+    wsec = b"".join(b32(x[i]) + b32(xj[i]) + b32(al[i]) + b32(r[i]) + b32(rj[i]) + b32(be[i]) for i in range(n))
+    return dict(stmt=stmt, secrets=sec, ids=ids, rnd=b"".join(b32(sc()) for _ in range(11 * n)), args=(bytes(bi), bytes(bj)),
+                wsecrets=wsec, wargs=(bytes(bi), bytes(bj), bytes(bits)))
 
 
 REC = {"pokdlog": (96, 1), "powfcom": (352, 4), "stage1": (672, 8), "stage2": (1344, 16)}
@@ -181,6 +187,8 @@ def test_prove_verify_parity_and_tampering(engine, oracle, kind):
     ver_e, ver_o = getattr(engine, kind + "_verify"), getattr(oracle, kind + "_verify")
     proofs = prove_e(w["stmt"], w["secrets"], *w["args"], w["ids"], w["rnd"])
     assert proofs == prove_o(w["stmt"], w["secrets"], *w["args"], w["ids"], w["rnd"])
+    if kind != "pokdlog":   # the prover with witnesses (pa_*_prove_w) publishes the same bytes
+        assert getattr(engine, kind + "_prove_w")(w["stmt"], w["wsecrets"], *w["wargs"], w["ids"], w["rnd"]) == proofs
     assert ver_e(proofs, w["stmt"], w["ids"]) == bytes([1] * n) == ver_o(proofs, w["stmt"], w["ids"])
     # negative tests (the reference has none): every scalar field flipped,
     # every eps replaced by another valid point, wrong id — verdicts must agree with the oracle

@@ -44,12 +44,14 @@ def test_goldens_cover_every_branch():
     assert tags >= {1, 2, "b=inf"} and stage2_shapes == {"rho11=0", "rho11!=0"} and r3 == {0, 1}
 
 
+@pytest.mark.parametrize("witness", [False, True], ids=["plain", "witness"])
 @pytest.mark.parametrize("path", GOLDEN[:4], ids=[os.path.basename(p) for p in GOLDEN[:4]])
-def test_device_proof_code_host_build_reproduces_reference(oracle, path):
+def test_device_proof_code_host_build_reproduces_reference(oracle, path, witness):
     """pa_proof.cuh / pa_sha256.cuh compiled for the host (PTX carry flag emulated):
-    provers and verifiers, one proof at a time, against the reference transcript."""
+    provers and verifiers, one proof at a time, against the reference transcript.  witness: the provers that use
+    the prover's knowledge of discrete logarithms (pa_*_prove_w) must publish the very same bytes."""
     import hostcheck_backend
     gold = open(path, "rb").read()
     t = seal_flow.parse_transcript(gold)
-    fl = seal_flow.SealFlow(hostcheck_backend.HostcheckBackend(oracle), t["n"], t["c"], t["seed"], t["bids"])
+    fl = seal_flow.SealFlow(hostcheck_backend.HostcheckBackend(oracle), t["n"], t["c"], t["seed"], t["bids"], witness=witness)
     assert fl.run() == gold and fl.ok
