@@ -20,18 +20,19 @@ typedef uint32_t u32;
 template <int KIND> __device__ __forceinline__ void extra(u32 &x, u32 y) {
   if (KIND == 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(y));
   if (KIND == 2) asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(x) : "r"(y));
-  if (KIND == 3) asm volatile("xor.b32 %0, %0, %1;" : "+r"(x) : "r"(y));
+  if (KIND == 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(x) : "r"(y), "r"(0x5A5A5A5Au));
   if (KIND == 4) asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x) : "r"(y));
   if (KIND == 5) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(x) : "r"(y));
   if (KIND == 6) asm volatile("prmt.b32 %0, %0, %1, 0x2103;" : "+r"(x) : "r"(y));
 }
 template <int KIND, int K> __device__ __forceinline__ void extras(u32 &e0, u32 &e1, u32 &e2, u32 &e3, u32 y) {
+  // e0 op= e1, e1 op= e2, e2 op= e3, e3 op= e0: values keep changing, nothing folds into a constant
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    if ((k & 3) == 0) extra<KIND>(e0, y);
-    if ((k & 3) == 1) extra<KIND>(e1, y);
-    if ((k & 3) == 2) extra<KIND>(e2, y);
-    if ((k & 3) == 3) extra<KIND>(e3, y);
+    if ((k & 3) == 0) extra<KIND>(e0, e1);
+    if ((k & 3) == 1) extra<KIND>(e1, e2);
+    if ((k & 3) == 2) extra<KIND>(e2, e3);
+    if ((k & 3) == 3) extra<KIND>(e3, e0);
   }
 }
 
