@@ -174,11 +174,14 @@ PA_HD void glv_decompose(glv_split &o, const sc &k) {
   }
 }
 
-#define PA_GLV_WINDOWS 33  // 4-bit windows over 132 bits, plus one carry digit
+// |k1|, |k2| < 2^128 for every k < n (the bound libsecp256k1 proves for these lattice constants; the largest
+// halves seen over 2 10^5 random and rounding-boundary scalars are 0.64 2^128, tests/test_hostcheck.py), so
+// kp = |k| + 0x88...8 (32 nibbles) < 2^129: 32 signed digits and a top digit that is 0 or 1 - 128 doublings.
+#define PA_GLV_WINDOWS 32  // signed 4-bit windows over 128 bits; digit 32 is the carry out of the recoding
 
-// kp = |k| + 0x888...8 (33 nibbles): digit i = nibble_i(kp) - 8, digit 33 = the carry out
+// kp = |k| + 0x888...8 (32 nibbles): digit i = nibble_i(kp) - 8 for i < 32, digit 32 = what is left above (0 or 1)
 PA_HD void glv_recode(u32 kp[5], const u32 k[5]) {
-  const u32 add[5] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x8u};
+  const u32 add[5] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x0u};
   u64 c = 0;
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
@@ -187,8 +190,8 @@ PA_HD void glv_recode(u32 kp[5], const u32 k[5]) {
     c = t >> 32;
   }
 }
-PA_HD int glv_digit(const u32 kp[5], int i) {  // i in [0, 33]
-  if (i == PA_GLV_WINDOWS) return (int)((kp[4] >> 4) & 1u);
+PA_HD int glv_digit(const u32 kp[5], int i) {  // i in [0, 32]
+  if (i == PA_GLV_WINDOWS) return (int)(kp[4] & 15u);  // <= 1 by the bound above (the table would serve up to 8)
   return (int)((kp[i >> 3] >> ((i & 7) * 4)) & 15u) - 8;
 }
 

@@ -154,6 +154,15 @@ int hc_jac_eq_aff(const unsigned char *p, const unsigned char *q) {
   if (!jac_is_inf(P)) { fe z; fe_set_zero(z); z.v[0] = 5; fe z2, z3; fe_sqr(z2, z); fe_mul(z3, z2, z); fe_mul(P.X, P.X, z2); fe_mul(P.Y, P.Y, z3); P.Z = z; }
   return jac_eq_aff(P, b) ? 1 : 0;
 }
+// the GLV halves of k: out = |k1| (5 limbs LE), |k2| (5 limbs LE), neg1, neg2 as 42 bytes
+void hc_glv_split(const unsigned char *k, unsigned char *out) {
+  sc s; sc_from_be(s, k);
+  glv_split g;
+  glv_decompose(g, s);
+  for (int i = 0; i < 5; ++i) for (int b = 0; b < 4; ++b) { out[4 * i + b] = (unsigned char)(g.k1[i] >> (8 * b)); out[20 + 4 * i + b] = (unsigned char)(g.k2[i] >> (8 * b)); }
+  out[40] = g.neg1 ? 1 : 0;
+  out[41] = g.neg2 ? 1 : 0;
+}
 const unsigned int *hc_comb_table() { ensure_tab(); return g_tab.data(); }
 }
 

@@ -138,3 +138,27 @@ def test_group_and_scalar_mult(hc):
     for a, b in [(5, N - 5), (1, 1), (0, 0), (7, 0), (0, 9), (N - 1, 1), (8, 8)]:
         assert lin(p, a, p, b) == E.mul(a + b, p)
         assert lin(p, a, E.neg(p), b) == E.mul(a - b, p)
+
+
+def test_glv_halves_stay_below_2_128(hc):
+    """The variable-base loop walks 32 signed 4-bit windows plus a 0/1 top digit (pa_smul.cuh, PA_GLV_WINDOWS): that needs
+    |k1|, |k2| < 2^128 for every scalar.  Random scalars, the edges, and scalars next to the rounding boundaries of the
+    two quotient estimates c_i = round(k g_i / 2^384)."""
+    LAM = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+    G1 = 0x3086D221A7D46BCDE86C90E49284EB153DAA8A1471E8CA7FE893209A45DBB031
+    G2 = 0xE4437ED6010E88286F547FA90ABFE4C4221208AC9DF506C61571B4AE8AC47F71
+    rnd = random.Random(2026)
+    ks = [0, 1, 2, N - 1, N - 2, N // 2, N // 2 + 1, N // 3, LAM, N - LAM] + [rnd.randrange(N) for _ in range(3000)]
+    for j in range(1, 400):
+        for g in (G1, G2):
+            k = (((2 * j + 1) << 383) // g) % N
+            ks += [(k - 1) % N, k, (k + 1) % N]
+    out = ctypes.create_string_buffer(42)
+    worst = 0
+    for k in ks:
+        hc.hc_glv_split(b32(k), out)
+        k1, k2 = int.from_bytes(out.raw[:20], "little"), int.from_bytes(out.raw[20:40], "little")
+        worst = max(worst, k1, k2)
+        s1, s2 = (-k1 if out.raw[40] else k1), (-k2 if out.raw[41] else k2)
+        assert (s1 + s2 * LAM - k) % N == 0
+    assert worst < 1 << 128
