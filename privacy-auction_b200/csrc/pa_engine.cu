@@ -6,7 +6,9 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -54,7 +56,7 @@ struct pa_ctx {
   } xchg;
   // optional per-kernel CUDA-event timing (pa_profile_begin / pa_profile_end)
   bool profiling = false;
-  struct Span { int kid; cudaEvent_t e0, e1; };
+  struct Span { int kid; cudaEvent_t e0, e1; cudaStream_t st; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> ev_pool;
 };
@@ -89,7 +91,7 @@ static cudaEvent_t ev_get(pa_ctx *ctx) {
 // launch a kernel on the context's stream; when profiling, bracket it with events
 #define PA_LAUNCH(ctx, kid, ...)                                   \
   do {                                                             \
-    pa_ctx::Span sp_{kid, nullptr, nullptr};                       \
+    pa_ctx::Span sp_{kid, nullptr, nullptr, (ctx)->stream};                       \
     if ((ctx)->profiling) {                                        \
       sp_.e0 = ev_get(ctx);                                        \
       sp_.e1 = ev_get(ctx);                                        \
@@ -668,6 +670,27 @@ int pa_profile_end(pa_ctx *ctx, pa_kernel_stat *out, size_t cap, size_t *count) 
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   double total[PA_K_COUNT] = {0};
   uint64_t cnt[PA_K_COUNT] = {0};
+  // development aid: PA_TIMELINE=<path prefix> appends "start_ms dur_ms lane kernel" per launch (relative to the first
+  // launch of the profiled region; lane = the stream it ran on) to <prefix>.<device>
+  if (const char *tl = getenv("PA_TIMELINE")) {
+    if (!ctx->spans.empty()) {
+      std::string path = std::string(tl) + "." + std::to_string(ctx->device);
+      if (FILE *f = fopen(path.c_str(), "a")) {
+        std::vector<cudaStream_t> lanes;
+        fprintf(f, "# region with %zu launches\n", ctx->spans.size());
+        for (auto &sp : ctx->spans) {
+          float t0 = 0, ms = 0;
+          cudaEventSynchronize(sp.e1);
+          cudaEventElapsedTime(&t0, ctx->spans[0].e0, sp.e0);
+          cudaEventElapsedTime(&ms, sp.e0, sp.e1);
+          size_t lane = std::find(lanes.begin(), lanes.end(), sp.st) - lanes.begin();
+          if (lane == lanes.size()) lanes.push_back(sp.st);
+          fprintf(f, "%9.3f %8.3f %zu %s\n", t0, ms, lane, PA_K_NAMES[sp.kid]);
+        }
+        fclose(f);
+      }
+    }
+  }
   for (auto &sp : ctx->spans) {
     float ms = 0;
     PA_CUDA(ctx, cudaEventElapsedTime(&ms, sp.e0, sp.e1));

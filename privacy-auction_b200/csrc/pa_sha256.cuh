@@ -7,22 +7,32 @@
 // is exactly the X || Y part, so hashing needs no field arithmetic at all (the
 // reference pays a field inversion per hashed point inside point2oct).
 //
-// One thread hashes one message; the message is streamed byte-wise into the
-// 16-word block buffer because the 65-byte encodings are not word aligned.
-// A challenge is 4..29 blocks next to ~10^6 multiply-adds of curve work.
+// One thread hashes one message.  The message is streamed through a 64-bit shift register: bytes where the
+// encoding demands it (the 04 / 00 prefix of a point, the id), whole big-endian words for the 64 coordinate
+// bytes of a point (aligned 16-byte loads from the wire record), so a point costs 17 steps instead of 65.
+// A challenge is 4..29 blocks next to ~10^6 multiply-adds of curve work, but with one proof per thread
+// these kernels run at lone-warp latency, which is why the streaming cost matters.
 #pragma once
 #include "pa_sc.cuh"
 
 struct sha256_state {
   u32 h[8];
-  u32 w[16];
-  u32 fill;  // bytes in w
+  u32 w[16];   // the block being filled (indexed by pos: lives in local memory on the device)
+  u32 pos;     // complete words in w
+  u32 nb;      // pending bytes (0..3), held in the low bits of acc
+  u64 acc;
   u32 blocks;
 };
 
 PA_HD u32 sha_rotr(u32 x, int n) { return (x >> n) | (x << (32 - n)); }
 
+// On the device the compression function is a real function (about 2,000 instructions): it is reached from every
+// place a block can fill up, and inlining it there would multiply the code.
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ void sha256_compress(u32 *h, const u32 *blk) {
+#else
 PA_HD void sha256_compress(u32 h[8], const u32 blk[16]) {
+#endif
   const u32 K[64] = {
       0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
       0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
@@ -63,50 +73,71 @@ PA_HD void sha256_init(sha256_state &s) {
   const u32 iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
 #pragma unroll
   for (int i = 0; i < 8; ++i) s.h[i] = iv[i];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) s.w[i] = 0;
-  s.fill = 0;
+  s.pos = 0;
+  s.nb = 0;
+  s.acc = 0;
   s.blocks = 0;
 }
 
-PA_HD void sha256_put(sha256_state &s, u32 byte) {
-  u32 wi = s.fill >> 2, sh = 24 - 8 * (s.fill & 3);
-  // dynamic word index: keep it a loop the compiler can turn into selects
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if ((u32)i == wi) s.w[i] |= (byte & 0xFFu) << sh;
-  if (++s.fill == 64) {
+PA_HD void sha256_emit(sha256_state &s, u32 word) {
+  s.w[s.pos] = word;
+  if (++s.pos == 16) {
     sha256_compress(s.h, s.w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s.w[i] = 0;
-    s.fill = 0;
+    s.pos = 0;
     s.blocks++;
   }
+}
+// one message byte
+PA_HD void sha256_put(sha256_state &s, u32 byte) {
+  s.acc = (s.acc << 8) | (byte & 0xFFu);
+  if (++s.nb == 4) {
+    sha256_emit(s, (u32)s.acc);
+    s.nb = 0;
+  }
+}
+// four message bytes, given as the big-endian word they form
+PA_HD void sha256_put_be32(sha256_state &s, u32 x) {
+  s.acc = (s.acc << 32) | x;
+  sha256_emit(s, (u32)(s.acc >> (8 * s.nb)));
 }
 
 PA_HD void sha256_put_bytes(sha256_state &s, const unsigned char *p, int n) {
   for (int i = 0; i < n; ++i) sha256_put(s, p[i]);
 }
 
-// one curve point in wire form (64 bytes X||Y, zeros = infinity)
+// one curve point in wire form (64 bytes X||Y at a 16-byte aligned address, zeros = infinity)
 PA_HD void sha256_put_point(sha256_state &s, const unsigned char *p) {
+  u32 v[16];
+#if defined(__CUDA_ARCH__)
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t = q[i];
+    v[4 * i] = __byte_perm(t.x, 0, 0x0123); v[4 * i + 1] = __byte_perm(t.y, 0, 0x0123);
+    v[4 * i + 2] = __byte_perm(t.z, 0, 0x0123); v[4 * i + 3] = __byte_perm(t.w, 0, 0x0123);
+  }
+#else
+  for (int i = 0; i < 16; ++i) v[i] = ((u32)p[4 * i] << 24) | ((u32)p[4 * i + 1] << 16) | ((u32)p[4 * i + 2] << 8) | (u32)p[4 * i + 3];
+#endif
   u32 nz = 0;
-  for (int i = 0; i < 64; ++i) nz |= p[i];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) nz |= v[i];
   if (!nz) {
     sha256_put(s, 0);  // EC_POINT_point2oct of infinity is the single byte 00
     return;
   }
   sha256_put(s, 4);
-  sha256_put_bytes(s, p, 64);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sha256_put_be32(s, v[i]);
 }
 
 PA_HD void sha256_final(sha256_state &s, u32 digest[8]) {
-  u64 bits = ((u64)s.blocks * 64 + s.fill) * 8;
+  u64 bits = ((u64)s.blocks * 64 + s.pos * 4 + s.nb) * 8;
   sha256_put(s, 0x80);
-  while (s.fill != 56) sha256_put(s, 0);
-  s.w[14] = (u32)(bits >> 32);
-  s.w[15] = (u32)bits;
-  sha256_compress(s.h, s.w);
+  while (s.nb != 0) sha256_put(s, 0);
+  while (s.pos != 14) sha256_emit(s, 0);
+  sha256_emit(s, (u32)(bits >> 32));
+  sha256_emit(s, (u32)bits);
 #pragma unroll
   for (int i = 0; i < 8; ++i) digest[i] = s.h[i];
 }
@@ -132,7 +163,11 @@ PA_HD void wire_generator(unsigned char g[64]) {
 PA_HD void challenge_hash(sc &h, const unsigned char *const *pts, int k, u64 id) {
   sha256_state s;
   sha256_init(s);
-  unsigned char g[64];
+#if defined(__CUDACC__)
+  __align__(16) unsigned char g[64];
+#else
+  alignas(16) unsigned char g[64];
+#endif
   wire_generator(g);
   sha256_put_point(s, g);
   for (int i = 0; i < k; ++i) sha256_put_point(s, pts[i]);
