@@ -190,75 +190,6 @@ k_seal_candidates(const unsigned char *Y, const unsigned char *rnd1, const u32 *
   st_jac(jout + 24 * ((size_t)i * 2 + which), r);
 }
 
-// state[0] = junction flag, state[1] = previous deciding step (-1: none), state[2] = next step to run,
-// state[3] = the first deciding step.
-// Walks steps [state[2], limit).  While `speculative` the keys were drawn on the assumption that no
-// junction has happened; they stay valid up to and including the step after the first deciding step
-// (its draws come after stage-1 proofs only), so the walk stops there.        SEAL/bidder.cpp:1301-1309, 1386-1421
-__global__ void __launch_bounds__(PA_SCAN_T)
-k_seal_decide(int m, int limit, int speculative, const unsigned char *bits, const u32 *boff, const unsigned char *cand,
-              unsigned char *prevbit, int *state, unsigned char *ebit, unsigned char *bj, unsigned char *b, int *stage,
-              int *prevstep, int *r3) {
-  __shared__ __align__(16) u32 part[PA_SCAN_T][24];
-  __shared__ int s_junc, s_last, s_deciding;
-  int t = threadIdx.x;
-  if (t == 0) s_junc = state[0], s_last = state[1];
-  __syncthreads();
-  int s = state[2];
-  for (; s < limit; ++s) {
-    int junc = s_junc;
-    jac acc;
-    jac_set_inf(acc);
-    for (int p = t; p < m; p += PA_SCAN_T) {
-      size_t i = (size_t)s * m + p;
-      int bit = bits[boff[p] + s];
-      int pb = prevbit[p];
-      int veto = bit && (!junc || pb);
-      ebit[i] = (unsigned char)veto;
-      bj[i] = (unsigned char)pb;
-      const unsigned char *src = cand + 64 * (2 * i + veto);
-      cp64(b + 64 * i, src);
-      aff x;
-      ld_aff(x, src);
-      jac_madd(acc, acc, x);
-    }
-    st_jac(part[t], acc);
-    __syncthreads();
-    for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
-      if (t < d) {
-        jac a, c;
-        ld_jac(a, part[t]);
-        ld_jac(c, part[t + d]);
-        jac_add(a, a, c);
-        st_jac(part[t], a);
-      }
-      __syncthreads();
-    }
-    if (t == 0) {
-      jac a;
-      ld_jac(a, part[0]);
-      s_deciding = jac_is_inf(a) ? 0 : 1;
-      stage[s] = junc ? 2 : 1;
-      prevstep[s] = s_last;
-      r3[s] = s_deciding;
-    }
-    __syncthreads();
-    bool stop = false;
-    if (s_deciding) {
-      for (int p = t; p < m; p += PA_SCAN_T) prevbit[p] &= bits[boff[p] + s];
-      if (speculative && !junc) stop = true;  // first deciding step: one more step is still valid
-      __syncthreads();
-      if (t == 0) {
-        if (!junc) state[3] = s;  // the junction
-        s_junc = 1, s_last = s;
-      }
-    }
-    __syncthreads();
-    if (stop && limit > s + 2) limit = s + 2;
-  }
-  if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
-}
-
 // statements and witnesses of the round-two proofs of every item; stage-1 items are the first n1
 __global__ void k_seal_stmt_items(int m, int n1, const int *stage, const int *prevstep, const u32 *boff, const unsigned char *b,
                                   const unsigned char *r1, const unsigned char *Y, const unsigned char *rnd1,
@@ -540,40 +471,138 @@ k_y_scan_shard(const unsigned char *X, size_t xstride, int m, int s0, unsigned c
   }
 }
 
-// k_seal_decide for a rank that holds a slice: one block walks steps [state[2], limit); per step it selects
-// and sums its own cryptograms, PUTS the sum, GETS every rank's sum, folds them and takes the decision all
-// ranks take alike.  The exchange happens inside the kernel, once per step.   SEAL/bidder.cpp:1301-1309, 1386-1421
+// ---- the walk, restated so that its sequential part shrinks with the race ---------------------------------
+// Round three asks whether S(s) = sum_p b_p(s) is infinity (SEAL/bidder.cpp:1393-1397), where b_p(s) is the veto
+// candidate R^x for the bidders that veto - those still in the race (prevDecidingBit = 1, initially everybody)
+// whose bit at step s is 1 - and the other candidate Y^x for everybody else (:1301-1309).  Hence
+//     S(s) = SY(s) + sum_{p in race, bit_p(s) = 1} D_p(s),   SY(s) = sum_p Y_p^x,   D_p(s) = R_p^x - Y_p^x.
+// SY(s) does not depend on the state of the auction: k_seal_sum_y adds it up for every step of a pass at once,
+// one block per step.  What is left for the sequential walk is the sum over the vetoing bidders, a tree whose
+// depth is log2 of the number of bidders still in the race; that number halves (random bids) at every deciding
+// step, so after ten deciding steps of a 1000-bidder auction a step costs a couple of additions.  The same
+// group element is tested as before, so the decisions are the same.  The walk only keeps the race (a compacted
+// list) and notes at which step each bidder left it (`elim`); what each bidder publishes at each step follows from
+// that and is written by k_seal_select, in parallel, afterwards.
+#define PA_WALK_T 256
 __global__ void __launch_bounds__(PA_SCAN_T)
-k_seal_walk_shard(int m, int limit, int speculative, const unsigned char *bits, const u32 *boff, const unsigned char *cand,
-                  unsigned char *prevbit, int *state, unsigned char *ebit, unsigned char *bj, unsigned char *b, int *stage,
-                  int *prevstep, int *r3, unsigned char *const *peers, int world, int rank, int par, u32 tag, int *err) {
+k_seal_sum_y(int m, int s0, const unsigned char *cand, u32 *sumy) {
   __shared__ __align__(16) u32 part[PA_SCAN_T][24];
-  __shared__ __align__(16) u32 tot[PA_XCHG_MAX_WORLD][24];
-  __shared__ int s_junc, s_last, s_deciding;
-  int t = threadIdx.x;
-  if (t == 0) s_junc = state[0], s_last = state[1];
+  const int s = s0 + blockIdx.x, t = threadIdx.x;
+  jac acc;
+  jac_set_inf(acc);
+  for (int p = t; p < m; p += PA_SCAN_T) {
+    aff x;
+    ld_aff(x, cand + 128 * ((size_t)s * m + p));
+    jac_madd(acc, acc, x);
+  }
+  st_jac(part[t], acc);
   __syncthreads();
+  for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
+    if (t < d) {
+      jac a, c;
+      ld_jac(a, part[t]);
+      ld_jac(c, part[t + d]);
+      jac_add(a, a, c);
+      st_jac(part[t], a);
+    }
+    __syncthreads();
+  }
+  if (t < 24) sumy[24 * (size_t)s + t] = part[0][t];
+}
+
+// block-wide: race1 = the entries p of race0[0..R) with keep(p); returns the new count (the same in every thread).
+// Dropped entries get elim[p] = s.  Order is preserved.
+PA_D int walk_compact(const u32 *race0, u32 *race1, int R, int s, const unsigned char *bits, const u32 *boff, u32 *elim,
+                      int *s_warp, int *s_total) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = PA_WALK_T / 32;
+  int base = 0;
+  for (int k0 = 0; k0 < R; k0 += PA_WALK_T) {
+    const int k = k0 + t;
+    u32 p = 0;
+    int keep = 0;
+    if (k < R) {
+      p = race0[k];
+      keep = bits[boff[p] + s] ? 1 : 0;
+      if (!keep) elim[p] = (u32)s;
+    }
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (keep) race1[off + __popc(mask & ((1u << lane) - 1u))] = p;
+    int tot = 0;
+    for (int w = 0; w < nw; ++w) tot += s_warp[w];
+    base += tot;
+    __syncthreads();
+  }
+  if (t == 0) *s_total = base;
+  __syncthreads();
+  return *s_total;
+}
+
+// state[0] = junction flag, state[1] = previous deciding step (-1: none), state[2] = next step to run,
+// state[3] = the first deciding step.  Walks steps [state[2], limit); while `speculative` it stops one step after the
+// first deciding step (the keys of later steps were drawn on counters that are no longer right).
+// SHARDED: this rank holds m of the bidders; per step the ranks' sums (24 words) are PUT into every peer's window and
+// folded, so that all ranks take the same decision.
+// race: 2 * m words of scratch; elim[p]: the deciding step at which bidder p left the race (0xFFFFFFFF: still in).
+template <bool SHARDED>
+__global__ void __launch_bounds__(PA_WALK_T)
+k_seal_walk(int m, int limit, int speculative, const unsigned char *bits, const u32 *boff, const unsigned char *cand,
+            const u32 *sumy, unsigned char *prevbit, u32 *elim, u32 *race, int *state, int *stage, int *prevstep, int *r3,
+            unsigned char *const *peers, int world, int rank, int par, u32 tag, int *err) {
+  __shared__ __align__(16) u32 part[PA_WALK_T][24];
+  __shared__ __align__(16) u32 tot[PA_XCHG_MAX_WORLD][24];
+  __shared__ int s_warp[PA_WALK_T / 32], s_total, s_junc, s_last, s_deciding;
+  const int t = threadIdx.x;
+  if (t == 0) s_junc = state[0], s_last = state[1];
+  // the race as a compact list, from the flags the previous pass left
+  u32 *r0 = race, *r1 = race + m;
+  {
+    const int lane = t & 31, warp = t >> 5, nw = PA_WALK_T / 32;
+    int base = 0;
+    for (int k0 = 0; k0 < m; k0 += PA_WALK_T) {
+      const int p = k0 + t;
+      const int keep = (p < m && prevbit[p]) ? 1 : 0;
+      const unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
+      if (lane == 0) s_warp[warp] = __popc(mask);
+      __syncthreads();
+      int off = base;
+      for (int w = 0; w < warp; ++w) off += s_warp[w];
+      if (keep) r0[off + __popc(mask & ((1u << lane) - 1u))] = (u32)p;
+      for (int w = 0; w < nw; ++w) base += s_warp[w];
+      __syncthreads();
+    }
+    if (t == 0) s_total = base;
+    __syncthreads();
+  }
+  int R = s_total;
   int s = state[2];
   for (; s < limit; ++s) {
-    int junc = s_junc;
+    const int junc = s_junc;
+    // this rank's sum over its vetoing bidders
     jac acc;
     jac_set_inf(acc);
-    for (int p = t; p < m; p += PA_SCAN_T) {
-      size_t i = (size_t)s * m + p;
-      int bit = bits[boff[p] + s];
-      int pb = prevbit[p];
-      int veto = bit && (!junc || pb);
-      ebit[i] = (unsigned char)veto;
-      bj[i] = (unsigned char)pb;
-      const unsigned char *src = cand + 64 * (2 * i + veto);
-      cp64(b + 64 * i, src);
-      aff x;
-      ld_aff(x, src);
-      jac_madd(acc, acc, x);
+    for (int k = t; k < R; k += PA_WALK_T) {
+      const u32 p = r0[k];
+      if (bits[boff[p] + s]) {
+        const unsigned char *c2 = cand + 128 * ((size_t)s * m + p);
+        aff y, v;
+        ld_aff(y, c2);
+        ld_aff(v, c2 + 64);
+        aff_neg(y, y);
+        jac d;
+        jac_from_aff(d, v);
+        jac_madd(d, d, y);  // D = R^x - Y^x
+        jac_add(acc, acc, d);
+      }
     }
-    st_jac(part[t], acc);
+    int width = 1;
+    while (width < R && width < PA_WALK_T) width <<= 1;
+    if (t < width) st_jac(part[t], acc);
     __syncthreads();
-    for (int d = PA_SCAN_T / 2; d > 0; d >>= 1) {
+    for (int d = width / 2; d > 0; d >>= 1) {
       if (t < d) {
         jac a, c;
         ld_jac(a, part[t]);
@@ -583,24 +612,34 @@ k_seal_walk_shard(int m, int limit, int speculative, const unsigned char *bits, 
       }
       __syncthreads();
     }
-    xchg_put(peers, world, 1, par, s, rank, part[0], tag);
-    if (!xchg_get(peers[rank], world, 1, par, s, tag, tot, err)) {
-      if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
-      return;
+    if (t == 0) {  // + the state-independent part of this step
+      jac a, c;
+      ld_jac(a, part[0]);
+      ld_jac(c, sumy + 24 * (size_t)s);
+      jac_add(a, a, c);
+      st_jac(part[0], a);
     }
-    for (int d = PA_XCHG_MAX_WORLD / 2; d > 0; d >>= 1) {  // fold the ranks' sums
-      if (t < d && t + d < world) {
-        jac a, c;
-        ld_jac(a, tot[t]);
-        ld_jac(c, tot[t + d]);
-        jac_add(a, a, c);
-        st_jac(tot[t], a);
+    __syncthreads();
+    if (SHARDED) {
+      xchg_put(peers, world, 1, par, s, rank, part[0], tag);
+      if (!xchg_get(peers[rank], world, 1, par, s, tag, tot, err)) {
+        if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
+        return;
       }
-      __syncthreads();
+      for (int d = PA_XCHG_MAX_WORLD / 2; d > 0; d >>= 1) {  // fold the ranks' sums
+        if (t < d && t + d < world) {
+          jac a, c;
+          ld_jac(a, tot[t]);
+          ld_jac(c, tot[t + d]);
+          jac_add(a, a, c);
+          st_jac(tot[t], a);
+        }
+        __syncthreads();
+      }
     }
     if (t == 0) {
       jac a;
-      ld_jac(a, tot[0]);
+      ld_jac(a, SHARDED ? tot[0] : part[0]);
       s_deciding = jac_is_inf(a) ? 0 : 1;
       stage[s] = junc ? 2 : 1;
       prevstep[s] = s_last;
@@ -609,9 +648,11 @@ k_seal_walk_shard(int m, int limit, int speculative, const unsigned char *bits, 
     __syncthreads();
     bool stop = false;
     if (s_deciding) {
-      for (int p = t; p < m; p += PA_SCAN_T) prevbit[p] &= bits[boff[p] + s];
+      R = walk_compact(r0, r1, R, s, bits, boff, elim, s_warp, &s_total);  // who vetoed stays in the race
+      u32 *sw = r0;
+      r0 = r1;
+      r1 = sw;
       if (speculative && !junc) stop = true;  // first deciding step: one more step is still valid
-      __syncthreads();
       if (t == 0) {
         if (!junc) state[3] = s;  // the junction
         s_junc = 1, s_last = s;
@@ -620,7 +661,24 @@ k_seal_walk_shard(int m, int limit, int speculative, const unsigned char *bits, 
     __syncthreads();
     if (stop && limit > s + 2) limit = s + 2;
   }
+  // the flags for the next pass
+  for (int p = t; p < m; p += PA_WALK_T) prevbit[p] = elim[p] == 0xFFFFFFFFu ? 1 : 0;
   if (t == 0) state[0] = s_junc, state[1] = s_last, state[2] = s;
+}
+
+// what every bidder publishes at the steps [s0, min(s1, state[2])) the walk has been through: it vetoes iff it is still
+// in the race (it left at step elim[p], i.e. it was in for every step <= elim[p]) and its bit is 1     SEAL/bidder.cpp:1301-1309
+__global__ void k_seal_select(int m, int s0, int s1, const int *state, const unsigned char *bits, const u32 *boff, const u32 *elim,
+                              const unsigned char *cand, unsigned char *ebit, unsigned char *bj, unsigned char *b) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = s0 + k / m, p = k % m;
+  if (s >= s1 || s >= state[2]) return;
+  const size_t i = (size_t)s * m + p;
+  const int pb = elim[p] >= (u32)s ? 1 : 0;
+  const int veto = (bits[boff[p] + s] && pb) ? 1 : 0;
+  ebit[i] = (unsigned char)veto;
+  bj[i] = (unsigned char)pb;
+  cp64(b + 64 * i, cand + 64 * (2 * i + veto));
 }
 
 // end of a sharded run: every rank PUTS (draws clean, verdict, max bid) and reads everybody's; out = the AND
@@ -836,6 +894,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     unsigned char *rnd1, *r1, *pokv, *r1ok, *Y, *cand, *b, *ebit, *bj, *stmt, *sec, *bi, *bjp, *cbp, *rnd2, *proof, *r2ok;
     unsigned char *Xall, *Yall, *part;  // sharded: every bidder's X / Y of every step; the ranks' partial sums of a step
     u32 *gidx, *lidx, *soffN;
+    u32 *sumy, *elim, *race;  // per step: sum of the no-veto candidates; per bidder: step at which it left the race; scratch
   } PH{};
   unsigned char *d_xsend = nullptr;  // peer window: staging of this rank's part of a plain all-gather
   u64 *d_xfinal = nullptr;
@@ -855,6 +914,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       PH.bi = pool.alloc<unsigned char>(T + 256); PH.bjp = pool.alloc<unsigned char>(T + 256); PH.cbp = pool.alloc<unsigned char>(T + 256);
       PH.rnd2 = pool.alloc<unsigned char>(T * 352 + 256); PH.proof = pool.alloc<unsigned char>(T * 1344 + 256);
       PH.r2ok = pool.alloc<unsigned char>(T + 256);
+      PH.sumy = pool.alloc<u32>(cmax * 24 + 8); PH.elim = pool.alloc<u32>(m); PH.race = pool.alloc<u32>(2 * m + 8);
       if (sharded && !p2p) {
         PH.Xall = pool.alloc<unsigned char>(cmax * nall * 64); PH.Yall = pool.alloc<unsigned char>(cmax * nall * 64);
         PH.gidx = pool.alloc<u32>(cmax * nall); PH.lidx = pool.alloc<u32>(T); PH.soffN = pool.alloc<u32>(cmax + 1);
@@ -908,6 +968,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       (rc = up(ctx, d_streams, streams)) || (rc = up(ctx, d_cid, cid)))
     return rc;
   PA_CUDA(ctx, cudaMemsetAsync(d_prevbit, 1, m, ctx->stream));  // prevDecidingBit(1), SEAL/bidder.cpp:23
+  if (phased) PA_CUDA(ctx, cudaMemsetAsync(PH.elim, 0xFF, m * sizeof(u32), ctx->stream));  // nobody has left the race
   PA_CUDA(ctx, cudaMemsetAsync(d_r1ok, 1, cmax * m, ctx->stream));
   PA_CUDA(ctx, cudaMemsetAsync(d_r2ok, 1, cmax * m, ctx->stream));
 
@@ -964,18 +1025,23 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     std::vector<u64> after(Mb);
     PA_CUDA(ctx, cudaMemcpyAsync(after.data(), d_sctr, Mb * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (size_t s = 0; s < m; ++s) {
-      bool clean = true;
-      for (u32 k = boff[s]; k < boff[s + 1]; ++k) clean &= after[k] == sctr[k] + 7;
-      u64 cnt = 7ull * (boff[s + 1] - boff[s]);
-      if (!clean) draws_clean = false;  // a rejected draw (probability 2^-128): counters are no longer arithmetic
-      if (!clean) {
-        u64 zero = 0;
-        PA_CUDA(ctx, cudaMemcpyAsync(d_ctr + s, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
-        PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<1, 1, 0, ctx->stream>>>(job->seed, d_streams + s, d_ctr + s, nullptr, (int)cnt, d_rndc + 224 * (size_t)boff[s], 1)));
-      } else {
-        PA_CUDA(ctx, cudaMemcpyAsync(d_ctr + s, &cnt, 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+      // every bidder's stream counter after the commit phase, in ONE upload (a copy per bidder cost 1.5 ms at n = 1000);
+      // bidders with a rejected draw are redone one by one afterwards
+      std::vector<u64> ctr_after(m);
+      std::vector<size_t> redo;
+      for (size_t s = 0; s < m; ++s) {
+        bool clean = true;
+        for (u32 k = boff[s]; k < boff[s + 1]; ++k) clean &= after[k] == sctr[k] + 7;
+        ctr_after[s] = clean ? 7ull * (boff[s + 1] - boff[s]) : 0;
+        if (!clean) draws_clean = false, redo.push_back(s);  // a rejected draw (probability 2^-128): counters are no longer arithmetic
       }
+      if ((rc = up(ctx, d_ctr, ctr_after))) return rc;
+      for (size_t s : redo) {
+        u64 cnt = 7ull * (boff[s + 1] - boff[s]);
+        PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<1, 1, 0, ctx->stream>>>(job->seed, d_streams + s, d_ctr + s, nullptr, (int)cnt, d_rndc + 224 * (size_t)boff[s], 1)));
+      }
+      PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // ctr_after goes out of scope
     }
     // commitment points, their Schnorr proofs (A: alpha, v_A; B: beta, v_B; 2 per record, one batch), the OR proof,
     // and the verification of all of it
@@ -1096,10 +1162,16 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
       PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.Y + 64 * i0, PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.cand + 128 * i0, 2 * cnt))) return rc2;
-      if (!sharded)
-        PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_decide<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3)));
-      else if (p2p)  // the walk and the per-step exchange of the ranks' cryptogram sums are one kernel
-        PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_walk_shard<<<1, PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, d_prevbit, PH.state, PH.ebit, PH.bj, PH.b, PH.stage, PH.prevstep, PH.r3, xpeers, xworld, xrank, xpar, (xepoch << 8) | xpass, xerr)));
+      if (!sharded || p2p) {
+        // the state-independent part of every step's sum at once, the walk over what depends on the race, and then what
+        // each bidder publishes at the steps walked (see "the walk, restated")
+        PA_LAUNCH(ctx, PA_K_YSCAN, (k_seal_sum_y<<<(unsigned)(s1 - s0), PA_SCAN_T, 0, ctx->stream>>>((int)m, (int)s0, PH.cand, PH.sumy)));
+        if (!sharded)
+          PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_walk<false><<<1, PA_WALK_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, PH.sumy, d_prevbit, PH.elim, PH.race, PH.state, PH.stage, PH.prevstep, PH.r3, nullptr, 1, 0, 0, 0u, nullptr)));
+        else  // the walk and the per-step exchange of the ranks' cryptogram sums are one kernel
+          PA_LAUNCH(ctx, PA_K_SUMINF, (k_seal_walk<true><<<1, PA_WALK_T, 0, ctx->stream>>>((int)m, (int)s1, speculative, d_bits, d_boff, PH.cand, PH.sumy, d_prevbit, PH.elim, PH.race, PH.state, PH.stage, PH.prevstep, PH.r3, xpeers, xworld, xrank, xpar, (xepoch << 8) | xpass, xerr)));
+        PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_select<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>((int)m, (int)s0, (int)s1, PH.state, d_bits, d_boff, PH.elim, PH.cand, PH.ebit, PH.bj, PH.b)));
+      }
       return PA_OK;
     };
     int st[4];
