@@ -55,6 +55,7 @@ struct pa_ctx {
     int *d_err = nullptr;                // set by a kernel whose wait for a peer timed out
   } xchg;
   // optional per-kernel CUDA-event timing (pa_profile_begin / pa_profile_end)
+  int prio_main = 0;                   // priority of `stream` (the greatest the device offers)
   bool profiling = false;
   struct Span { int kid; cudaEvent_t e0, e1; cudaStream_t st; };
   std::vector<Span> spans;
@@ -201,7 +202,13 @@ int pa_ctx_create(pa_ctx **out, int device) {
   };
   int cur = -1;
   if ((e = cudaGetDevice(&cur)) != cudaSuccess || cur != device) return fail("cudaSetDevice", e != cudaSuccess ? e : cudaErrorInvalidDevice);
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  // The context's own stream carries the sequential chain of a run (keys -> Y scan -> cryptograms -> walk); the side
+  // lanes of the runners (proofs, verification: bulk work without a successor) are created at the lowest priority, so
+  // that blocks of the chain are placed first whenever SM slots free up.
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  ctx->prio_main = prio_greatest;
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaMalloc((void **)&ctx->d_comb, PA_COMB_WORDS * sizeof(u32))) != cudaSuccess) return fail("cudaMalloc(comb)", e);
   if ((e = cudaMalloc((void **)&d_bases, PA_COMB_WINDOWS * 16 * sizeof(u32))) != cudaSuccess) return fail("cudaMalloc(bases)", e);
   k_comb_base<<<1, 32, 0, ctx->stream>>>(d_bases);
@@ -490,7 +497,7 @@ int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
   if (!ctx->s_in) {
     PA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     PA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-    PA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_alt, cudaStreamNonBlocking));
+    PA_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_alt, cudaStreamNonBlocking, ctx->prio_main));  // alternates with the main stream
     for (int i = 0; i < 3; ++i) {
       PA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
       PA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
