@@ -21,6 +21,7 @@ fixed-base kernel.  One step = one pass over that batch.
 """
 import argparse
 import importlib
+import ctypes
 import json
 import os
 import statistics
@@ -620,21 +621,38 @@ def main():
     h_out_f = torch.empty(64 * n, dtype=torch.uint8).pin_memory()
     h_out_v = torch.empty(64 * n, dtype=torch.uint8).pin_memory()
 
+    # one call for the step's two batches (pa_scalar_mul_jobs: the chunks of the two jobs share one copy/compute pipeline, so
+    # the copy-heavy fixed-base batch hides behind the compute-heavy variable-base one) ...
+    E_ = importlib.import_module("privacy-auction_b200.engine")
+    mj = (E_.MulJob * 2)()
+    mj[0].kind, mj[0].a, mj[0].out, mj[0].n = E_.MUL_FIXED, h_kf.data_ptr(), h_out_f.data_ptr(), n
+    mj[1].kind, mj[1].p, mj[1].a, mj[1].out, mj[1].n = E_.MUL_VAR, h_bases.data_ptr(), h_kv.data_ptr(), h_out_v.data_ptr(), n
+
     def step_e2e():
+        eng._check(eng.lib.pa_scalar_mul_jobs(eng.ctx, ctypes.addressof(mj), 2))
+
+    # ... and the same work as two calls, one after the other (the r01 figure)
+    def step_e2e_two_calls():
         eng._check(eng.lib.pa_fixed_base_mul(eng.ctx, h_kf.data_ptr(), h_out_f.data_ptr(), n))
         eng._check(eng.lib.pa_var_base_mul(eng.ctx, h_bases.data_ptr(), h_kv.data_ptr(), h_out_v.data_ptr(), n))
 
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
+    def time_e2e(step):
+        step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return 2.0 * n * world * e2e_steps / float(dt.item())
+
     e2e_steps = max(1, args.steps)
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = 2.0 * n * world * e2e_steps / float(e2e_s.item())
+    e2e_two_calls = time_e2e(step_e2e_two_calls)
+    h_out_f.zero_()
+    h_out_v.zero_()
+    e2e_value = time_e2e(step_e2e)
     # the e2e result must be the same bytes as the device-resident run
     same = bool(torch.equal(h_out_v.cuda(), t_out_v)) and bool(torch.equal(h_out_f.cuda(), t_out_f))
 
@@ -668,7 +686,11 @@ def main():
                        "l2": "working set per step ~270 MB (scalars, bases, affine outputs) > 126 MB L2; kernels are integer-pipe bound"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n, "d2h_bytes_per_step": 128 * n,
-                    "steps": e2e_steps, "bytes_match_device_run": same, "host_cores_pinned_per_rank": pinned_cores},
+                    "steps": e2e_steps, "bytes_match_device_run": same, "host_cores_pinned_per_rank": pinned_cores,
+                    "call": "pa_scalar_mul_jobs (both batches of the step in one pipelined call, host buffers in and out)",
+                    "two_calls_value": e2e_two_calls,
+                    "two_calls_note": "pa_fixed_base_mul then pa_var_base_mul (r01's e2e): with 8 ranks on one host the fixed-base call is bound by the "
+                                      "shared device-to-host path (11 GiB/s per rank with all ranks copying, profiles/r02f_e2e_probe8.txt)"},
             "gpu_launches": int(launches),
             # The path is 256-bit integer arithmetic: neither HBM nor the tensor cores bound it, the
             # integer multiply pipe does ("fmaheavy" in ncu).  achieved = executed 32x32->64 multiply-adds

@@ -136,6 +136,21 @@ int pa_double_mul_dev(pa_ctx *ctx, const uint8_t *d_a, const uint8_t *d_points, 
 int pa_lincomb2(pa_ctx *ctx, const uint8_t *p, const uint8_t *a, const uint8_t *q, const uint8_t *b, uint8_t *out, size_t n);
 int pa_lincomb2_dev(pa_ctx *ctx, const uint8_t *d_p, const uint8_t *d_a, const uint8_t *d_q, const uint8_t *d_b, uint8_t *d_out, size_t n);
 
+/* Several scalar-multiplication batches in ONE call (host buffers): what a caller gets from issuing pa_fixed_base_mul /
+ * pa_var_base_mul / pa_double_mul / pa_lincomb2 one after the other (e.g. the g^x of Bidder::roundOne, SEAL/bidder.cpp:
+ * 1217-1218, and the Y^x of roundTwo, :1303), with the chunks of the jobs interleaved in one copy/compute pipeline: the
+ * copies of a copy-heavy job (fixed base: 96 bytes per 2 us of GPU time) hide behind the kernels of a compute-heavy one
+ * (variable base).  On a host whose memory path is shared by 8 GPUs this is what keeps the end-to-end rate at the kernels'
+ * (profiles/r02f_e2e_probe8.txt).  kind FIXED: out = a*G; VAR: out = a*p; DOUBLE: out = a*G + b*p; LINCOMB2: out = a*p + b*q. */
+typedef struct {
+  int kind;
+  const uint8_t *a, *p, *b, *q;   /* scalars 32 B each, points 64 B each; unused ones NULL */
+  uint8_t *out;                   /* n x 64 B */
+  size_t n;
+} pa_mul_job;
+enum { PA_MUL_FIXED = 0, PA_MUL_VAR = 1, PA_MUL_DOUBLE = 2, PA_MUL_LINCOMB2 = 3 };
+int pa_scalar_mul_jobs(pa_ctx *ctx, const pa_mul_job *jobs, size_t njobs);
+
 /* out[i] = p[i] + q[i] (sub != 0: p[i] - q[i]).   EC_POINT_add / EC_POINT_invert,
  * SEAL/bidder.cpp:130, 178-180 */
 int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, int sub);

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -492,8 +493,23 @@ struct PArg {
 const size_t PA_PIPE_UNIT = (size_t)148 * PA_BLOCK;
 const size_t PA_PIPE_CHUNK = PA_PIPE_UNIT * PA_PIPE_CHUNK_BLOCKS, PA_PIPE_EDGE = PA_PIPE_UNIT * PA_PIPE_EDGE_BLOCKS;
 
-template <typename F>
-int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
+// One job of a pipelined call: n items, its per-item arguments, and the device-pointer implementation.
+struct PJob {
+  size_t n;
+  PArg args[6];
+  int nargs;
+  std::function<int(unsigned char **, size_t)> run;
+};
+struct PChunk {
+  int job;
+  size_t off, cnt;
+  double pos;  // middle of the chunk as a fraction of its job: chunks of several jobs are interleaved by this
+};
+
+// Several jobs in ONE copy/compute pipeline: the chunks of the jobs are interleaved (by their relative position in their
+// job), so that the copies of a copy-heavy job (fixed base: 96 bytes per 2 us of GPU time) hide behind the kernels of a
+// compute-heavy one (variable base: 160 bytes per 17 us).  Results are those of running the jobs one after the other.
+int pipelined_jobs(pa_ctx *ctx, std::vector<PJob> &jobs) {
   if (!ctx->s_in) {
     PA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     PA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -515,10 +531,32 @@ int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
       cudaStreamSynchronize(c->s_out);
     }
   } drain{ctx, ctx->stream};
-  const size_t CH = n < PA_PIPE_CHUNK ? n : PA_PIPE_CHUNK;
-  size_t slot_bytes = 1024;
-  for (int i = 0; i < nargs; ++i) slot_bytes += align_up(args[i].per * CH, 256);
-  const int slots = n > CH ? 3 : 1;
+  // chunks: whole waves; a job longer than one chunk starts and ends with a short one (the first copy in and the last
+  // copy out of a call are not hidden by anything)
+  std::vector<PChunk> chunks;
+  size_t nmax = 0, slot_bytes = 1024;
+  for (size_t j = 0; j < jobs.size(); ++j) {
+    const PJob &J = jobs[j];
+    nmax = J.n > nmax ? J.n : nmax;
+    const size_t CHj = J.n < PA_PIPE_CHUNK ? J.n : PA_PIPE_CHUNK;
+    size_t bytes = 1024;
+    for (int i = 0; i < J.nargs; ++i) bytes += align_up(J.args[i].per * CHj, 256);
+    slot_bytes = bytes > slot_bytes ? bytes : slot_bytes;
+    size_t k = 0, cnt = 0;
+    for (size_t off = 0; off < J.n; off += cnt, ++k) {
+      const size_t left = J.n - off;
+      if (J.n <= PA_PIPE_CHUNK) cnt = J.n;
+      else if (k == 0) cnt = PA_PIPE_EDGE;
+      else if (left > PA_PIPE_CHUNK + PA_PIPE_EDGE) cnt = PA_PIPE_CHUNK;
+      else if (left > PA_PIPE_EDGE) cnt = left - PA_PIPE_EDGE;
+      else cnt = left;
+      chunks.push_back(PChunk{(int)j, off, cnt, ((double)off + 0.5 * (double)cnt) / (double)J.n});
+    }
+  }
+  if (chunks.empty()) return PA_OK;
+  std::stable_sort(chunks.begin(), chunks.end(), [](const PChunk &a, const PChunk &b) { return a.pos < b.pos; });
+  const size_t CH = nmax < PA_PIPE_CHUNK ? nmax : PA_PIPE_CHUNK;
+  const int slots = chunks.size() > 1 ? 3 : 1;
   int rc = stage_reserve(ctx, slot_bytes * slots + 1024);
   if (rc) return rc;
   if ((rc = work_reserve(ctx, CH))) return rc;  // no arena growth (= sync) inside the pipeline
@@ -529,51 +567,57 @@ int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
     std::swap(ctx->d_work, ctx->d_work_alt);
     std::swap(ctx->work_bytes, ctx->work_alt_bytes);
   };
-  if (n > CH) {
+  if (chunks.size() > 1) {
     swap_alt();
     rc = work_reserve(ctx, CH);
     swap_alt();
     if (rc) return rc;
   }
-  size_t k = 0, cnt = 0;
-  for (size_t off = 0; off < n; off += cnt, ++k) {
-    const size_t left = n - off;
-    if (n <= CH) cnt = n;
-    else if (k == 0) cnt = PA_PIPE_EDGE;                                  // short head: first copy in is exposed
-    else if (left > CH + PA_PIPE_EDGE) cnt = CH;
-    else if (left > PA_PIPE_EDGE) cnt = left - PA_PIPE_EDGE;              // leave a short tail: last copy out is exposed
-    else cnt = left;
+  for (size_t k = 0; k < chunks.size(); ++k) {
+    const PChunk &C = chunks[k];
+    const PJob &J = jobs[C.job];
+    const size_t CHj = J.n < PA_PIPE_CHUNK ? J.n : PA_PIPE_CHUNK;
     const int slot = (int)(k % slots);
     unsigned char *base = ctx->d_stage + slot_bytes * slot, *d[16];
     size_t o = 0;
-    for (int i = 0; i < nargs; ++i) {
+    for (int i = 0; i < J.nargs; ++i) {
       d[i] = base + o;
-      o += align_up(args[i].per * CH, 256);
+      o += align_up(J.args[i].per * CHj, 256);
     }
     if (k >= (size_t)slots) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[slot], 0));  // slot free again
-    for (int i = 0; i < nargs; ++i)
-      if (args[i].in)
-        PA_CUDA(ctx, cudaMemcpyAsync(d[i], (const unsigned char *)args[i].in + args[i].per * off, args[i].per * cnt, cudaMemcpyHostToDevice, ctx->s_in));
+    for (int i = 0; i < J.nargs; ++i)
+      if (J.args[i].in)
+        PA_CUDA(ctx, cudaMemcpyAsync(d[i], (const unsigned char *)J.args[i].in + J.args[i].per * C.off, J.args[i].per * C.cnt, cudaMemcpyHostToDevice, ctx->s_in));
     PA_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
     const bool alt = (k & 1) != 0;
     if (alt) swap_alt();
     cudaError_t e1 = cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0);
-    rc = e1 == cudaSuccess ? run(d, cnt) : PA_OK;
+    rc = e1 == cudaSuccess ? J.run(d, C.cnt) : PA_OK;
     cudaError_t e2 = cudaEventRecord(ctx->ev_comp[slot], ctx->stream);
     if (alt) swap_alt();
     PA_CUDA(ctx, e1);
     if (rc) return rc;
     PA_CUDA(ctx, e2);
     PA_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0));
-    for (int i = 0; i < nargs; ++i)
-      if (args[i].out)
-        PA_CUDA(ctx, cudaMemcpyAsync((unsigned char *)args[i].out + args[i].per * off, d[i], args[i].per * cnt, cudaMemcpyDeviceToHost, ctx->s_out));
+    for (int i = 0; i < J.nargs; ++i)
+      if (J.args[i].out)
+        PA_CUDA(ctx, cudaMemcpyAsync((unsigned char *)J.args[i].out + J.args[i].per * C.off, d[i], J.args[i].per * C.cnt, cudaMemcpyDeviceToHost, ctx->s_out));
     PA_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
   }
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->s_alt));
   PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PA_OK;
+}
+
+template <typename F>
+int pipelined(pa_ctx *ctx, size_t n, const PArg *args, int nargs, F run) {
+  std::vector<PJob> jobs(1);
+  jobs[0].n = n;
+  jobs[0].nargs = nargs;
+  for (int i = 0; i < nargs; ++i) jobs[0].args[i] = args[i];
+  jobs[0].run = run;
+  return pipelined_jobs(ctx, jobs);
 }
 }  // namespace
 
@@ -610,6 +654,48 @@ int pa_lincomb2(pa_ctx *ctx, const uint8_t *p, const uint8_t *a, const uint8_t *
   if (n == 0) return PA_OK;
   PArg g[] = {{p, 0, 64}, {a, 0, 32}, {q, 0, 64}, {b, 0, 32}, {0, out, 64}};
   return pipelined(ctx, n, g, 5, [&](unsigned char **d, size_t cnt) { return pa_lincomb2_dev(ctx, d[0], d[1], d[2], d[3], d[4], cnt); });
+}
+
+int pa_scalar_mul_jobs(pa_ctx *ctx, const pa_mul_job *jobs, size_t njobs) {
+  PA_ENTER(ctx);
+  PA_ARGCHECK(ctx, ctx && (njobs == 0 || jobs) && njobs <= 64);
+  std::vector<PJob> pj;
+  for (size_t j = 0; j < njobs; ++j) {
+    const pa_mul_job &m = jobs[j];
+    if (m.n == 0) continue;
+    PJob J;
+    J.n = m.n;
+    switch (m.kind) {
+      case PA_MUL_FIXED:
+        PA_ARGCHECK(ctx, m.a && m.out);
+        J.nargs = 2;
+        J.args[0] = PArg{m.a, 0, 32}; J.args[1] = PArg{0, m.out, 64};
+        J.run = [ctx](unsigned char **d, size_t cnt) { return pa_fixed_base_mul_dev(ctx, d[0], d[1], cnt); };
+        break;
+      case PA_MUL_VAR:
+        PA_ARGCHECK(ctx, m.p && m.a && m.out);
+        J.nargs = 3;
+        J.args[0] = PArg{m.p, 0, 64}; J.args[1] = PArg{m.a, 0, 32}; J.args[2] = PArg{0, m.out, 64};
+        J.run = [ctx](unsigned char **d, size_t cnt) { return pa_var_base_mul_dev(ctx, d[0], d[1], d[2], cnt); };
+        break;
+      case PA_MUL_DOUBLE:
+        PA_ARGCHECK(ctx, m.a && m.p && m.b && m.out);
+        J.nargs = 4;
+        J.args[0] = PArg{m.a, 0, 32}; J.args[1] = PArg{m.p, 0, 64}; J.args[2] = PArg{m.b, 0, 32}; J.args[3] = PArg{0, m.out, 64};
+        J.run = [ctx](unsigned char **d, size_t cnt) { return pa_double_mul_dev(ctx, d[0], d[1], d[2], d[3], cnt); };
+        break;
+      case PA_MUL_LINCOMB2:
+        PA_ARGCHECK(ctx, m.p && m.a && m.q && m.b && m.out);
+        J.nargs = 5;
+        J.args[0] = PArg{m.p, 0, 64}; J.args[1] = PArg{m.a, 0, 32}; J.args[2] = PArg{m.q, 0, 64}; J.args[3] = PArg{m.b, 0, 32}; J.args[4] = PArg{0, m.out, 64};
+        J.run = [ctx](unsigned char **d, size_t cnt) { return pa_lincomb2_dev(ctx, d[0], d[1], d[2], d[3], d[4], cnt); };
+        break;
+      default:
+        return pa_fail(ctx, PA_EINVAL, "pa_scalar_mul_jobs: unknown job kind");
+    }
+    pj.push_back(J);
+  }
+  return pipelined_jobs(ctx, pj);
 }
 
 int pa_point_add(pa_ctx *ctx, const uint8_t *p, const uint8_t *q, uint8_t *out, size_t n, int sub) {

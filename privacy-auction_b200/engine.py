@@ -103,6 +103,7 @@ SIGNATURES = {
     "pa_xchg_connect": (ctypes.c_int, [_ctx, _vp, ctypes.c_int, ctypes.c_int]),
     "pa_xchg_skip": (ctypes.c_int, [_ctx]),
     "pa_xchg_close": (ctypes.c_int, [_ctx]),
+    "pa_scalar_mul_jobs": (ctypes.c_int, [_ctx, _vp, _sz]),
     "pa_profile_begin": (ctypes.c_int, [_ctx]),
     "pa_profile_end": (ctypes.c_int, [_ctx, ctypes.c_void_p, _sz, ctypes.POINTER(_sz)]),
 }
@@ -113,6 +114,15 @@ class KernelStat(ctypes.Structure):
 
 
 ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int)
+
+
+class MulJob(ctypes.Structure):
+    """pa_mul_job (include/pa_engine.h)"""
+    _fields_ = [("kind", ctypes.c_int), ("a", ctypes.c_void_p), ("p", ctypes.c_void_p), ("b", ctypes.c_void_p), ("q", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("n", ctypes.c_size_t)]
+
+
+MUL_FIXED, MUL_VAR, MUL_DOUBLE, MUL_LINCOMB2 = 0, 1, 2, 3
 
 
 class SealJob(ctypes.Structure):
@@ -403,6 +413,26 @@ class Engine:
 
     def stage2_prove_w(self, stmt, secrets, bi, bj, cbit, ids, rnd):
         return self._run("pa_stage2_prove_w", (stmt, secrets, bytes(bi), bytes(bj), bytes(cbit), self._ids(ids), rnd), 1344 * len(ids), len(ids))
+
+    def scalar_mul_jobs(self, jobs):
+        """pa_scalar_mul_jobs: jobs = [(kind, dict(a=, p=, b=, q=), n)] with host byte strings; returns the outputs in order.
+        Same results as the single calls, one interleaved copy/compute pipeline."""
+        arr = (MulJob * len(jobs))()
+        keep, outs = [], []
+        for k, (kind, ops, n) in enumerate(jobs):
+            arr[k].kind, arr[k].n = kind, n
+            for name in ("a", "p", "b", "q"):
+                if ops.get(name) is not None:
+                    ptr, ref = _buf(ops[name])
+                    keep.append(ref)
+                    setattr(arr[k], name, ptr.value)
+            out = bytearray(64 * n)
+            ptr, ref = _buf(out)
+            keep.append(ref)
+            arr[k].out = ptr.value
+            outs.append(out)
+        self._check(self.lib.pa_scalar_mul_jobs(self.ctx, ctypes.addressof(arr), len(jobs)))
+        return [bytes(o) for o in outs]
 
     def commit_points(self, alpha, beta, bits):
         return self._run("pa_commit_points", (alpha, beta, bytes(bits)), 192 * len(bits), len(bits))

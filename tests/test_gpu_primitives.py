@@ -170,3 +170,28 @@ def test_two_contexts_and_argument_errors(pa, oracle):
     finally:
         a.close()
         b.close()
+
+
+def test_scalar_mul_jobs_match_single_calls(engine, oracle):
+    """pa_scalar_mul_jobs: four job kinds of different lengths in one interleaved pipeline (one of them longer than a
+    pipeline chunk, so that chunks of different jobs really alternate) == the single calls == the oracle on a sample."""
+    import importlib
+    E_ = importlib.import_module("privacy-auction_b200.engine")
+    rnd = random.Random(909)
+    sizes = {"fixed": 400000, "var": 3000, "double": 1500, "lincomb2": 700}
+    sc = lambda n: b"".join(rnd.getrandbits(256).to_bytes(32, "big") for _ in range(n))
+    kf = sc(sizes["fixed"])
+    pts = engine.fixed_base_mul(sc(sizes["var"]))
+    kv, ka, kb = sc(sizes["var"]), sc(sizes["double"]), sc(sizes["double"])
+    la, lb = sc(sizes["lincomb2"]), sc(sizes["lincomb2"])
+    jobs = [(E_.MUL_FIXED, dict(a=kf), sizes["fixed"]),
+            (E_.MUL_VAR, dict(p=pts, a=kv), sizes["var"]),
+            (E_.MUL_DOUBLE, dict(a=ka, p=pts[:64 * sizes["double"]], b=kb), sizes["double"]),
+            (E_.MUL_LINCOMB2, dict(p=pts[:64 * sizes["lincomb2"]], a=la, q=pts[64 * 100:64 * (100 + sizes["lincomb2"])], b=lb), sizes["lincomb2"])]
+    out = engine.scalar_mul_jobs(jobs)
+    assert out[0] == engine.fixed_base_mul(kf)
+    assert out[1] == engine.var_base_mul(pts, kv) == oracle.var_base_mul(pts, kv)
+    assert out[2] == engine.double_mul(ka, pts[:64 * sizes["double"]], kb)
+    assert out[3] == engine.lincomb2(pts[:64 * sizes["lincomb2"]], la, pts[64 * 100:64 * (100 + sizes["lincomb2"])], lb)
+    assert out[0][:64 * 500] == oracle.fixed_base_mul(kf[:32 * 500])
+    assert engine.scalar_mul_jobs([]) == []
