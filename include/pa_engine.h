@@ -99,7 +99,7 @@ uint64_t pa_ctx_reruns(pa_ctx *ctx);
  *   pa_xchg_skip     a rank that owns no bidder of a sharded auction calls this instead of pa_seal_run
  *                    (keeps the run counter the ranks share in step);
  *   pa_xchg_close    unmaps and frees (also done by pa_ctx_destroy). */
-#define PA_XCHG_BYTES ((size_t)4 << 20)
+#define PA_XCHG_BYTES ((size_t)8 << 20)
 #define PA_XCHG_MAX_WORLD 16
 int pa_xchg_create(pa_ctx *ctx, uint8_t *handle64);
 int pa_xchg_connect(pa_ctx *ctx, const uint8_t *handles, int world, int rank);

@@ -325,7 +325,7 @@ k_seal_decide_shard(int s, int m, int limit, int world, const unsigned char *bit
 //   the junction) is never mistaken for its first value.
 //   bulk area: two buffers for a plain all-gather of up to PA_XCHG_BULK bytes (the step-major schedule's X
 //   and b), tagged with a sequence number per (buffer, rank).
-#define PA_XCHG_STEPS 64
+#define PA_XCHG_STEPS 256  // real steps (<= 64) and the virtual steps of the junction planes
 #define PA_XCHG_SLOTS (3 * 2 * PA_XCHG_STEPS * PA_XCHG_MAX_WORLD)
 #define PA_XCHG_BULK_OFF ((size_t)PA_XCHG_SLOTS * 128 + 4096)
 #define PA_XCHG_BULK ((PA_XCHG_BYTES - PA_XCHG_BULK_OFF) / 2)
@@ -900,15 +900,29 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
   u64 *d_xfinal = nullptr;
   const size_t nall = job->n[0];
   const size_t T = phased ? cmax * m : 0;
+  // Junction planes (see the phase-major schedule below): the keys, Y and candidates of the steps after the junction for the
+  // guesses J = 0..3, computed beside the first pass when that is cheap (a small slice: the GPU is far from full).
+  // Plane q holds steps [q + 2, cmax) at virtual steps [vplane[q], vplane[q + 1]).
+  std::vector<size_t> vplane;
+  size_t VT = 0;  // virtual steps in total
+  if (phased && (!sharded || p2p) && cmax >= 6) {
+    size_t v = cmax;
+    vplane.push_back(v);
+    for (size_t g = 0; g < 4 && g + 2 < cmax; ++g) v += cmax - g - 2, vplane.push_back(v);
+    VT = v - cmax;
+    // the same decision on every rank: by the slice, not by this rank's share of it
+    if (VT * (sharded ? (size_t)job->slice : m) > 40000 || cmax + VT > PA_XCHG_STEPS) vplane.clear(), VT = 0;  // not cheap: no planes
+  }
+  const size_t TX = T + VT * m;  // items incl. the planes
   const size_t nY = sharded ? nall : m;
   auto carve = [&](DevPool &pool) {
     if (phased) {
-      PH.istream = pool.alloc<u64>(T); PH.ictr = pool.alloc<u64>(T); PH.pid = pool.alloc<u64>(T);
-      PH.soff = pool.alloc<u32>(cmax + 1);
+      PH.istream = pool.alloc<u64>(TX); PH.ictr = pool.alloc<u64>(TX); PH.pid = pool.alloc<u64>(T);
+      PH.soff = pool.alloc<u32>(cmax + VT + 1);
       PH.stage = pool.alloc<int>(cmax); PH.prevstep = pool.alloc<int>(cmax); PH.r3 = pool.alloc<int>(cmax); PH.state = pool.alloc<int>(4);
-      PH.rnd1 = pool.alloc<unsigned char>(T * 128); PH.r1 = pool.alloc<unsigned char>(T * 320);
+      PH.rnd1 = pool.alloc<unsigned char>(TX * 128); PH.r1 = pool.alloc<unsigned char>(TX * 320);
       PH.pokv = pool.alloc<unsigned char>(T * 2); PH.r1ok = pool.alloc<unsigned char>(T);
-      PH.Y = pool.alloc<unsigned char>(T * 64); PH.cand = pool.alloc<unsigned char>(T * 128); PH.b = pool.alloc<unsigned char>(T * 64);
+      PH.Y = pool.alloc<unsigned char>(TX * 64); PH.cand = pool.alloc<unsigned char>(TX * 128); PH.b = pool.alloc<unsigned char>(T * 64);
       PH.ebit = pool.alloc<unsigned char>(T); PH.bj = pool.alloc<unsigned char>(T);
       PH.stmt = pool.alloc<unsigned char>(T * 704 + 256); PH.sec = pool.alloc<unsigned char>(T * 192 + 256);
       PH.bi = pool.alloc<unsigned char>(T + 256); PH.bjp = pool.alloc<unsigned char>(T + 256); PH.cbp = pool.alloc<unsigned char>(T + 256);
@@ -1090,8 +1104,8 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       return base + 9ull * ((size_t)J + 1) + 15ull * (s - (size_t)J - 1);
     };
     {
-      std::vector<u32> soff(c + 1);
-      for (size_t k = 0; k <= c; ++k) soff[k] = (u32)(k * m);
+      std::vector<u32> soff(c + VT + 1);
+      for (size_t k = 0; k <= c + VT; ++k) soff[k] = (u32)(k * m);
       std::vector<u64> pid(T);
       for (size_t i = 0; i < T; ++i) pid[i] = ids[i % m];
       int st0[4] = {0, -1, 0, 0};
@@ -1099,7 +1113,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       PA_CUDA(ctx, cudaMemcpyAsync(PH.state, st0, sizeof st0, cudaMemcpyHostToDevice, ctx->stream));
       PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // st0 / vectors go out of scope
     }
-    std::vector<u64> istream(T), ictr(T), after(T);
+    std::vector<u64> istream(TX), ictr(TX), after(TX);
     // the Schnorr proofs of X and R of every item, one batch (and their verification)
     auto pok_all = [&]() -> int {
       int rc2;
@@ -1115,9 +1129,21 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     };
     bool pok_on_lane = false;
     // keys, Y and both cryptogram candidates of steps [s0, s1), then the walk through those steps
-    auto run_steps = [&](size_t s0, size_t s1, long J, int speculative) -> int {
+    // the proofs of X and R go to a side lane as soon as every key is final (they write the proof fields of the round-one
+    // records; the passes read the point fields)
+    auto start_pok = [&]() -> int {
+      int rc2;
+      PA_CUDA(ctx, cudaEventRecord(ev_r1[1], ctx->stream));
+      LaneScope ls(ctx, L_pok);
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[1], 0));
+      if ((rc2 = pok_all())) return rc2;
+      PA_CUDA(ctx, cudaEventRecord(ev_pok[0], ctx->stream));
+      pok_on_lane = true;
+      return PA_OK;
+    };
+    // keys, Y and both cryptogram candidates of the (real or virtual) steps [s0, s1); istream / ictr of these items are set
+    auto run_keys = [&](size_t s0, size_t s1, bool final_keys) -> int {
       const size_t i0 = s0 * m, cnt = (s1 - s0) * m;
-      for (size_t i = i0; i < i0 + cnt; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, J);
       PA_CUDA(ctx, cudaMemcpyAsync(PH.istream + i0, istream.data() + i0, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
       PA_CUDA(ctx, cudaMemcpyAsync(PH.ictr + i0, ictr.data() + i0, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
       PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(cnt), PA_BLOCK, 0, ctx->stream>>>(job->seed, PH.istream + i0, PH.ictr + i0, nullptr, 4, PH.rnd1 + 128 * i0, (int)cnt)));
@@ -1126,16 +1152,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
       PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.r1 + 320 * i0, 2 * cnt, 2, 320))) return rc2;
-      if (!speculative && s1 == c && !pok_on_lane) {
-        // these are the last keys: every X and R is final, so their proofs can run beside the rest of this pass
-        // (they write the proof fields of the round-one records, the pass reads the point fields)
-        PA_CUDA(ctx, cudaEventRecord(ev_r1[1], ctx->stream));
-        LaneScope ls(ctx, L_pok);
-        PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[1], 0));
-        if ((rc2 = pok_all())) return rc2;
-        PA_CUDA(ctx, cudaEventRecord(ev_pok[0], ctx->stream));
-        pok_on_lane = true;
-      }
+      if (final_keys && !pok_on_lane && (rc2 = start_pok())) return rc2;  // these are the last keys: every X and R is final
       if (!sharded) {
         if ((rc2 = work_reserve(ctx, cnt))) return rc2;
         PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(s1 - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
@@ -1162,6 +1179,11 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
       PA_LAUNCH(ctx, PA_K_VAR, (k_seal_candidates<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.Y + 64 * i0, PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.cand + 128 * i0, 2 * cnt))) return rc2;
+      return PA_OK;
+    };
+    // the walk through the steps [s0, s1) whose candidates are in place
+    auto run_walk = [&](size_t s0, size_t s1, int speculative) -> int {
+      const size_t cnt = (s1 - s0) * m;
       if (!sharded || p2p) {
         // the state-independent part of every step's sum at once, the walk over what depends on the race, and then what
         // each bidder publishes at the steps walked (see "the walk, restated")
@@ -1174,6 +1196,11 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       }
       return PA_OK;
     };
+    auto run_steps = [&](size_t s0, size_t s1, long J, int speculative) -> int {
+      for (size_t i = s0 * m; i < s1 * m; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, J);
+      int rc2 = run_keys(s0, s1, !speculative && s1 == c);
+      return rc2 ? rc2 : run_walk(s0, s1, speculative);
+    };
     int st[4];
     bool clean = true;
     long J = -1;
@@ -1182,6 +1209,52 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       // steps that doubles while no junction shows up (with random bids it is step 0 or 1; only an auction
       // of all-zero bids goes through every window); after it, one pass takes all remaining steps.
       size_t done = 0, win = 2;
+      if (VT) {
+        // Junction planes.  A small slice leaves the GPU far from full and every pass is a chain of lone-warp latencies,
+        // so the second pass is taken out of the chain: beside the first window (steps 0 .. 4 on stage-1 counters) a
+        // side lane computes keys, Y and candidates of the steps after the junction for each of the guesses J = 0 .. 3
+        // (counters: key_ctr(., guess)).  If the walk finds the junction at one of them, that plane is copied into place
+        // and only the walk is left to do; otherwise the planes are dropped and the windows go on as usual.
+        const size_t nplanes = vplane.size() - 1, w1 = nplanes + 1 < c ? nplanes + 1 : c;  // first window: steps [0, w1), valid for J <= w1 - 2
+        ++xpass;
+        for (size_t q = 0; q < nplanes; ++q)
+          for (size_t v = vplane[q]; v < vplane[q + 1]; ++v)
+            for (size_t k = 0; k < m; ++k) istream[v * m + k] = streams[k], ictr[v * m + k] = key_ctr(q + 2 + (v - vplane[q]), (long)q);
+        {
+          PA_CUDA(ctx, cudaEventRecord(ev_r1[1], ctx->stream));
+          LaneScope ls(ctx, L_pok);
+          PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[1], 0));
+          if ((rc = run_keys(c, c + VT, false))) return rc;
+          PA_CUDA(ctx, cudaEventRecord(ev_pok[1], ctx->stream));
+        }
+        if ((rc = run_steps(0, w1, -1, 1))) return rc;
+        PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[1], 0));  // the planes
+        PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (p2p && (rc = xchg_check())) return rc;
+        for (size_t i = 0; i < w1 * m; ++i) clean &= after[i] == ictr[i] + 4;
+        if (st[0]) J = st[3];
+        done = (size_t)st[2];
+        win = 8;
+        if (J >= 0 && (size_t)J < nplanes && done == (size_t)J + 2 && done < c) {
+          const size_t q = (size_t)J, src = vplane[q] * m, dst = done * m, cnt = (c - done) * m;
+          PA_CUDA(ctx, cudaMemcpyAsync(PH.rnd1 + 128 * dst, PH.rnd1 + 128 * src, 128 * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+          PA_CUDA(ctx, cudaMemcpyAsync(PH.r1 + 320 * dst, PH.r1 + 320 * src, 320 * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+          PA_CUDA(ctx, cudaMemcpyAsync(PH.Y + 64 * dst, PH.Y + 64 * src, 64 * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+          PA_CUDA(ctx, cudaMemcpyAsync(PH.cand + 128 * dst, PH.cand + 128 * src, 128 * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+          for (size_t i = 0; i < cnt; ++i) {
+            clean &= after[src + i] == ictr[src + i] + 4;
+            istream[dst + i] = istream[src + i], ictr[dst + i] = ictr[src + i], after[dst + i] = after[src + i];
+          }
+          if (!pok_on_lane && (rc = start_pok())) return rc;  // every X and R is final now
+          ++xpass;
+          if ((rc = run_walk(done, c, 0))) return rc;
+          PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+          PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+          if (p2p && (rc = xchg_check())) return rc;
+          done = (size_t)st[2];
+        }
+      }
       while (done < c) {
         const size_t s1 = J < 0 ? (done + win < c ? done + win : c) : c;
         ++xpass;

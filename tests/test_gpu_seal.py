@@ -227,6 +227,27 @@ def test_runner_reproduces_reference_transcript(engine, path, schedule):
     assert seal_flow.sections_to_transcripts(t["seed"], [t["n"]], [t["c"]], t["bids"], res)[0] == gold
 
 
+@pytest.mark.parametrize("first_one", [0, 1, 2, 3, 4, 7, None], ids=lambda v: f"J={v}")
+def test_phase_major_junction_planes_match_oracle(engine, oracle, first_one):
+    """The phase-major schedule computes, beside its first window, the steps after the junction for the guesses
+    J = 0..3 (pa_seal.cuh, "junction planes") and copies the right plane into place.  Auctions whose first deciding step
+    is 0, 1, 2, 3 (a plane is used), 4 and 7 (no plane fits: the windows go on) and never (all-zero bids) must publish the
+    oracle's bytes in both schedules."""
+    rnd = random.Random(77 + (first_one if first_one is not None else 99))
+    n, c = 9, 10
+    if first_one is None:
+        bids = [0] * n
+    else:   # the highest set bit of the maximum is bit c - 1 - first_one
+        top = c - first_one
+        bids = [rnd.randrange(1 << top) for _ in range(n)]
+        bids[rnd.randrange(n)] |= 1 << (top - 1)
+    want = seal_flow.SealFlow(oracle, n, c, 123, bids).run()
+    for schedule in (2, 1):
+        res = engine.seal_run(123, [n], [c], bids, verify=True, sections=True, schedule=schedule)
+        assert res["ok"] == [True] and res["max_bid"] == [max(bids)]
+        assert seal_flow.sections_to_transcripts(123, [n], [c], bids, res)[0] == want, schedule
+
+
 def test_runner_batch_of_ragged_auctions_matches_oracle(engine, oracle):
     """genTests-style batch (tests/genTests.py:13-17): n ~ U{1..20}, c ~ U{1..32}, in ONE lock-step run;
     every auction's transcript must equal the oracle's run of that auction alone."""
