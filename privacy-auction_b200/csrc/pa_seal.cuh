@@ -1027,19 +1027,22 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
   };
 
   // ================= commit phase ===================================================
+  std::vector<u64> sstream(Mb), sctr(Mb), cafter(Mb);  // commit-phase draw streams, counters before and after
+  std::function<int()> commit_on_lane;                  // phase-major: queued behind the first pass (below)
   {
     // 7 draws per (bidder, bit): slot k of bidder s starts at counter 7 * (k - boff[s]) of the bidder's
     // stream.  That arithmetic is exact unless a draw is rejected (probability 2^-128 per draw); if the
-    // counters show a rejection, that bidder's draws are regenerated sequentially.
-    std::vector<u64> sstream(Mb), sctr(Mb);
+    // counters show a rejection, that bidder's draws are regenerated sequentially (step-major) or the whole
+    // auction is run again step-major (phase-major, which looks at the counters at its first synchronisation).
     for (size_t s = 0; s < m; ++s)
       for (u32 k = boff[s]; k < boff[s + 1]; ++k) sstream[k] = streams[s], sctr[k] = 7ull * (k - boff[s]);
     if ((rc = up(ctx, d_sstream, sstream)) || (rc = up(ctx, d_sctr, sctr))) return rc;
     PA_LAUNCH(ctx, PA_K_RNG, (k_rng_fill<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(job->seed, d_sstream, d_sctr, nullptr, 7, d_rndc, (int)Mb)));
-    std::vector<u64> after(Mb);
+    std::vector<u64> &after = cafter;
     PA_CUDA(ctx, cudaMemcpyAsync(after.data(), d_sctr, Mb * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    {
+    if (phased) PA_CUDA(ctx, cudaEventRecord(ev_r1[0], ctx->stream));  // the commit draws are there
+    if (!phased) {
+      PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       // every bidder's stream counter after the commit phase, in ONE upload (a copy per bidder cost 1.5 ms at n = 1000);
       // bidders with a rejected draw are redone one by one afterwards
       std::vector<u64> ctr_after(m);
@@ -1079,12 +1082,18 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       PA_LAUNCH(ctx, PA_K_VERDICT, (k_seal_and_pairs<<<grid_for(Mb), PA_BLOCK, 0, ctx->stream>>>(d_cv, d_cv + 2 * Mb, d_cv + 3 * Mb, (int)Mb)));
       return PA_OK;
     };
-    if (phased) {  // on a side lane: the steps do not need the commitments until the round-two statements are assembled
-      PA_CUDA(ctx, cudaEventRecord(ev_r1[0], ctx->stream));
-      LaneScope ls(ctx, L_verify);
-      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[0], 0));
-      if ((rc = commit_work())) return rc;
-      PA_CUDA(ctx, cudaEventRecord(ev_verified[0], ctx->stream));
+    if (phased) {
+      // on a side lane: the steps do not need the commitments until the round-two statements are assembled.  Its ~20
+      // launches are QUEUED only after the first pass of the walk's chain has been (the host issues launches one at a
+      // time, and that chain is the critical path of a single auction).
+      commit_on_lane = [&, commit_work]() -> int {
+        LaneScope ls(ctx, L_verify);
+        PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[0], 0));
+        int rc2 = commit_work();
+        if (rc2) return rc2;
+        PA_CUDA(ctx, cudaEventRecord(ev_verified[0], ctx->stream));
+        return PA_OK;
+      };
     } else if ((rc = commit_work())) {
       return rc;
     }
@@ -1131,15 +1140,38 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     // keys, Y and both cryptogram candidates of steps [s0, s1), then the walk through those steps
     // the proofs of X and R go to a side lane as soon as every key is final (they write the proof fields of the round-one
     // records; the passes read the point fields)
+    // keys_final() marks the point of the main stream at which every X and R is final; start_pok() queues the proofs on
+    // their lane behind that point - called only after the rest of the pass has been queued on the main stream, which is
+    // the critical path (the host issues launches one at a time).
+    bool keys_marked = false;
+    auto keys_final = [&]() -> int {
+      PA_CUDA(ctx, cudaEventRecord(ev_r1[1], ctx->stream));
+      keys_marked = true;
+      return PA_OK;
+    };
     auto start_pok = [&]() -> int {
       int rc2;
-      PA_CUDA(ctx, cudaEventRecord(ev_r1[1], ctx->stream));
+      if (!keys_marked || pok_on_lane) return PA_OK;
       LaneScope ls(ctx, L_pok);
       PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[1], 0));
       if ((rc2 = pok_all())) return rc2;
       PA_CUDA(ctx, cudaEventRecord(ev_pok[0], ctx->stream));
       pok_on_lane = true;
       return PA_OK;
+    };
+    // the commit phase's lane and the check of its draw counters, once, behind the first pass
+    bool commit_queued = false;
+    auto queue_commit = [&]() -> int {
+      if (commit_queued) return PA_OK;
+      commit_queued = true;
+      return commit_on_lane();
+    };
+    bool commit_checked = false;
+    auto check_commit_draws = [&]() {  // after a synchronisation of the main stream
+      if (commit_checked) return;
+      commit_checked = true;
+      for (size_t k = 0; k < Mb; ++k)
+        if (cafter[k] != sctr[k] + 7) draws_clean = false;  // a rejected draw: the auction is run again step-major
     };
     // keys, Y and both cryptogram candidates of the (real or virtual) steps [s0, s1); istream / ictr of these items are set
     auto run_keys = [&](size_t s0, size_t s1, bool final_keys) -> int {
@@ -1152,7 +1184,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       if ((rc2 = work_reserve(ctx, 2 * cnt))) return rc2;
       PA_LAUNCH(ctx, PA_K_FIXED, (k_seal_r1_points<<<grid_for(2 * cnt), PA_BLOCK, 0, ctx->stream>>>(PH.rnd1 + 128 * i0, ctx->d_comb, work_jac(ctx), (int)cnt)));
       if ((rc2 = normalize_to(ctx, PH.r1 + 320 * i0, 2 * cnt, 2, 320))) return rc2;
-      if (final_keys && !pok_on_lane && (rc2 = start_pok())) return rc2;  // these are the last keys: every X and R is final
+      if (final_keys && !keys_marked && (rc2 = keys_final())) return rc2;  // these are the last keys: every X and R is final
       if (!sharded) {
         if ((rc2 = work_reserve(ctx, cnt))) return rc2;
         PA_LAUNCH(ctx, PA_K_YSCAN, (k_y_scan<<<(unsigned)(s1 - s0), PA_SCAN_T, 0, ctx->stream>>>(PH.r1 + 320 * i0, 320, PH.soff, (int)cnt, work_jac(ctx))));
@@ -1198,8 +1230,10 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     };
     auto run_steps = [&](size_t s0, size_t s1, long J, int speculative) -> int {
       for (size_t i = s0 * m; i < s1 * m; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, J);
-      int rc2 = run_keys(s0, s1, !speculative && s1 == c);
-      return rc2 ? rc2 : run_walk(s0, s1, speculative);
+      int rc2;
+      if ((rc2 = run_keys(s0, s1, !speculative && s1 == c)) || (rc2 = run_walk(s0, s1, speculative))) return rc2;
+      if ((rc2 = start_pok())) return rc2;  // bulk work, queued behind the chain
+      return queue_commit();
     };
     int st[4];
     bool clean = true;
@@ -1217,20 +1251,23 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
         // and only the walk is left to do; otherwise the planes are dropped and the windows go on as usual.
         const size_t nplanes = vplane.size() - 1, w1 = nplanes + 1 < c ? nplanes + 1 : c;  // first window: steps [0, w1), valid for J <= w1 - 2
         ++xpass;
+        // the two chains the first synchronisation waits for are queued first (planes, then the window and its walk: they
+        // are equally long and run side by side), the commit phase's bulk work behind them
         for (size_t q = 0; q < nplanes; ++q)
           for (size_t v = vplane[q]; v < vplane[q + 1]; ++v)
             for (size_t k = 0; k < m; ++k) istream[v * m + k] = streams[k], ictr[v * m + k] = key_ctr(q + 2 + (v - vplane[q]), (long)q);
         {
-          PA_CUDA(ctx, cudaEventRecord(ev_r1[1], ctx->stream));
-          LaneScope ls(ctx, L_pok);
-          PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[1], 0));
+          LaneScope ls(ctx, L_pok);  // needs nothing from the main stream
           if ((rc = run_keys(c, c + VT, false))) return rc;
           PA_CUDA(ctx, cudaEventRecord(ev_pok[1], ctx->stream));
         }
-        if ((rc = run_steps(0, w1, -1, 1))) return rc;
+        for (size_t i = 0; i < w1 * m; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, -1);
+        if ((rc = run_keys(0, w1, false)) || (rc = run_walk(0, w1, 1))) return rc;
         PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = queue_commit())) return rc;
         PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[1], 0));  // the planes
         PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        check_commit_draws();
         if (p2p && (rc = xchg_check())) return rc;
         for (size_t i = 0; i < w1 * m; ++i) clean &= after[i] == ictr[i] + 4;
         if (st[0]) J = st[3];
@@ -1246,10 +1283,11 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
             clean &= after[src + i] == ictr[src + i] + 4;
             istream[dst + i] = istream[src + i], ictr[dst + i] = ictr[src + i], after[dst + i] = after[src + i];
           }
-          if (!pok_on_lane && (rc = start_pok())) return rc;  // every X and R is final now
+          if (!keys_marked && (rc = keys_final())) return rc;  // every X and R is final now
           ++xpass;
           if ((rc = run_walk(done, c, 0))) return rc;
           PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+          if ((rc = start_pok())) return rc;
           PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
           if (p2p && (rc = xchg_check())) return rc;
           done = (size_t)st[2];
@@ -1261,6 +1299,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
         if ((rc = run_steps(done, s1, J, J < 0 ? 1 : 0))) return rc;
         PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        check_commit_draws();
         if (p2p && (rc = xchg_check())) return rc;
         for (size_t i = done * m; i < s1 * m; ++i) clean &= after[i] == ictr[i] + 4;
         if (J < 0 && st[0]) J = st[3];
@@ -1302,7 +1341,10 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     std::vector<int> stage(c), r3(c);
     PA_CUDA(ctx, cudaMemcpyAsync(stage.data(), PH.stage, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PA_CUDA(ctx, cudaMemcpyAsync(r3.data(), PH.r3, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!keys_marked && (rc = keys_final())) return rc;          // no second pass was needed: the keys are final as they are
+    if ((rc = queue_commit()) || (rc = start_pok())) return rc;  // (already queued on every path that made a pass)
     PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    check_commit_draws();
     if (J < 0)
       for (size_t s2 = 0; s2 < c; ++s2)
         if (r3[s2]) { J = (long)s2; break; }  // a junction in the last two steps never triggers the second pass
@@ -1312,8 +1354,15 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     const size_t n1 = c1 * m, n2 = T - n1;
     const size_t o_stmt = align_up(n1 * 448, 256), o_sec = align_up(n1 * 128, 256), o_b = align_up(n1, 256),
                  o_rnd = align_up(n1 * 160, 256), o_proof = align_up(n1 * 672, 256);
-    if (pok_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[0], 0));
-    else if ((rc = pok_all())) return rc;
+    // The round-one proofs (their lane) write the proof fields of the round-one records; what follows reads the point
+    // fields only, so it does not wait for them - the results do.  (Test hook: a corrupted KEY must reach the statements
+    // deterministically, so then the wait stays here.)
+    const bool pok_wait_early = ctx->corrupt.section == 2 && ctx->corrupt.offset < 128;
+    if (!pok_on_lane) {
+      if ((rc = pok_all())) return rc;
+    } else if (pok_wait_early) {
+      PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[0], 0));
+    }
     // ---- round-two proofs: statements, draws (right after the four key draws), prove, verify -----------------
     PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_enc[1], 0));  // the commitment points (side lane)
     PA_LAUNCH(ctx, PA_K_ENCODE, (k_seal_stmt_items<<<grid_for(T), PA_BLOCK, 0, ctx->stream>>>((int)m, (int)n1, PH.stage, PH.prevstep, d_boff, PH.b, PH.r1, PH.Y, PH.rnd1, d_crec, d_rndc, PH.ebit, PH.bj, d_bits, PH.stmt, PH.sec, PH.bi, PH.stmt + o_stmt, PH.sec + o_sec, PH.bi + o_b, PH.bjp + o_b, PH.cbp + o_b, (int)T)));
@@ -1348,6 +1397,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     if (s1_on_lane) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_proved[0], 0));
     // ---- results ---------------------------------------------------------------------------------------------
     PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_verified[0], 0));  // the commit phase (side lane)
+    if (pok_on_lane && !pok_wait_early) PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[0], 0));  // the round-one proofs
     if ((rc = collect_commitments())) return rc;
     std::vector<unsigned char> r1ok(T), r2ok(T);
     PA_CUDA(ctx, cudaMemcpyAsync(r1ok.data(), PH.r1ok, T, cudaMemcpyDeviceToHost, ctx->stream));
