@@ -76,7 +76,11 @@ CommitmentPub Bidder::commitBid() {
   for (size_t i = 0; i < c_; ++i) A[i] = pts[i].A, B[i] = pts[i].B;
   check(pa_pokdlog_prove(e, bytes(A), bytes(alpha), ids.data(), bytes(vA), bytes(pokA), c_), "pa_pokdlog_prove");
   check(pa_pokdlog_prove(e, bytes(B), bytes(beta), ids.data(), bytes(vB), bytes(pokB), c_), "pa_pokdlog_prove");
-  check(pa_powfcom_prove(e, bytes(pts), bytes(alpha), bits.data(), ids.data(), bytes(rnd), bytes(com), c_), "pa_powfcom_prove");
+  // the prover with witnesses: this bidder knows alpha AND beta, so every point of the OR proof is one fixed-base
+  // multiplication (include/pa_engine.h); the proof bytes are those of pa_powfcom_prove
+  std::vector<Scalar> ab(2 * c_);
+  for (size_t i = 0; i < c_; ++i) ab[2 * i] = alpha[i], ab[2 * i + 1] = beta[i];
+  check(pa_powfcom_prove_w(e, bytes(pts), bytes(ab), bits.data(), ids.data(), bytes(rnd), bytes(com), c_), "pa_powfcom_prove_w");
   for (size_t i = 0; i < c_; ++i) {
     commitments[i] = Commitment{pts[i].phi, pts[i].A, pts[i].B, alpha[i], beta[i]};
     pubs[i].phi = pts[i].phi, pubs[i].A = pts[i].A, pubs[i].B = pts[i].B;
@@ -198,18 +202,18 @@ RoundTwoPub Bidder::roundTwo(const std::vector<Point> &Xs, size_t step) {
   if (!junctionFlag) {
     pub.stage = STAGE1;
     Point stmt[7] = {b, keys[step].X, curInfo[id_].Y, keys[step].R, cm.phi, cm.A, cm.B};
-    Scalar sec[2] = {keys[step].x, cm.alpha};
+    Scalar sec[4] = {keys[step].x, cm.alpha, keys[step].r, cm.beta};  // extended secrets: prover with witnesses
     std::vector<Scalar> rnd = draw(5);
-    check(pa_stage1_prove(e, stmt[0].b, sec[0].b, &bi, &id, bytes(rnd), (uint8_t *)&pub.powf.powfstage1, 1), "pa_stage1_prove");
+    check(pa_stage1_prove_w(e, stmt[0].b, sec[0].b, &bi, &id, bytes(rnd), (uint8_t *)&pub.powf.powfstage1, 1), "pa_stage1_prove_w");
   } else {
     pub.stage = STAGE2;
     const Key &kj = keys[prevDecidingStep];
     Point stmt[11] = {b, keys[step].X, keys[step].R, prevDecidingInfo[id_].b, kj.X, kj.R, cm.phi, cm.A, cm.B,
                       curInfo[id_].Y, prevDecidingInfo[id_].Y};
-    Scalar sec[3] = {keys[step].x, kj.x, cm.alpha};
-    uint8_t bj = (uint8_t)prevDecidingBit;
+    Scalar sec[6] = {keys[step].x, kj.x, cm.alpha, keys[step].r, kj.r, cm.beta};
+    uint8_t bj = (uint8_t)prevDecidingBit, cbit = (uint8_t)(binaryBidStr[step] - '0');  // cbit: the bit committed to in Ci
     std::vector<Scalar> rnd = draw(11);
-    check(pa_stage2_prove(e, stmt[0].b, sec[0].b, &bi, &bj, &id, bytes(rnd), (uint8_t *)&pub.powf.powfstage2, 1), "pa_stage2_prove");
+    check(pa_stage2_prove_w(e, stmt[0].b, sec[0].b, &bi, &bj, &cbit, &id, bytes(rnd), (uint8_t *)&pub.powf.powfstage2, 1), "pa_stage2_prove_w");
   }
   TimeTracker::getInstance().stop(BIDDER_CATEGORY);
   return pub;
