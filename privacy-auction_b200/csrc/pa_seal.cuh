@@ -1028,7 +1028,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
 
   // ================= commit phase ===================================================
   std::vector<u64> sstream(Mb), sctr(Mb), cafter(Mb);  // commit-phase draw streams, counters before and after
-  std::function<int()> commit_on_lane;                  // phase-major: queued behind the first pass (below)
+  std::function<int()> commit_on_lane;
   {
     // 7 draws per (bidder, bit): slot k of bidder s starts at counter 7 * (k - boff[s]) of the bidder's
     // stream.  That arithmetic is exact unless a draw is rejected (probability 2^-128 per draw); if the
@@ -1083,9 +1083,10 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       return PA_OK;
     };
     if (phased) {
-      // on a side lane: the steps do not need the commitments until the round-two statements are assembled.  Its ~20
-      // launches are QUEUED only after the first pass of the walk's chain has been (the host issues launches one at a
-      // time, and that chain is the critical path of a single auction).
+      // on a side lane: the steps do not need the commitments until the round-two statements are assembled.  It is queued
+      // at once, without waiting for the check of its draw counters (the phase-major schedule looks at them at its first
+      // synchronisation): measured on 8 GPUs, this bulk work must START first - it then runs beside the passes, while the
+      // GPU is nearly idle, instead of beside the stage-2 group (queued behind the first pass: 7.5 -> 8.0 ms).
       commit_on_lane = [&, commit_work]() -> int {
         LaneScope ls(ctx, L_verify);
         PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_r1[0], 0));
@@ -1094,6 +1095,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
         PA_CUDA(ctx, cudaEventRecord(ev_verified[0], ctx->stream));
         return PA_OK;
       };
+      if ((rc = commit_on_lane())) return rc;
     } else if ((rc = commit_work())) {
       return rc;
     }
@@ -1159,13 +1161,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       pok_on_lane = true;
       return PA_OK;
     };
-    // the commit phase's lane and the check of its draw counters, once, behind the first pass
-    bool commit_queued = false;
-    auto queue_commit = [&]() -> int {
-      if (commit_queued) return PA_OK;
-      commit_queued = true;
-      return commit_on_lane();
-    };
+    // the check of the commit phase's draw counters, at the first synchronisation
     bool commit_checked = false;
     auto check_commit_draws = [&]() {  // after a synchronisation of the main stream
       if (commit_checked) return;
@@ -1232,8 +1228,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
       for (size_t i = s0 * m; i < s1 * m; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, J);
       int rc2;
       if ((rc2 = run_keys(s0, s1, !speculative && s1 == c)) || (rc2 = run_walk(s0, s1, speculative))) return rc2;
-      if ((rc2 = start_pok())) return rc2;  // bulk work, queued behind the chain
-      return queue_commit();
+      return start_pok();  // bulk work, queued behind the chain
     };
     int st[4];
     bool clean = true;
@@ -1251,8 +1246,8 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
         // and only the walk is left to do; otherwise the planes are dropped and the windows go on as usual.
         const size_t nplanes = vplane.size() - 1, w1 = nplanes + 1 < c ? nplanes + 1 : c;  // first window: steps [0, w1), valid for J <= w1 - 2
         ++xpass;
-        // the two chains the first synchronisation waits for are queued first (planes, then the window and its walk: they
-        // are equally long and run side by side), the commit phase's bulk work behind them
+        // the two chains the first synchronisation waits for: planes, then the window and its walk (they are equally long
+        // and run side by side)
         for (size_t q = 0; q < nplanes; ++q)
           for (size_t v = vplane[q]; v < vplane[q + 1]; ++v)
             for (size_t k = 0; k < m; ++k) istream[v * m + k] = streams[k], ictr[v * m + k] = key_ctr(q + 2 + (v - vplane[q]), (long)q);
@@ -1264,7 +1259,6 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
         for (size_t i = 0; i < w1 * m; ++i) istream[i] = streams[i % m], ictr[i] = key_ctr(i / m, -1);
         if ((rc = run_keys(0, w1, false)) || (rc = run_walk(0, w1, 1))) return rc;
         PA_CUDA(ctx, cudaMemcpyAsync(st, PH.state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
-        if ((rc = queue_commit())) return rc;
         PA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_pok[1], 0));  // the planes
         PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         check_commit_draws();
@@ -1342,7 +1336,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
     PA_CUDA(ctx, cudaMemcpyAsync(stage.data(), PH.stage, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PA_CUDA(ctx, cudaMemcpyAsync(r3.data(), PH.r3, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (!keys_marked && (rc = keys_final())) return rc;          // no second pass was needed: the keys are final as they are
-    if ((rc = queue_commit()) || (rc = start_pok())) return rc;  // (already queued on every path that made a pass)
+    if ((rc = start_pok())) return rc;  // (already queued on every path that made a second pass)
     PA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     check_commit_draws();
     if (J < 0)
