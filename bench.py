@@ -364,7 +364,9 @@ def seal_figures(eng, pa, rank, world, dist, torch, config5_auctions=4096, trans
     n4, c4, seed4, bids = G4["n"], G4["c"], G4["seed"], G4["bids"]
     sync = lambda: (dist.barrier() if dist else None, torch.cuda.synchronize(), eng.sync())
     if world > 1 and transport != "nccl":
-        D.connect_peer_windows(eng)
+        if not D.connect_peer_windows(eng):   # no peer access on this box: all ranks fall back together
+            assert transport == "auto", "--transport xchg: the peer exchange windows could not be mapped on this box"
+            transport = "nccl"
 
     def run4(sections=False):
         if world == 1:

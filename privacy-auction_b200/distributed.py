@@ -16,15 +16,38 @@ import torch.distributed as dist
 def connect_peer_windows(engine):
     """Create this rank's peer exchange window and map everybody else's (CUDA IPC over NVLink): after this the
     kernels of a sharded auction exchange their per-step sums by writing into each other's HBM.  The 64-byte
-    handles travel through torch.distributed once; nothing else does afterwards."""
-    if engine.xchg_world:
-        return
-    rank, world = dist.get_rank(), dist.get_world_size()
-    mine = engine.xchg_create()
+    handles travel through torch.distributed once; nothing else does afterwards.
+    Returns True when EVERY rank has mapped every window; if any rank could not (no peer access between two GPUs,
+    IPC refused in a container), all ranks close their windows and return False together, and seal_run_sharded's
+    transport "auto" then uses the NCCL call-backs."""
+    world = dist.get_world_size()
+    if engine.xchg_world == world:
+        return True
+    rank = dist.get_rank()
+    ok = 1
+    try:
+        mine = engine.xchg_create()
+    except Exception:
+        mine, ok = b"", 0
     handles = [None] * world
     dist.all_gather_object(handles, mine)
-    engine.xchg_connect(handles, rank)
-    dist.barrier()
+    if ok and all(len(h) == 64 for h in handles):
+        try:
+            engine.xchg_connect(handles, rank)
+        except Exception:
+            ok = 0
+    else:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        try:
+            engine.xchg_close()
+        except Exception:
+            pass
+        engine.xchg_world = 0
+        return False
+    return True
 
 
 def seal_run_sharded(engine, seed, n, c, bids_all, verify=True, sections=False, transport="auto", schedule=0):

@@ -231,6 +231,11 @@ class Engine:
     def xchg_skip(self):
         self._check(self.lib.pa_xchg_skip(self.ctx))
 
+    def xchg_close(self):
+        """pa_xchg_close: unmap the peers' windows and free this rank's."""
+        self._check(self.lib.pa_xchg_close(self.ctx))
+        self.xchg_world = 0
+
     def close(self):
         if self.ctx:
             self.lib.pa_ctx_destroy(self.ctx)
