@@ -162,3 +162,36 @@ def test_glv_halves_stay_below_2_128(hc):
         s1, s2 = (-k1 if out.raw[40] else k1), (-k2 if out.raw[41] else k2)
         assert (s1 + s2 * LAM - k) % N == 0
     assert worst < 1 << 128
+
+
+def test_challenge_hash_and_draw_stream_all_alignments(hc):
+    """pa_sha256.cuh streams a message through a 64-bit shift register, whole words for the coordinates of a point, single
+    bytes for the 04 / 00 prefixes and the id: every number of points (every alignment of the block boundaries), with
+    points at infinity (one byte instead of 65) at every position of a short message and at random positions of long ones,
+    against hashlib; and the PA draw stream against its definition."""
+    rnd = random.Random(4242)
+    pts = [E.mul(rnd.randrange(1, N), E.G) for _ in range(8)]
+
+    def chal(points, ident):
+        buf = b"".join(E.enc64(p) for p in points)
+        out = ctypes.create_string_buffer(32)
+        hc.hc_challenge(buf, len(points), ctypes.c_ulonglong(ident), out)
+        return int.from_bytes(out.raw, "big")
+
+    for k in range(0, 29):
+        ps = [rnd.choice(pts) for _ in range(k)]
+        ident = rnd.getrandbits(64)
+        assert chal(ps, ident) == E.challenge(ps, ident), k
+        for _ in range(3):   # some of them at infinity
+            qs = [E.INF if rnd.random() < 0.3 else p for p in ps]
+            assert chal(qs, ident) == E.challenge(qs, ident), k
+    for k in range(1, 6):      # infinity at every position
+        for pos in range(k):
+            qs = [E.INF if i == pos else pts[i] for i in range(k)]
+            assert chal(qs, 7) == E.challenge(qs, 7)
+    assert chal([E.INF] * 27, 1) == E.challenge([E.INF] * 27, 1)
+    out = ctypes.create_string_buffer(32)
+    for seed, stream, ctr in [(0, 0, 0), (42, 5, 7), (2**64 - 1, 2**64 - 1, 2**64 - 1), (1, (3 << 32) | 9, 123456789)]:
+        hc.hc_stream_draw(ctypes.c_ulonglong(seed), ctypes.c_ulonglong(stream), ctypes.c_ulonglong(ctr), out)
+        assert int.from_bytes(out.raw, "big") == E.pa_draw(seed, stream, ctr)
+
