@@ -9,15 +9,23 @@ fixed-base kernel.  One step = one pass over that batch.
 
   value      : scalar mults / s, inputs resident in HBM, CUDA-event timed on the
                engine's stream, max over ranks, aggregate over all GPUs (weak scaling)
-  e2e        : the same batch through the host-buffer C-ABI calls
-               (pa_fixed_base_mul / pa_var_base_mul) from pinned host memory,
-               H2D and D2H copies inside the timed region
-  roofline   : integer-pipe (IMAD) roofline of the dominant kernel k_var_base,
-               algorithmic work from SURVEY.md §8(d) (2,900 field mults x 272
-               IMAD units per variable-base mult), duration from CUDA events
-               bracketing the kernel inside the timed region
+  e2e        : the same batch through the host-buffer C ABI from pinned host memory, H2D and D2H
+               copies inside the timed region, timed over --steps: one pa_scalar_mul_jobs call per
+               step (both batches in one interleaved copy/compute pipeline); the same work as two
+               calls (pa_fixed_base_mul, pa_var_base_mul) is reported beside it
+  roofline   : the dominant kernel k_var_base against the integer multiplier pipe: IMAD.WIDE
+               executed per launch (profiles/kernel_work.json, counted by ncu on the shipped
+               kernel) / launch time from CUDA events inside the timed region, over the larger of
+               the measured carry-chained IMAD.WIDE loop and the pipe's 4-cycle ceiling; the
+               SURVEY.md section 8(d) nominal figure beside it
   cpu_baseline / --impl reference : OpenSSL libcrypto EC_POINT_mul in the
                reference's call shapes (oracle/_ref/ecmul_ref) on the host cores
+  cpu_auction_baselines (N = 1) : the unmodified reference's SEAL 10 20 and CCS22 20 32 run whole on
+               every host core, Tier-B samples of configs 4 and 5
+  seal       : BASELINE's auction figures - ONE SEAL auction of 1000 bidders x 32 bits sharded by
+               bidder over the ranks and checked against the oracle's digests on every rank
+               (matches_golden, also under e2e and config.also_measured), genTests-style and CCS22
+               batches, verifies/s per proof kind
 """
 import argparse
 import importlib
