@@ -782,6 +782,10 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
 // auction is simply run again step-major, where every counter is carried sequentially.
 extern "C" int pa_seal_run(pa_ctx *ctx, const pa_seal_job *job) {
   PA_ENTER(ctx);
+  // ONE exchange epoch per call, whether or not the auction is run twice: a rank that owns no bidder calls pa_xchg_skip once
+  // per auction and must stay in step with the others.  (The second, step-major run uses other slots and tags than the first:
+  // bulk all-gathers, which the phase-major schedule does not use, and the end-of-run tag 254 instead of 255.)
+  if (job && job->use_xchg) ctx->xchg.epoch++;
   bool rerun = false;
   int rc = seal_run_impl(ctx, job, &rerun);
   if (rc == PA_OK && rerun) {
@@ -811,8 +815,7 @@ static int seal_run_impl(pa_ctx *ctx, const pa_seal_job *job, bool *rerun_step_m
   PA_ARGCHECK(ctx, !p2p || (ctx->xchg.world >= xworld && ctx->xchg.rank == xrank && job->lo == (uint32_t)xrank * job->slice &&
                             (size_t)job->slice * 64 * xworld <= PA_XCHG_BULK));
   u32 xpass = 0, xseq = 0;  // passes / plain all-gathers of this run
-  if (p2p) ctx->xchg.epoch++;
-  const u32 xepoch = ctx->xchg.epoch;
+  const u32 xepoch = ctx->xchg.epoch;  // advanced by pa_seal_run / pa_xchg_skip
   const int xpar = (int)(xepoch & 1u);
   unsigned char *const *xpeers = ctx->xchg.d_peers;
   int *xerr = ctx->xchg.d_err;
