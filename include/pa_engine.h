@@ -107,7 +107,10 @@ int pa_xchg_skip(pa_ctx *ctx);
 int pa_xchg_close(pa_ctx *ctx);
 
 /* device memory helpers for the _dev entry points (cudaMalloc / cudaMemcpyAsync
- * on the context's stream) so that a host program needs no CUDA headers */
+ * on the context's stream) so that a host program needs no CUDA headers.  Every device pointer
+ * handed to a _dev entry point must be 16-byte aligned (what pa_dev_alloc returns is; record strides are
+ * multiples of 32): points and scalars are moved with 16-byte loads and stores.  PA_EINVAL otherwise where
+ * the entry point can tell. */
 int pa_dev_alloc(pa_ctx *ctx, void **dptr, size_t bytes);
 int pa_dev_free(pa_ctx *ctx, void *dptr);
 int pa_dev_upload(pa_ctx *ctx, void *dptr, const void *host, size_t bytes);

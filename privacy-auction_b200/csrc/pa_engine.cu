@@ -1020,6 +1020,7 @@ int pa_point_sum_is_inf_dev(pa_ctx *ctx, const uint8_t *B, const uint32_t *offse
 int pa_challenge_dev(pa_ctx *ctx, const uint8_t *points, size_t k, const uint64_t *ids, uint8_t *out, size_t n) {
   PA_ENTER(ctx);
   PA_ARGCHECK(ctx, ctx && k <= 32 && (n == 0 || (ids && out && (points || k == 0))));
+  PA_ARGCHECK(ctx, aligned16(points) && aligned16(out));  // wire points and scalars are moved with 16-byte loads and stores
   if (n == 0) return PA_OK;
   PA_LAUNCH(ctx, PA_K_CHALLENGE, (k_challenge<<<grid_for(n), PA_BLOCK, 0, ctx->stream>>>(points, (int)k, (const u64 *)ids, out, (int)n)));
   return PA_OK;
